@@ -1,0 +1,108 @@
+"""ctypes binding of liblbgpu.so (include/lbgpu.h).  Fails loudly when the library or a CUDA
+device is missing: there is no CPU path behind this module."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+Q = 19
+
+
+class LbGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("lbgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class LbGpuParams(C.Structure):
+    _fields_ = [("size", C.c_int32 * 3), ("boundary", C.c_int32 * 6), ("lbF", C.c_double * 3),
+                ("initDynVisc", C.c_double), ("plasticVisc", C.c_double), ("yieldStress", C.c_double),
+                ("turbConst", C.c_double), ("slipCoefficient", C.c_double),
+                ("freeSurface", C.c_int32), ("forceField", C.c_int32), ("nonNewtonian", C.c_int32),
+                ("turbulence", C.c_int32),
+                ("unitLength", C.c_double), ("unitTime", C.c_double), ("unitDensity", C.c_double),
+                ("nWalls", C.c_int32), ("device", C.c_int32),
+                ("slabAxis", C.c_int32), ("nSlabs", C.c_int32), ("slabIndex", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+# every symbol include/lbgpu.h declares
+EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuInit", "lbGpuStep", "lbGpuRun",
+           "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
+           "lbGpuLaunchCount", "lbGpuFinalize")
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen liblbgpu.so (building it with nvcc if absent) and declare the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    if not os.path.exists(path):
+        raise FileNotFoundError(path + " is missing: run `python -m hybird_b200.build`")
+    L = C.CDLL(path)
+    vp = C.c_void_p
+    L.lbGpuLastError.restype = C.c_char_p
+    L.lbGpuAbiVersion.restype = C.c_int
+    L.lbGpuDeviceCount.restype = C.c_int
+    L.lbGpuInit.restype = C.c_int
+    L.lbGpuInit.argtypes = [C.POINTER(LbGpuParams), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.lbGpuStep.restype = C.c_int
+    L.lbGpuStep.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
+    L.lbGpuRun.restype = C.c_int
+    L.lbGpuRun.argtypes = [vp, C.c_int, C.c_uint32]
+    L.lbGpuParticleForces.restype = C.c_int
+    L.lbGpuParticleForces.argtypes = [vp, vp, vp, vp, vp]
+    L.lbGpuFetchFields.restype = C.c_int
+    L.lbGpuFetchFields.argtypes = [vp] * 10
+    L.lbGpuCounts.restype = C.c_int
+    L.lbGpuCounts.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
+    L.lbGpuSynchronize.restype = C.c_int
+    L.lbGpuSynchronize.argtypes = [vp]
+    L.lbGpuLastStepMs.restype = C.c_int
+    L.lbGpuLastStepMs.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lbGpuLaunchCount.restype = C.c_int
+    L.lbGpuLaunchCount.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.lbGpuFinalize.restype = C.c_int
+    L.lbGpuFinalize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise LbGpuError(rc, load_library().lbGpuLastError().decode())
+
+
+def ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(p: dict, device=-1) -> LbGpuParams:
+    P = LbGpuParams()
+    P.size[:] = [int(v) for v in p["size"]]
+    P.boundary[:] = [int(v) for v in p["boundary"]]
+    P.lbF[:] = [float(v) for v in p["lbF"]]
+    for k in ("initDynVisc", "plasticVisc", "yieldStress", "turbConst", "slipCoefficient", "unitLength", "unitTime",
+              "unitDensity"):
+        setattr(P, k, float(p[k]))
+    for k in ("freeSurface", "forceField", "nonNewtonian", "turbulence"):
+        setattr(P, k, int(p[k]))
+    P.nWalls = int(p.get("nWalls", 0))
+    P.device = int(device)
+    P.slabAxis = 0
+    P.nSlabs = 1
+    P.slabIndex = 0
+    return P

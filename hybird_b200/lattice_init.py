@@ -1,0 +1,279 @@
+"""Host-side lattice initialisation: the state LB::latticeBolzmannInit hands to the first step.
+
+The drop-in shim (hybird_b200/shim/LB_gpu.cpp) lets the reference's own host code build this
+state and uploads it; this module builds the same state without the reference for the benchmark,
+the smoke test and the GPU tests: types, particle flags, wall nodes, hydrostatic density, initial
+velocity, masses.  It restates LB.cpp:324-996 (initializeTypes, initializeLists,
+initializeVariables, initializeWalls) and DEM::initializeWalls (DEM.cpp:435-640) for box domains
+whose boundaries are the six lattice planes (problemName NONE / demChute); cylinders, objects and
+the other hard-coded problem geometries are out of scope.  numpy only - no device code here;
+populations are left to lbGpuInit (f=NULL => equilibrium of (n,u), as node::initialize does).
+
+All arrays are in the reference's cell order i = x + X*(y + Y*z).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# D3Q19 velocity set, lattice.h:36-60
+CX = np.array([0, 1, -1, 0, 0, 0, 0, 1, -1, -1, 1, 0, 0, 0, 0, 1, -1, 1, -1])
+CY = np.array([0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1, -1, 1, 0, 0, 0, 0])
+CZ = np.array([0, 0, 0, 0, 0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, -1, 1])
+
+FLUID, GAS, INTERFACE, PERIODIC, SLIP_STAT, SLIP_DYN, STAT_WALL, DYN_WALL, CURVED = 0, 2, 3, 4, 5, 6, 7, 8, 9
+P_BIT, NODE_BIT = 0x10, 0x20
+
+PARTICLE_DTYPE = np.dtype([("x0", "<f8", 3), ("r", "<f8"), ("radiusVec", "<f8", 3), ("clusterIndex", "<u4"),
+                           ("particleIndex", "<u4")], align=True)
+ELEMENT_DTYPE = np.dtype([("x1", "<f8", 3), ("wGlobal", "<f8", 3), ("compBegin", "<u4"), ("compEnd", "<u4")],
+                         align=True)
+
+
+@dataclass
+class Wall:
+    """DEM wall created from a lattice boundary (DEM.cpp:435-640)."""
+    index: int
+    axis: int
+    side: int  # 0 = low plane, 1 = high plane
+    moving: bool
+    slip: bool
+    vel: tuple = (0.0, 0.0, 0.0)  # physical units
+
+
+@dataclass
+class LatticeState:
+    params: dict
+    type_flags: np.ndarray
+    solidIndex: np.ndarray
+    n: np.ndarray
+    u: np.ndarray
+    mass: np.ndarray
+    visc: np.ndarray
+    walls: list = field(default_factory=list)
+    parts: np.ndarray = None
+    elmts: np.ndarray = None
+    comps: np.ndarray = None
+
+
+def params_from_case(case: dict) -> dict:
+    """LB::latticeBoltzmannGet (LB.cpp:85-188): units, sizes, scaled viscosities and force."""
+    L = float(case.get("unitLength", 1.0)); T = float(case.get("unitTime", 1.0)); D = float(case.get("unitDensity", 1.0))
+    size = [int(math.floor(float(case["lbSize" + a]) / L + 0.5)) for a in "XYZ"]
+    # measureUnits::setComposite (node.cpp:476-488)
+    accel = L / T / T
+    dynVisc = D * L * L / T
+    stress = D * L * L / T / T
+    speed = L / T
+    lbF = [float(case.get("lbF" + a, 0.0)) for a in "XYZ"]
+    if case.get("problemName") == "demChute":  # LB.cpp:163-171
+        inc = float(case.get("chuteInclination", 0.0))
+        g = 9.086
+        lbF = [-1.0 * g * math.sin(inc * (math.pi / 180)), -1.0 * 0.0, -1.0 * g * math.cos(inc * (math.pi / 180))]
+    return dict(
+        size=size, boundary=[int(case["boundary%d" % k]) for k in range(6)],
+        lbF=[v / accel for v in lbF],
+        initVelocity=[float(case.get("initVelocity" + a, 0.0)) / speed for a in "XYZ"],
+        initDynVisc=float(case["initVisc"]) / dynVisc, plasticVisc=float(case["plasticVisc"]) / dynVisc,
+        yieldStress=float(case["yieldStress"]) / stress, turbConst=float(case.get("turbConst", 0.0)),
+        slipCoefficient=float(case.get("slipCoefficient", 0.0)),
+        freeSurface=int(case.get("freeSurfaceSolve", 0)), forceField=int(case.get("forceFieldSolve", 0)),
+        nonNewtonian=int(case.get("nonNewtonianSolve", 0)), turbulence=int(case.get("turbulenceSolve", 0)),
+        unitLength=L, unitTime=T, unitDensity=D)
+
+
+def make_walls(params: dict, wall_vel=()) -> list:
+    """DEM::initializeWalls (DEM.cpp:435-640): one wall per boundary of type 5..8, indexed in order."""
+    walls = []
+    for k in range(6):
+        b = params["boundary"][k]
+        if b in (5, 6, 7, 8):
+            walls.append(Wall(index=len(walls), axis=k // 2, side=k % 2, moving=b in (6, 8), slip=b in (5, 6)))
+    for w in wall_vel:
+        walls[int(w[0])].vel = (float(w[1]), float(w[2]), float(w[3]))
+    return walls
+
+
+def coords(size):
+    X, Y, Z = size
+    i = np.arange(X * Y * Z, dtype=np.int64)
+    return i % X, (i // X) % Y, i // (X * Y)
+
+
+class Neighbors:
+    """neighbors[i].d[j] as LB::initializeLatticeBoundaries builds it (LB.cpp:377-472): shell cells point to
+    themselves, interior cells get i+ne[j] with a per-axis wrap when that side is periodic; d[0] of interior
+    cells is never assigned and stays 0.  One direction is materialised at a time (large domains)."""
+
+    def __init__(self, size, boundary):
+        self.size = size
+        self.boundary = boundary
+        X, Y, Z = size
+        self.x, self.y, self.z = coords(size)
+        self.shell = (self.x == 0) | (self.x == X - 1) | (self.y == 0) | (self.y == Y - 1) | (self.z == 0) | (self.z == Z - 1)
+        self.idx = np.arange(X * Y * Z, dtype=np.int64)
+
+    def __getitem__(self, j):
+        X, Y, Z = self.size
+        b = self.boundary
+        if j == 0:
+            return np.where(self.shell, self.idx, 0)
+        xs, ys, zs = self.x + CX[j], self.y + CY[j], self.z + CZ[j]
+        if CX[j]:
+            if b[1] == PERIODIC: xs = np.where(xs == X - 1, 1, xs)
+            if b[0] == PERIODIC: xs = np.where(xs == 0, X - 2, xs)
+        if CY[j]:
+            if b[3] == PERIODIC: ys = np.where(ys == Y - 1, 1, ys)
+            if b[2] == PERIODIC: ys = np.where(ys == 0, Y - 2, ys)
+        if CZ[j]:
+            if b[5] == PERIODIC: zs = np.where(zs == Z - 1, 1, zs)
+            if b[4] == PERIODIC: zs = np.where(zs == 0, Z - 2, zs)
+        return np.where(self.shell, self.idx, xs + X * (ys + Y * zs))
+
+
+def neighbor_table(size, boundary):
+    nb = Neighbors(size, boundary)
+    return np.stack([nb[j] for j in range(19)])
+
+
+def expand_elements(elements, unit_length=1.0):
+    """Particles/elements for single-sphere elements (elmt::generateParticles, elmt.cpp:122-137)."""
+    nE = len(elements)
+    parts = np.zeros(nE, PARTICLE_DTYPE)
+    elmts = np.zeros(nE, ELEMENT_DTYPE)
+    for e, el in enumerate(elements):
+        if int(el.get("size", 1)) != 1:
+            raise ValueError("expand_elements handles single-sphere elements; clusters come from a DEM trace")
+        parts[e]["x0"] = el["x0"]; parts[e]["r"] = el["radius"]; parts[e]["clusterIndex"] = e; parts[e]["particleIndex"] = e
+        elmts[e]["x1"] = el["x1"]; elmts[e]["wGlobal"] = el["w"]; elmts[e]["compBegin"] = e; elmts[e]["compEnd"] = e + 1
+    return parts, elmts, np.arange(nE, dtype=np.uint32)
+
+
+def advance_kinematic(parts, elmts, x0_elmt, dt):
+    """Prescribed rigid motion used by tests/bench: x0 += x1*dt; single-sphere elements."""
+    x0_elmt += elmts["x1"] * dt
+    parts["x0"] = x0_elmt[parts["clusterIndex"]] + parts["radiusVec"]
+    return parts
+
+
+def build_state(case: dict, parts=None) -> LatticeState:
+    """LB::latticeBolzmannInit (LB.cpp:190-219) for a box case (see oracle/cases.py for the keys)."""
+    prm = params_from_case(case)
+    X, Y, Z = prm["size"]
+    N = X * Y * Z
+    bnd = prm["boundary"]
+    for b in bnd:
+        if b not in (4, 5, 6, 7, 8):
+            raise ValueError("boundary type %d not supported" % b)
+    L = prm["unitLength"]
+    speed = L / prm["unitTime"]
+    x, y, z = coords(prm["size"])
+    t = np.zeros(N, dtype=np.uint8)  # initializeNodes: all fluid
+
+    def is_wall(a):
+        return (a >= 5) & (a <= 9)
+    # initializeLatticeBoundaries (LB.cpp:394-432): per axis `if lo ... else if hi`, solid wins in corners
+    for axis, c, n_ in ((0, x, X), (1, y, Y), (2, z, Z)):
+        lo = (c == 0) & ~is_wall(t)
+        t[lo] = bnd[2 * axis]
+        hi = (c == n_ - 1) & ~is_wall(t)  # `else if`: a cell is never on both planes of one axis
+        t[hi] = bnd[2 * axis + 1]
+    nb = Neighbors(prm["size"], bnd)
+
+    # initializeParticleBoundaries (LB.cpp:475-495): active cells, highest particle index wins
+    pflag = np.zeros(N, dtype=bool)
+    solid = np.zeros(N, dtype=np.uint32)
+    if parts is not None and len(parts):
+        active = (t == FLUID) | (t == INTERFACE)
+        for k in range(len(parts)):
+            c0 = parts[k]["x0"] / L
+            r = parts[k]["r"] / L
+            # bounding box first, exact test (tVect::insideSphere, vector.cpp:153-158) inside it
+            box = (np.abs(x - c0[0]) <= r + 1) & (np.abs(y - c0[1]) <= r + 1) & (np.abs(z - c0[2]) <= r + 1) & active
+            ids = np.nonzero(box)[0]
+            dx, dy, dz = x[ids] - c0[0], y[ids] - c0[1], z[ids] - c0[2]
+            ins = (dx * dx + dy * dy + dz * dz) < r * r
+            pflag[ids[ins]] = True
+            solid[ids[ins]] = parts[k]["particleIndex"]
+
+    # initializeWallBoundaries (LB.cpp:497-533): DEM walls in index order; later walls override
+    walls = make_walls(prm, case.get("wall_vel", ()))
+    for w in walls:
+        c, n_ = ((x, X), (y, Y), (z, Z))[w.axis]
+        if w.side == 0:
+            p = 0.5 * L / L
+            sel = (1.0 * (c - p)) < 0.0
+        else:
+            p = (float(n_) - 1.5) * L / L
+            sel = (-1.0 * (c - p)) < 0.0
+        solid[sel] = w.index
+        t[sel] = (SLIP_DYN if w.moving else SLIP_STAT) if w.slip else (DYN_WALL if w.moving else STAT_WALL)
+
+    # initializeInterface (LB.cpp:605-815): gas region, then the two closure loops
+    gas = np.zeros(N, dtype=bool)
+    if case.get("problemName") == "demChute":  # LB.cpp:612-627
+        gas |= ((z - (0.025 / L + 0.5)) * 1.0) > 0.0
+    if "fluid_box" in case:
+        b = case["fluid_box"]
+        gas |= ~((x >= b[0]) & (x <= b[1]) & (y >= b[2]) & (y <= b[3]) & (z >= b[4]) & (z <= b[5]))
+    if "gas_box" in case:
+        b = case["gas_box"]
+        gas |= (x >= b[0]) & (x <= b[1]) & (y >= b[2]) & (y <= b[3]) & (z >= b[4]) & (z <= b[5])
+    for key, inside_is_gas in (("gas_sphere", True), ("fluid_sphere", False)):
+        if key in case:
+            s = case[key]
+            d2 = (x - s[0]) * (x - s[0]) + (y - s[1]) * (y - s[1]) + (z - s[2]) * (z - s[2])
+            ins = d2 < s[3] * s[3]
+            gas |= ins if inside_is_gas else ~ins
+    t[(t == FLUID) & gas] = GAS
+    if (t == GAS).any():
+        fluid = t == FLUID
+        near_gas = np.zeros(N, dtype=bool)
+        for j in range(1, 19):
+            near_gas |= t[nb[j]] == GAS
+        t[fluid & near_gas] = INTERFACE
+        near_fluid = np.zeros(N, dtype=bool)
+        for j in range(1, 19):
+            near_fluid |= t[nb[j]] == FLUID
+        t[(t == INTERFACE) & ~near_fluid] = GAS
+
+    # initializeVariables (LB.cpp:909-944): hydrostatic density below the highest active cell
+    active = (t == FLUID) | (t == INTERFACE)
+    lbF = prm["lbF"]
+    n = np.zeros(N); u = np.zeros((N, 3)); mass = np.zeros(N); visc = np.zeros(N)
+    if active.any():
+        maxP = (float(x[active].max()), float(y[active].max()), float(z[active].max()))
+    else:
+        maxP = (0.0, 0.0, 0.0)
+    dot = ((x - maxP[0]) * lbF[0] + (y - maxP[1]) * lbF[1]) + (z - maxP[2]) * lbF[2]
+    dens = 1.0 + 3.0 * 1.0 * 1.0 * 1.0 * dot
+    fl = t == FLUID
+    itf = t == INTERFACE
+    n[fl] = dens[fl]; mass[fl] = 1.0
+    n[itf] = 1.0; mass[itf] = 0.5 * 1.0
+    visc[active] = prm["initDynVisc"]
+    for k in range(3):  # node::initialize: u = lbmDt*F/2/n + velocity
+        u[active, k] = lbF[k] * 1.0 / 2.0 / n[active] + prm["initVelocity"][k]
+    node = active.copy()
+
+    # initializeWalls (LB.cpp:946-996): a node for every wall cell linked (j=0..18) from a non-wall cell
+    nonwall = ~is_wall(t)
+    linked = np.zeros(N, dtype=bool)
+    for j in range(19):
+        linked[nb[j][nonwall]] = True
+    wall_node = linked & is_wall(t)
+    n[wall_node] = 1.0
+    wvel = np.zeros((len(walls), 3))
+    for w in walls:
+        if w.moving:  # wall::getSpeed with omega = 0 (utils.cpp:38-50)
+            wvel[w.index] = [w.vel[0] / speed, w.vel[1] / speed, w.vel[2] / speed]
+    dyn = wall_node & ((t == DYN_WALL) | (t == SLIP_DYN))
+    if dyn.any():
+        u[dyn] = wvel[solid[dyn]]
+    node |= wall_node
+
+    tf = (t | (pflag.astype(np.uint8) * P_BIT) | (node.astype(np.uint8) * NODE_BIT)).astype(np.uint8)
+    prm["nWalls"] = len(walls)
+    return LatticeState(params=prm, type_flags=tf, solidIndex=solid, n=n, u=u, mass=mass, visc=visc, walls=walls)

@@ -1,0 +1,143 @@
+"""Host mirror of the reference's `LB` class (LB.h:32-215) on top of the C ABI.
+
+Same method names, argument meaning and call order as the reference so that a driver written
+against hybird's goCycle (hybird.cpp:35-66) reads the same:
+
+    lb = LB(params); lb.latticeBolzmannInit(state)
+    each cycle:  lb.latticeBoltzmannFreeSurfaceStep()            # if freeSurface
+                 lb.latticeBoltzmannCouplingStep(newNeighborList, elmts, particles, components)
+                 F, M, V, wallF = lb.latticeBolzmannStep(elmts, particles)
+
+The free-surface and coupling calls only record the request; the device work of one cycle is
+issued by latticeBolzmannStep through a single lbGpuStep call, in the reference's order.
+Errors follow the reference's convention for this path (ASSERT -> message + exit(1), macros.h:8)
+translated to Python: LbGpuError carrying the library's message.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class LB:
+    def __init__(self, params: dict, device: int = -1):
+        self.params = dict(params)
+        self.lib = abi.load_library()
+        self.P = abi.make_params(params, device)
+        self.h = C.c_void_p()
+        self.N = int(np.prod(params["size"]))
+        self.nWalls = int(params.get("nWalls", 0))
+        self.freeSurface = bool(params["freeSurface"])
+        self._fs_requested = False
+        self._couple = None
+        self._last = (np.zeros(0, abi_particle_dtype()), np.zeros(0, abi_element_dtype()), np.zeros(0, np.uint32))
+        self.time = 0
+
+    # -- LB::latticeBolzmannInit (LB.h:158) -----------------------------------------------------
+    def latticeBolzmannInit(self, type_flags, solidIndex, n, u, mass, visc, f=None):
+        a = lambda x, dt: np.ascontiguousarray(x, dtype=dt)
+        tf, si = a(type_flags, np.uint8), a(solidIndex, np.uint32)
+        n_, u_, m_, v_ = a(n, np.float64), a(u, np.float64), a(mass, np.float64), a(visc, np.float64)
+        f_ = None if f is None else a(f, np.float64)
+        for arr, cnt in ((tf, self.N), (si, self.N), (n_, self.N), (u_, 3 * self.N), (m_, self.N), (v_, self.N)):
+            if arr.size != cnt:
+                raise ValueError("latticeBolzmannInit: array of %d elements, expected %d" % (arr.size, cnt))
+        if f_ is not None and f_.size != abi.Q * self.N:
+            raise ValueError("latticeBolzmannInit: f must hold 19*N values")
+        abi.check(self.lib.lbGpuInit(C.byref(self.P), abi.ptr(tf), abi.ptr(si), abi.ptr(f_), abi.ptr(n_), abi.ptr(u_),
+                                     abi.ptr(m_), abi.ptr(v_), C.byref(self.h)))
+        return self
+
+    # -- LB::latticeBoltzmannFreeSurfaceStep (LB.h:161) ------------------------------------------
+    def latticeBoltzmannFreeSurfaceStep(self):
+        self._fs_requested = True
+
+    # -- LB::latticeBoltzmannCouplingStep (LB.h:160) ---------------------------------------------
+    def latticeBoltzmannCouplingStep(self, newNeighborList, elmts, particles, components):
+        """Returns False: the reference resets dem.newNeighborList through its bool& (LB.cpp:258)."""
+        self._couple = (bool(newNeighborList), np.ascontiguousarray(particles), np.ascontiguousarray(elmts),
+                        np.ascontiguousarray(components, dtype=np.uint32))
+        return False
+
+    # -- LB::latticeBolzmannStep (LB.h:159) ------------------------------------------------------
+    def latticeBolzmannStep(self, elmts=None, particles=None, fetch_forces=True):
+        fs = int(self._fs_requested and self.freeSurface)
+        if self._couple is not None:
+            rescan, parts, els, comps = self._couple
+            self._last = (parts, els, comps)
+            abi.check(self.lib.lbGpuStep(self.h, fs, 1, int(rescan), abi.ptr(parts), len(parts), abi.ptr(els), len(els),
+                                         abi.ptr(comps), len(comps)))
+        else:
+            abi.check(self.lib.lbGpuStep(self.h, fs, 0, 0, None, 0, None, 0, None, 0))
+        self._fs_requested = False
+        self._couple = None
+        self.time += 1
+        if not fetch_forces:
+            return None
+        return self.forces()
+
+    def forces(self):
+        nE = len(self._last[1])
+        F = np.zeros((nE, 3)); M = np.zeros((nE, 3)); V = np.zeros(nE); W = np.zeros((self.nWalls, 3))
+        abi.check(self.lib.lbGpuParticleForces(self.h, abi.ptr(F) if nE else None, abi.ptr(M) if nE else None,
+                                               abi.ptr(V) if nE else None, abi.ptr(W) if self.nWalls else None))
+        return F, M, V, W
+
+    def run(self, steps, free_surface=None):
+        """`steps` cycles without particles, issued back to back (no host round trip)."""
+        fs = self.freeSurface if free_surface is None else free_surface
+        abi.check(self.lib.lbGpuRun(self.h, int(fs), int(steps)))
+        self.time += int(steps)
+
+    def synchronize(self):
+        abi.check(self.lib.lbGpuSynchronize(self.h))
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        abi.check(self.lib.lbGpuLastStepMs(self.h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        v = C.c_uint64()
+        abi.check(self.lib.lbGpuLaunchCount(self.h, C.byref(v)))
+        return int(v.value)
+
+    def counts(self):
+        c = (C.c_uint64 * 4)()
+        abi.check(self.lib.lbGpuCounts(self.h, C.byref(c)))
+        return dict(fluid=int(c[0]), interface=int(c[1]), particle=int(c[2]), steps=int(c[3]))
+
+    # -- what IO reads from lb.types / lb.nodes (IO.cpp:698-831) ---------------------------------
+    def fetch(self, fields=("type_flags", "solidIndex", "n", "u", "mass", "visc", "shearRate", "hydroForce", "f")):
+        N = self.N
+        shapes = dict(type_flags=((N,), np.uint8), solidIndex=((N,), np.uint32), n=((N,), np.float64),
+                      u=((N, 3), np.float64), mass=((N,), np.float64), visc=((N,), np.float64),
+                      shearRate=((N,), np.float64), hydroForce=((N, 3), np.float64), f=((N, abi.Q), np.float64))
+        out = {k: np.zeros(shapes[k][0], shapes[k][1]) for k in fields}
+        order = ("type_flags", "solidIndex", "n", "u", "mass", "visc", "shearRate", "hydroForce", "f")
+        abi.check(self.lib.lbGpuFetchFields(self.h, *[abi.ptr(out.get(k)) for k in order]))
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.lbGpuFinalize(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def abi_particle_dtype():
+    from .lattice_init import PARTICLE_DTYPE
+    return PARTICLE_DTYPE
+
+
+def abi_element_dtype():
+    from .lattice_init import ELEMENT_DTYPE
+    return ELEMENT_DTYPE

@@ -1,0 +1,126 @@
+/* lbgpu.h -- C ABI of the B200 lattice-Boltzmann engine (liblbgpu.so).
+ *
+ * The reference (gnomeCreative/hybird) has no FFI: its boundary for the LB hot path is the C++
+ * class `LB` (LB.h:32-215), called from goCycle (hybird.cpp:35-66) and read by IO (IO.cpp).
+ * Each entry point below replaces one of those calls; the reference-side binding is the
+ * `LB` shim in hybird_b200/shim/LB_gpu.cpp.
+ *
+ *   lbGpuInit            <- LB::latticeBolzmannInit        (LB.h:158, LB.cpp:190-219) state upload
+ *   lbGpuStep            <- LB::latticeBoltzmannFreeSurfaceStep (LB.h:161, LB.cpp:235-245)
+ *                           LB::latticeBoltzmannCouplingStep    (LB.h:160, LB.cpp:247-280)
+ *                           LB::latticeBolzmannStep             (LB.h:159, LB.cpp:221-233)
+ *                           in the order goCycle issues them (hybird.cpp:49-57)
+ *   lbGpuParticleForces  <- elmts[].FHydro/MHydro/fluidVolume written by LB::computeHydroForces
+ *                           (LB.cpp:1851-1919) and walls[].FHydro written by LB::streaming
+ *                           (LB.cpp:1321-1341,1485-1487)
+ *   lbGpuFetchFields     <- IO's direct reads of lb.types[i], lb.nodes[i]->{n,u,visc,mass,
+ *                           shearRate} (IO.cpp:698-831, 835-895)
+ *
+ * Conventions: plain C, POD only, no exceptions cross the boundary.  Every function returns 0 on
+ * success or a negative LBGPU_E* code; lbGpuLastError() gives the message.  All host arrays are
+ * in the reference's cell order i = x + X*(y + Y*z) (LB.cpp:2317-2337) including the 1-cell
+ * boundary shell.  The caller owns host buffers; the library owns device memory.  Calls must come
+ * from one host thread per handle.  There is no CPU fallback: without a CUDA device every entry
+ * point fails with LBGPU_ENODEVICE.
+ */
+#ifndef LBGPU_H
+#define LBGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBGPU_ABI_VERSION 1
+
+enum {
+    LBGPU_OK = 0,
+    LBGPU_EINVAL = -1,      /* bad argument */
+    LBGPU_ENODEVICE = -2,   /* no CUDA device / driver */
+    LBGPU_ECUDA = -3,       /* CUDA runtime error */
+    LBGPU_EUNSUPPORTED = -4,/* feature of the reference not implemented (curved walls, type 9) */
+    LBGPU_ETYPE = -5,       /* "TYPE ERROR" of LB::streaming (LB.cpp:1458-1461): link to an illegal cell type */
+    LBGPU_ECOMM = -6        /* multi-GPU halo transport error */
+};
+
+/* cell-type byte: nodeType::t (node.h:71-84) in the low nibble plus flag bits */
+#define LBGPU_TYPE_MASK 0x0F
+#define LBGPU_P_BIT 0x10    /* nodeType::p, "inside particle" (node.h:86) */
+#define LBGPU_NODE_BIT 0x20 /* lb.nodes[i] != 0 (IO.cpp:747) */
+
+typedef struct {
+    int32_t size[3];      /* lbSize[0..2] incl. shell (LB.cpp:110-112) */
+    int32_t boundary[6];  /* boundary0..5 (LB.cpp:175-181): 4 periodic, 5/6 slip stat/dyn, 7/8 no-slip stat/dyn */
+    double lbF[3];        /* body force, lattice units (LB.cpp:173) */
+    double initDynVisc;   /* lattice units (LB.cpp:140) */
+    double plasticVisc;   /* lattice units (LB.cpp:141) */
+    double yieldStress;   /* lattice units (LB.cpp:142) */
+    double turbConst;     /* LB.cpp:185 */
+    double slipCoefficient; /* LB.cpp:183 */
+    int32_t freeSurface, forceField, nonNewtonian, turbulence; /* hybird.cpp:184-190 */
+    double unitLength, unitTime, unitDensity; /* LB.cpp:93-98; composites as measureUnits::setComposite */
+    int32_t nWalls;       /* dem.walls.size(): length of the wall-force output */
+    int32_t device;       /* CUDA device ordinal; -1 = current device */
+    /* slab decomposition (multi-GPU): this handle owns global planes [slabBegin, slabEnd) along
+     * slabAxis (0,1,2) plus one ghost plane on each cut side. nSlabs<=1: whole domain. */
+    int32_t slabAxis, nSlabs, slabIndex;
+    int32_t reserved[5];
+} LbGpuParams;
+
+typedef struct {
+    double x0[3], r, radiusVec[3]; /* particle::x0, r, radiusVec in physical units (elmt.h:17-36) */
+    uint32_t clusterIndex, particleIndex;
+} LbGpuParticle;                  /* 64 bytes */
+
+typedef struct {
+    double x1[3], wGlobal[3];     /* elmt::x1, wGlobal in physical units (elmt.h:70-90) */
+    uint32_t compBegin, compEnd;  /* elmt::components as a range of the flattened `components` array */
+} LbGpuElement;                   /* 56 bytes */
+
+typedef struct LbGpuHandle LbGpuHandle;
+
+const char* lbGpuLastError(void);
+int lbGpuAbiVersion(void);
+int lbGpuDeviceCount(void);
+
+/* Upload the state LB::latticeBolzmannInit produced.
+ *   type_flags  N bytes: t | p<<4 | node<<5
+ *   solidIndex  N
+ *   f           19*N doubles, cell-major ([i][j] like node::f) or NULL => equilibrium of (n,u) as node::initialize
+ *   n,u,mass,visc  N, 3N (cell-major), N, N; read where the node bit is set (wall cells carry the wall velocity in u)
+ */
+int lbGpuInit(const LbGpuParams* params, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
+              const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out);
+
+/* One goCycle worth of LB work, in the reference's order: free-surface step (if doFreeSurface),
+ * coupling step (if doCoupling; rescanParticles = dem.newNeighborList), LB step.
+ * parts/elmts/components may be NULL when nParts == 0. Asynchronous on the handle's stream. */
+int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParticles, const LbGpuParticle* parts,
+              uint32_t nParts, const LbGpuElement* elmts, uint32_t nElmts, const uint32_t* components,
+              uint32_t nComponents);
+
+/* Same step repeated `count` times with no particles (pure-fluid / free-surface runs). */
+int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
+
+/* Results of the last step in physical units; any pointer may be NULL. Synchronises. */
+int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHydro /*3*nElmts*/,
+                        double* fluidVolume /*nElmts*/, double* wallFHydro /*3*nWalls*/);
+
+/* Host mirrors for IO; any pointer may be NULL. f is cell-major post-collision populations
+ * (node::fs after the last step). Synchronises. */
+int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, double* n, double* u, double* mass,
+                     double* visc, double* shearRate, double* hydroForce, double* f);
+
+/* counters: [0]=fluid cells, [1]=interface cells, [2]=cells with p flag, [3]=LB steps done */
+int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]);
+int lbGpuSynchronize(LbGpuHandle* h);
+/* device time of the kernels launched by the last lbGpuStep/lbGpuRun call, milliseconds (CUDA events) */
+int lbGpuLastStepMs(LbGpuHandle* h, float* ms);
+/* number of kernels this handle launched so far */
+int lbGpuLaunchCount(LbGpuHandle* h, uint64_t* launches);
+int lbGpuFinalize(LbGpuHandle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -61,8 +61,8 @@ def run_case(case, steps, workdir="/tmp/hb_cases", dumps=None, verbose=True, typ
         if hdr["freeSurface"]:
             o.latticeBoltzmannFreeSurfaceStep()
         if demSolve:
-            o.latticeBoltzmannCouplingStep(flag, parts, elmts, comps)
-        F, M, V, Wf = o.latticeBolzmannStep(parts, elmts)
+            o.latticeBoltzmannCouplingStep(flag, elmts, parts, comps)
+        F, M, V, Wf = o.latticeBolzmannStep(elmts, parts)
         if types is not None:
             mine = (o.type_flags & 0x1F)
             if np.count_nonzero(mine != types[s]):
