@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the hybird LB hot path on B200 (fp64 D3Q19), driver contract.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2]
+
+A "step" is one LB time step (LB::latticeBolzmannStep and, for free-surface workloads, the
+free-surface step in front of it) over the whole lattice.  Workload at N=1: BASELINE.json
+configs[1], the pure-fluid D3Q19 periodic channel 256^3 (BGK, Newtonian, body force, no
+particles); at N>1 the channel is extended along z to 256x256x(254*N+2) and cut into N z-slabs
+(weak scaling), one rank per GPU, halo planes exchanged every step.
+
+Prints ONE JSON line (rank 0).  `value` = active-cell updates / s with the state resident in HBM,
+timed with CUDA events on the engine's stream; `e2e` = the same metric through the C ABI with
+host buffers (lbGpuStep + lbGpuParticleForces per step, wall clock); `roofline` = 304 B per
+update x active cells / fused-kernel time against MEASURED_PEAKS.json; `cpu_baseline` = the
+unmodified reference (oracle/_ref/ref_harness) timed on the host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE = 2 * 19 * 8  # 19 fp64 populations read + 19 written
+METRIC = "MLUPS (fp64 D3Q19) at 1/2/4/8 B200 and % of HBM roofline vs ref CPU"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for ln in self.proc.stdout:
+                self.lines.append((time.time(), ln.strip()))
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines]
+        for ln in rows:
+            c = [x.strip() for x in ln.split(",")]
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(c) > 5 + k and c[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_case(name, n_slabs=1):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    cat = cases.catalogue()
+    case = dict(cat[name])
+    if n_slabs > 1:
+        if name != "cfg2":
+            raise SystemExit("multi-GPU bench is defined for the cfg2 channel")
+        case["lbSizeZ"] = 254 * n_slabs + 2
+    return case
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (unmodified, oracle/_ref/ref_harness)
+# ---------------------------------------------------------------------------------------------
+def reference_sample_case(name):
+    """Bounded sample of the workload for the CPU runs: same physics and boundaries, the periodic
+    channel cropped in y (the flow is invariant along x and y) so a step takes ~1 s of CPU."""
+    case = workload_case(name)
+    if name == "cfg2":
+        case["lbSizeY"] = 34
+        sample = "cfg2 channel cropped to 256x34x256 (2.2 M cells, same physics/boundaries)"
+    else:
+        sample = name + " at full size"
+    case["name"] = name + "_cpu_sample"
+    return case, sample
+
+
+def run_reference(name, steps, warmup, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cases
+    threads = threads or (os.cpu_count() or 1)
+    case, sample = reference_sample_case(name)
+    kind = "reference"
+    with tempfile.TemporaryDirectory() as wd:
+        if os.path.exists(cases.REF_HARNESS):
+            _, so = cases.run_reference(case, wd, steps, time_mode=True, warmup=warmup, threads=threads)
+            rec = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
+            mlups, ms, act = rec["mlups_active"], rec["ms_per_step"], rec["active_mean"]
+            threads = rec["threads"]
+        else:  # the C restatement (port) when the compiled reference did not travel
+            kind = "port"
+            mlups, ms, act = run_port(case, steps, warmup, threads)
+    return dict(value=mlups, unit="MLUPS", cores=int(threads), kind=kind, sample=sample + ", %d steps after %d warm-up" % (steps, warmup),
+                ms_per_step=ms, active_cells=act)
+
+
+def run_port(case, steps, warmup, threads):
+    import numpy as np
+    import lbo
+    from hybird_b200 import lattice_init as li
+    st = li.build_state(case)
+    o = lbo.Oracle(st.params, st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc, threads=threads)
+    fs = st.params["freeSurface"]
+    def one():
+        if fs:
+            o.latticeBoltzmannFreeSurfaceStep()
+        o.latticeBolzmannStep()
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = time.perf_counter() - t0
+    act = float(np.count_nonzero(np.isin(o.type_flags & 15, (0, 3))))
+    o.close()
+    return act * steps / dt / 1e6, 1e3 * dt / steps, act
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    r = run_reference(args.workload, steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MLUPS", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def main_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from hybird_b200 import LB, lattice_init as li
+    from hybird_b200 import slabs
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    case = workload_case(args.workload, world)
+    t_init = time.time()
+    lb, info = slabs.build_engine(case, rank, world, device=local_rank, dist=dist if world > 1 else None)
+    active_local = info["active_local"]
+    active_total = info["active_total"]
+    t_init = time.time() - t_init
+
+    def barrier():
+        lb.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    # ---- device-resident throughput: W warm-up steps, then exactly K steps ----
+    lb.run(W)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = lb.launch_count()
+    barrier()
+    t0w = time.time()
+    lb.run(K)
+    lb.synchronize()
+    ms_dev = lb.last_step_ms()          # CUDA events on the engine's stream around the K steps
+    kern_ms, kern_n = lb.last_kernel_ms()  # CUDA events around each fused k_step launch (last <=512 of the K)
+    kern_ms = kern_ms / max(kern_n, 1)
+    t1w = time.time()
+    launches = lb.launch_count() - l0
+    barrier()
+    if sampler:
+        time.sleep(0.2)
+        sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms_dev, kern_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, kern_ms = float(t[0]), float(t[1])
+    mlups = active_total * K / (ms_dev * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers: lbGpuStep + lbGpuParticleForces per step ----
+    Ke = min(K, 200)
+    parts, elmts, comps = info["parts"], info["elmts"], info["comps"]
+    h2d = int(parts.nbytes + elmts.nbytes + comps.nbytes)
+    d2h = int(8 * (7 * len(elmts) + 3 * lb.nWalls))
+    fs = bool(info["params"]["freeSurface"])
+    def e2e_step():
+        if fs:
+            lb.latticeBoltzmannFreeSurfaceStep()
+        if len(parts):
+            lb.latticeBoltzmannCouplingStep(False, elmts, parts, comps)
+        return lb.latticeBolzmannStep(elmts, parts)  # returns host F, M, V, wallF (synchronous)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    te = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    lb.synchronize()
+    te = time.perf_counter() - te
+    if world > 1:
+        t = torch.tensor([te], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        te = float(t[0])
+    e2e_mlups = active_total * Ke / te / 1e6
+
+    # cost of the other host-facing calls (not per step in the reference either: init once, fetch per export)
+    tf = time.perf_counter()
+    fields = lb.fetch(("type_flags", "n", "u", "mass"))
+    fetch_ms = 1e3 * (time.perf_counter() - tf)
+    fetch_bytes = int(sum(v.nbytes for v in fields.values()))
+    del fields
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = load_peaks()
+    kern_avg_ms = kern_ms
+    achieved = BYTES_PER_UPDATE * active_local / (kern_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    clocks = sampler.summary(t0w, t1w) if sampler else {}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = run_reference(args.workload, 8, 2)
+            cpu = {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as e:  # noqa: BLE001
+            cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
+    size = info["params"]["size"]
+    line = {
+        "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: D3Q19 periodic channel %dx%dx%d, BGK Newtonian tau=1, body force, no particles"
+                               % (args.workload, size[0], size[1], info["global_z"]) if args.workload == "cfg2" else args.workload,
+                   "lattice": [int(size[0]), int(size[1]), int(info["global_z"])], "active_cells": int(active_total),
+                   "parallelism": info["parallelism"],
+                   "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (info["bytes_resident"] / 1e9),
+                   "init_upload_s": round(t_init, 2)},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": info["kernel"],
+                     "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(active_local),
+                     "kernel_ms": kern_avg_ms},
+        "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "call": "lbGpuStep(host particle/element arrays) + lbGpuParticleForces(host) per step",
+                "fetch_fields_ms": fetch_ms, "fetch_fields_bytes": fetch_bytes},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return main_reference(args, rank, world)
+    return main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,7 +33,7 @@ class LbGpuParams(C.Structure):
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuInit", "lbGpuStep", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
-           "lbGpuLaunchCount", "lbGpuFinalize")
+           "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuFinalize")
 
 _lib = None
 
@@ -73,6 +73,8 @@ def load_library(build_if_missing=True):
     L.lbGpuSynchronize.argtypes = [vp]
     L.lbGpuLastStepMs.restype = C.c_int
     L.lbGpuLastStepMs.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lbGpuLastKernelMs.restype = C.c_int
+    L.lbGpuLastKernelMs.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.lbGpuLaunchCount.restype = C.c_int
     L.lbGpuLaunchCount.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.lbGpuFinalize.restype = C.c_int

@@ -97,6 +97,10 @@ struct LbGpuHandle {
     uint32_t blocks = 0;
     double uLength = 1, uSpeed = 1, uAngVel = 1, uForce = 1, uTorque = 1, uVolume = 1;
     float lastMs = 0.f;
+    // CUDA-event pairs around the fused step kernel of the last lbGpuStep/lbGpuRun call (ring of KEV)
+    static constexpr uint32_t KEV = 512;
+    std::vector<cudaEvent_t> kev0, kev1;
+    uint32_t kevCount = 0;
 
     double* fbuf(int k) { return k == 0 ? fA.p : fB.p; }
     uint8_t* tbuf(int k) { return k == 0 ? type0.p : type1.p; }
@@ -253,7 +257,11 @@ int lb_step(LbGpuHandle* h) {
     const int nSums = 1 + 3 * h->prm.nWalls;
     if (h->dynWall) CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * (size_t)B * nSums, s));
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall);
+    const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
+    CU(cudaEventRecord(h->kev0[ke], s));
     k<<<B, BLOCK, 0, s>>>(d);
+    CU(cudaEventRecord(h->kev1[ke], s));
+    ++h->kevCount;
     ++h->launches;
     if (h->dynWall) {
         k_reduce_partials<<<1, 1024, 0, s>>>(h->partial.p, B, nSums, h->sums.p + 4, 0);
@@ -349,6 +357,8 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
+        h->kev0.resize(LbGpuHandle::KEV); h->kev1.resize(LbGpuHandle::KEV);
+        for (uint32_t k = 0; k < LbGpuHandle::KEV; ++k) { CU(cudaEventCreate(&h->kev0[k])); CU(cudaEventCreate(&h->kev1[k])); }
         h->stride = ((size_t)N + 31) / 32 * 32;
         h->blocks = (N + BLOCK - 1) / BLOCK;
         h->fs = prm->freeSurface != 0;
@@ -446,6 +456,7 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
     if (nParts && (!parts || !elmts || !components)) return fail(LBGPU_EINVAL, "lbGpuStep: particle arrays missing");
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->evA, h->stream));
+    h->kevCount = 0;
     int rc;
     if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
     if (doCoupling) {
@@ -461,6 +472,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     if (!h) return fail(LBGPU_EINVAL, "lbGpuRun: null handle");
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->evA, h->stream));
+    h->kevCount = 0;
     for (uint32_t k = 0; k < count; ++k) {
         int rc;
         if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
@@ -482,6 +494,21 @@ int lbGpuLastStepMs(LbGpuHandle* h, float* ms) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventSynchronize(h->evB));
     CU(cudaEventElapsedTime(ms, h->evA, h->evB));
+    return LBGPU_OK;
+}
+
+int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches) {
+    if (!h || !msSum || !launches) return fail(LBGPU_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const uint32_t n = h->kevCount < LbGpuHandle::KEV ? h->kevCount : LbGpuHandle::KEV;
+    float sum = 0.f;
+    for (uint32_t k = 0; k < n; ++k) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->kev0[k], h->kev1[k]));
+        sum += ms;
+    }
+    *msSum = sum; *launches = n;
     return LBGPU_OK;
 }
 
@@ -605,6 +632,8 @@ int lbGpuFinalize(LbGpuHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
+    for (cudaEvent_t e : h->kev0) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->kev1) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->pinnedStatus) cudaFreeHost(h->pinnedStatus);
     if (h->stream) cudaStreamDestroy(h->stream);

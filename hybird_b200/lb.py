@@ -100,6 +100,12 @@ class LB:
         abi.check(self.lib.lbGpuLastStepMs(self.h, C.byref(ms)))
         return float(ms.value)
 
+    def last_kernel_ms(self):
+        """(sum of fused-kernel device times, number of launches) of the last run()/step call."""
+        ms, n = C.c_float(), C.c_uint32()
+        abi.check(self.lib.lbGpuLastKernelMs(self.h, C.byref(ms), C.byref(n)))
+        return float(ms.value), int(n.value)
+
     def launch_count(self):
         v = C.c_uint64()
         abi.check(self.lib.lbGpuLaunchCount(self.h, C.byref(v)))

@@ -116,6 +116,9 @@ int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]);
 int lbGpuSynchronize(LbGpuHandle* h);
 /* device time of the kernels launched by the last lbGpuStep/lbGpuRun call, milliseconds (CUDA events) */
 int lbGpuLastStepMs(LbGpuHandle* h, float* ms);
+/* device time of the fused stream-collide kernel alone: sum over the (at most 512 most recent)
+ * launches of the last lbGpuStep/lbGpuRun call, CUDA events on the engine's stream. Synchronises. */
+int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches);
 /* number of kernels this handle launched so far */
 int lbGpuLaunchCount(LbGpuHandle* h, uint64_t* launches);
 int lbGpuFinalize(LbGpuHandle* h);
