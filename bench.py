@@ -91,6 +91,13 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_label(name, n_slabs=1):
+    if name == "cfg2":
+        return "cfg2: D3Q19 periodic channel 256x256x%d, BGK Newtonian tau=1, body force, no particles" % (
+            256 if n_slabs == 1 else 254 * n_slabs + 2)
+    return name
+
+
 def workload_case(name, n_slabs=1):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cases
@@ -169,7 +176,7 @@ def main_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "sample": r["sample"]},
+            "config": {"workload": workload_label(args.workload, args.gpus), "sample": r["sample"]},
             "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -296,8 +303,7 @@ def main_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: D3Q19 periodic channel %dx%dx%d, BGK Newtonian tau=1, body force, no particles"
-                               % (args.workload, size[0], size[1], info["global_z"]) if args.workload == "cfg2" else args.workload,
+        "config": {"workload": workload_label(args.workload, world),
                    "lattice": [int(size[0]), int(size[1]), int(info["global_z"])], "active_cells": int(active_total),
                    "parallelism": info["parallelism"],
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (info["bytes_resident"] / 1e9),
@@ -323,7 +329,7 @@ def main_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="cfg2")

@@ -27,11 +27,11 @@ class LbGpuParams(C.Structure):
                 ("unitLength", C.c_double), ("unitTime", C.c_double), ("unitDensity", C.c_double),
                 ("nWalls", C.c_int32), ("device", C.c_int32),
                 ("slabAxis", C.c_int32), ("nSlabs", C.c_int32), ("slabIndex", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("nLocalSlabs", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 # every symbol include/lbgpu.h declares
-EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuInit", "lbGpuStep", "lbGpuRun",
+EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuStep", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuFinalize")
 
@@ -57,6 +57,8 @@ def load_library(build_if_missing=True):
     L.lbGpuLastError.restype = C.c_char_p
     L.lbGpuAbiVersion.restype = C.c_int
     L.lbGpuDeviceCount.restype = C.c_int
+    L.lbGpuSlabRange.restype = C.c_int
+    L.lbGpuSlabRange.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.lbGpuInit.restype = C.c_int
     L.lbGpuInit.argtypes = [C.POINTER(LbGpuParams), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.lbGpuStep.restype = C.c_int
@@ -104,7 +106,8 @@ def make_params(p: dict, device=-1) -> LbGpuParams:
         setattr(P, k, int(p[k]))
     P.nWalls = int(p.get("nWalls", 0))
     P.device = int(device)
-    P.slabAxis = 0
-    P.nSlabs = 1
-    P.slabIndex = 0
+    P.slabAxis = 2
+    P.nSlabs = int(p.get("nSlabs", 1))
+    P.slabIndex = int(p.get("slabIndex", 0))
+    P.nLocalSlabs = int(p.get("nLocalSlabs", P.nSlabs))
     return P

@@ -7,7 +7,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB = os.path.join(HERE, "liblbgpu.so")
+LIB = os.environ.get("LBGPU_LIB") or os.path.join(HERE, "liblbgpu.so")  # LBGPU_LIB: A/B experiments with alternative builds
 SOURCES = [os.path.join(HERE, "csrc", "lbgpu.cu")]
 DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("lb_kernels.cuh", "lb_d3q19.cuh")] + \
     [os.path.join(ROOT, "include", "lbgpu.h")]
@@ -36,7 +36,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + SOURCES + ["-o", LIB]
+    extra = os.environ.get("LBGPU_EXTRA_FLAGS", "").split()
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + SOURCES + ["-o", LIB]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout)

@@ -1,9 +1,14 @@
 // lbgpu.cu -- host side of liblbgpu.so: the C ABI of include/lbgpu.h on top of lb_kernels.cuh.
 //
-// One handle = one CUDA device = one slab of the lattice.  All work of a handle is issued on its
-// own stream; lbGpuStep is asynchronous except for the particle flood fill, which needs a 4-byte
-// read-back per generation.  There is deliberately no CPU path: without a device every entry
-// point returns LBGPU_ENODEVICE.
+// A handle owns one or more SLABS of the lattice (cut along z, the slowest index, so halo planes
+// are contiguous).  Each slab is a self-contained device lattice with one ghost plane on every cut
+// side; periodic boundaries use the same ghost mechanism inside a slab (k_fill_ghosts).  The ghost
+// planes between slabs of one handle are refreshed by device-to-device plane copies on the
+// handle's stream; slabs of other processes (one process per GPU) are reached through NCCL
+// send/recv (lbgpu_comm.cuh).
+// All work of a handle is issued on its own stream; lbGpuStep is asynchronous except for the
+// particle flood fill, which needs a 4-byte read-back per generation.  There is deliberately no
+// CPU path: without a device every entry point returns LBGPU_ENODEVICE.
 #include "../../include/lbgpu.h"
 
 #include <cuda_runtime.h>
@@ -12,6 +17,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <new>
 #include <string>
 #include <vector>
@@ -64,22 +70,42 @@ struct DevBuf {
     ~DevBuf() { release(); }
 };
 
+using namespace lb;
+
+// One device-resident part of the lattice: global planes [zBegin, zEnd) plus a plane below and above.
+struct Slab {
+    int index = 0;          // slab number in the global decomposition
+    int zBegin = 1, zEnd = 1;
+    uint32_t N = 0, XY = 0;
+    size_t stride = 0, pad = 0;
+    uint32_t blocks = 0;                 // blocks covering all N cells
+    uint32_t ownBegin = 0, ownEnd = 0;   // cells of the planes the per-cell kernels cover (everything but remote ghost planes)
+    Dev dev;                             // template for kernel parameters (pointers filled per launch)
+    DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
+    DevBuf<uint8_t> type0, type1, mark;
+    DevBuf<uint32_t> solidIndex, bulk;
+    DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
+    uint32_t nGhost = 0;
+    DevBuf<double> partial, sums, scal, elemOut;
+    DevBuf<unsigned long long> counters;  // [0] nInterface [1..3] k_count scratch
+    DevBuf<uint32_t> status;              // [0] type error, [1] flood-fill counter
+    // host copies of what lbGpuInit received for the ghost cells (they are dead cells of the reference)
+    std::vector<uint32_t> ghostIdx, ghostSolid;
+    std::vector<uint8_t> ghostType;
+    bool remoteLo = false, remoteHi = false;  // the z-/z+ ghost plane belongs to another slab
+    double* fbuf(int k) { return (k == 0 ? fA.p : fB.p) + pad; }
+    uint8_t* tbuf(int k) { return k == 0 ? type0.p : type1.p; }
+};
+
 }  // namespace
 
 struct LbGpuHandle {
     LbGpuParams prm;
     int device = 0;
-    uint32_t N = 0;
-    size_t stride = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
-    lb::Dev dev;  // template for kernel parameters (pointers filled per launch)
-    DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
-    DevBuf<uint8_t> type0, type1, mark;
-    DevBuf<uint32_t> solidIndex;
-    DevBuf<double> partial, sums, scal, elemOut, wallOut;
-    DevBuf<unsigned long long> counters;  // [0] nInterface [1..3] k_count scratch
-    DevBuf<uint32_t> status;              // [0] type error, [1] flood-fill counter
+    std::vector<std::unique_ptr<Slab>> slabs;
+    int nSlabsGlobal = 1, firstSlab = 0;
     DevBuf<lb::RawParticle> rawParts;
     DevBuf<lb::RawElement> rawElmts;
     DevBuf<lb::Particle> parts;
@@ -91,24 +117,17 @@ struct LbGpuHandle {
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
     int curType = 0;  // type buffer holding the current types
-    bool fs = false, shear = false, force = false, macroAlways = false, dynWall = false;
+    bool fs = false, shear = false, force = false, macroAlways = false, dynWall = false, slip = false;
     bool macroValid = true, lastStepFirst = false, lastStepCoupled = false, typesFlipped = false;
     uint64_t steps = 0, launches = 0;
-    uint32_t blocks = 0;
     double uLength = 1, uSpeed = 1, uAngVel = 1, uForce = 1, uTorque = 1, uVolume = 1;
-    float lastMs = 0.f;
     // CUDA-event pairs around the fused step kernel of the last lbGpuStep/lbGpuRun call (ring of KEV)
     static constexpr uint32_t KEV = 512;
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
-
-    double* fbuf(int k) { return k == 0 ? fA.p : fB.p; }
-    uint8_t* tbuf(int k) { return k == 0 ? type0.p : type1.p; }
 };
 
 namespace {
-
-using namespace lb;
 
 typedef void (*StepKernel)(const Dev);
 
@@ -134,21 +153,25 @@ StepKernel select_step(bool force, bool shear, bool macro, bool couple, bool fsO
     return shear ? pick_step<true, true, true, false>(fsOn, dyn) : pick_step<true, false, true, false>(fsOn, dyn);
 }
 
-Dev dev_for(LbGpuHandle* h, bool fsStep) {
-    Dev d = h->dev;
-    d.fsrc = h->fbuf(h->cur);
-    d.fdst = h->fbuf(h->cur ^ 1);
-    if (fsStep) {
-        d.typeOld = h->tbuf(h->curType);
-        d.type = h->tbuf(h->curType ^ 1);
-    } else {
-        d.typeOld = h->tbuf(h->curType);
-        d.type = h->tbuf(h->curType);
-    }
+// kernel parameters of slab s for the current buffers; per-cell kernels cover the owned planes
+Dev dev_for(LbGpuHandle* h, Slab* s) {
+    Dev d = s->dev;
+    d.fsrc = s->fbuf(h->cur);
+    d.fdst = s->fbuf(h->cur ^ 1);
+    for (int k = 0; k < Q; ++k) { d.fsrcK[k] = d.fsrc + (size_t)k * s->stride; d.fdstK[k] = d.fdst + (size_t)k * s->stride; }
+    d.typeOld = s->tbuf(h->curType);
+    d.type = s->tbuf(h->curType);
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
+    d.cellBegin = s->ownBegin; d.cellEnd = s->ownEnd;
     return d;
 }
+Dev dev_all(LbGpuHandle* h, Slab* s) {  // same, covering every cell including remote ghost planes
+    Dev d = dev_for(h, s);
+    d.cellBegin = 0; d.cellEnd = s->N;
+    return d;
+}
+uint32_t own_blocks(const Slab* s) { return (s->ownEnd - s->ownBegin + BLOCK - 1) / BLOCK; }
 
 int ensure_pinned(LbGpuHandle* h, size_t bytes) {
     if (bytes <= h->pinnedBytes) return 0;
@@ -160,6 +183,100 @@ int ensure_pinned(LbGpuHandle* h, size_t bytes) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Ghost refresh: local periodic mirrors inside every slab, then the planes between slabs.
+// `what` is a mask of lb::G_* fields; G_POPS refers to the destination population buffer.
+// ---------------------------------------------------------------------------------------------
+const int POPS_UP[5] = { 5, 11, 13, 15, 18 };    // CZ > 0: pulled by the slab above out of its lower ghost plane
+const int POPS_DOWN[5] = { 6, 12, 14, 16, 17 };  // CZ < 0
+
+template <class T>
+int copy_plane(T* dst, uint32_t dstPlane, const T* src, uint32_t srcPlane, uint32_t XY, cudaStream_t st) {
+    CU(cudaMemcpyAsync(dst + (size_t)dstPlane * XY, src + (size_t)srcPlane * XY, sizeof(T) * XY, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// plane `sp` of slab a -> ghost plane `dp` of slab b (same process)
+int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32_t what, bool up, bool typeNew) {
+    cudaStream_t st = h->stream;
+    const uint32_t XY = a->XY;
+    int rc;
+    if (what & G_POPS) {
+        double* src = a->fbuf(h->cur ^ 1); double* dst = b->fbuf(h->cur ^ 1);
+        if (h->slip) {
+            for (int k = 0; k < Q; ++k) if ((rc = copy_plane(dst + (size_t)k * b->stride, dp, src + (size_t)k * a->stride, sp, XY, st))) return rc;
+        } else {
+            const int* ks = up ? POPS_UP : POPS_DOWN;
+            for (int q = 0; q < 5; ++q)
+                if ((rc = copy_plane(dst + (size_t)ks[q] * b->stride, dp, src + (size_t)ks[q] * a->stride, sp, XY, st))) return rc;
+        }
+    }
+    if (what & G_POPS_SRC) {
+        double* src = a->fbuf(h->cur); double* dst = b->fbuf(h->cur);
+        for (int k = 0; k < Q; ++k) if ((rc = copy_plane(dst + (size_t)k * b->stride, dp, src + (size_t)k * a->stride, sp, XY, st))) return rc;
+    }
+    if (what & G_TYPE) { const int tbi = typeNew ? (h->curType ^ 1) : h->curType; if ((rc = copy_plane(b->tbuf(tbi), dp, a->tbuf(tbi), sp, XY, st))) return rc; }
+    if (what & G_SOLID) if ((rc = copy_plane(b->solidIndex.p, dp, a->solidIndex.p, sp, XY, st))) return rc;
+    if (what & G_MASS) if ((rc = copy_plane(b->mass.p, dp, a->mass.p, sp, XY, st))) return rc;
+    if (what & G_MACRO) {
+        if ((rc = copy_plane(b->n.p, dp, a->n.p, sp, XY, st))) return rc;
+        if ((rc = copy_plane(b->ux.p, dp, a->ux.p, sp, XY, st))) return rc;
+        if ((rc = copy_plane(b->uy.p, dp, a->uy.p, sp, XY, st))) return rc;
+        if ((rc = copy_plane(b->uz.p, dp, a->uz.p, sp, XY, st))) return rc;
+    }
+    if (what & G_VISC) if ((rc = copy_plane(b->visc.p, dp, a->visc.p, sp, XY, st))) return rc;
+    if (what & G_HF) {
+        if ((rc = copy_plane(b->hfx.p, dp, a->hfx.p, sp, XY, st))) return rc;
+        if ((rc = copy_plane(b->hfy.p, dp, a->hfy.p, sp, XY, st))) return rc;
+        if ((rc = copy_plane(b->hfz.p, dp, a->hfz.p, sp, XY, st))) return rc;
+    }
+    if ((what & G_MARK) && a->mark.p) if ((rc = copy_plane(b->mark.p, dp, a->mark.p, sp, XY, st))) return rc;
+    return 0;
+}
+
+// typeNew: the type buffer being written by a free-surface step (curType^1) instead of the current one
+int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false) {
+    cudaStream_t st = h->stream;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        if (!s->nGhost) continue;
+        Dev d = dev_for(h, s);
+        if (typeNew) d.type = s->tbuf(h->curType ^ 1);
+        k_fill_ghosts<<<(s->nGhost + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d, s->gDst.p, s->gSrc.p, s->gPop.p, 0, s->nGhost, what, s->mark.p);
+        ++h->launches;
+    }
+    const int G = (int)h->slabs.size();
+    if (G > 1) {
+        const bool ring = h->prm.boundary[4] == T_PERIODIC;
+        for (int k = 0; k < G; ++k) {
+            Slab* a = h->slabs[k].get();
+            const int ku = (k + 1 < G) ? k + 1 : (ring ? 0 : -1);
+            if (ku < 0) continue;
+            Slab* b = h->slabs[ku].get();
+            int rc;
+            // a's top owned plane -> b's lower ghost plane; b's bottom owned plane -> a's upper ghost plane
+            if ((rc = copy_face(h, a, (uint32_t)a->dev.Z - 2, b, 0, what, true, typeNew))) return rc;
+            if ((rc = copy_face(h, b, 1, a, (uint32_t)a->dev.Z - 1, what, false, typeNew))) return rc;
+        }
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// sums over the slabs of small per-slab device arrays (fixed slab order), result in slab 0's array
+__global__ void k_add_arrays(double* __restrict__ dst, const double* __restrict__ src, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void k_add_counters(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+__global__ void k_add_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += src[i];
+}
+
 int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
                      uint32_t nElmts, const uint32_t* comps, uint32_t nComps) {
     static_assert(sizeof(LbGpuParticle) == sizeof(RawParticle) && sizeof(LbGpuElement) == sizeof(RawElement), "ABI layout");
@@ -167,7 +284,7 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
     if (nElmts > h->rawElmts.n) {
         CU(h->rawElmts.alloc(nElmts + nElmts / 2 + 16));
         CU(h->elmts.alloc(h->rawElmts.n));
-        CU(h->elemOut.alloc(h->rawElmts.n * 7));
+        for (auto& s : h->slabs) CU(s->elemOut.alloc(h->rawElmts.n * 7));
     }
     if (nComps > h->comps.n) CU(h->comps.alloc(nComps + nComps / 2 + 16));
     const size_t bP = sizeof(RawParticle) * nParts, bE = sizeof(RawElement) * nElmts, bC = sizeof(uint32_t) * nComps;
@@ -192,20 +309,62 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
 }
 
 int free_surface_step(LbGpuHandle* h) {
-    Dev d = dev_for(h, true);
-    const uint32_t B = h->blocks;
-    cudaStream_t s = h->stream;
-    d.pull = h->steps > 0;
-    k_fs_mass<<<B, BLOCK, 0, s>>>(d);
-    k_fs_mutate<<<B, BLOCK, 0, s>>>(d, h->mark.p);
-    k_fs_smooth<<<B, BLOCK, 0, s>>>(d, h->mark.p, h->partial.p);
-    k_fs_isolated<0><<<B, BLOCK, 0, s>>>(d, h->partial.p + B, h->counters.p);
-    CU(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long), s));
-    k_fs_isolated<1><<<B, BLOCK, 0, s>>>(d, h->partial.p + 2 * (size_t)B, h->counters.p);
-    k_reduce_partials<<<1, 1024, 0, s>>>(h->partial.p, B, 3, h->sums.p, 0);
-    k_fs_finalize<<<1, 1, 0, s>>>(h->sums.p, h->counters.p, h->scal.p);
-    k_redistribute<<<B, BLOCK, 0, s>>>(d, h->scal.p + 1);
-    h->launches += 8;
+    cudaStream_t st = h->stream;
+    int rc;
+    auto fsdev = [&](Slab* s) {
+        Dev d = dev_for(h, s);
+        d.type = s->tbuf(h->curType ^ 1);
+        d.pull = h->steps > 0;
+        return d;
+    };
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        const Dev d = fsdev(s);
+        const uint32_t B = own_blocks(s);
+        k_fs_mass<<<B, BLOCK, 0, st>>>(d);
+        k_fs_mutate<<<B, BLOCK, 0, st>>>(d, s->mark.p);
+        h->launches += 2;
+    }
+    if ((rc = exchange(h, G_MARK | G_TYPE, true))) return rc;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        k_fs_smooth<<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s->mark.p, s->partial.p);
+        ++h->launches;
+    }
+    if ((rc = exchange(h, G_TYPE, true))) return rc;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        k_fs_isolated<0><<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s->partial.p + s->blocks, s->counters.p);
+        ++h->launches;
+    }
+    if ((rc = exchange(h, G_TYPE, true))) return rc;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        const uint32_t B = own_blocks(s);
+        CU(cudaMemsetAsync(s->counters.p, 0, sizeof(unsigned long long), st));
+        k_fs_isolated<1><<<B, BLOCK, 0, st>>>(fsdev(s), s->partial.p + 2 * (size_t)s->blocks, s->counters.p);
+        // three partial arrays with a pitch of s->blocks; the first B entries of each are used
+        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p, B, 1, s->sums.p, 0);
+        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p + s->blocks, B, 1, s->sums.p + 1, 0);
+        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p + 2 * (size_t)s->blocks, B, 1, s->sums.p + 2, 0);
+        h->launches += 4;
+    }
+    Slab* s0 = h->slabs[0].get();
+    for (size_t k = 1; k < h->slabs.size(); ++k) {
+        k_add_arrays<<<1, 32, 0, st>>>(s0->sums.p, h->slabs[k]->sums.p, 3);
+        k_add_counters<<<1, 32, 0, st>>>(s0->counters.p, h->slabs[k]->counters.p, 1);
+        h->launches += 2;
+    }
+    k_fs_finalize<<<1, 1, 0, st>>>(s0->sums.p, s0->counters.p, s0->scal.p);
+    ++h->launches;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        if (s != s0) CU(cudaMemcpyAsync(s->counters.p, s0->counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        k_redistribute<<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s0->scal.p + 1);
+        ++h->launches;
+    }
+    // new interface cells carry n, u, visc taken from their donors: refresh everything a neighbour may read
+    if ((rc = exchange(h, G_TYPE | G_MASS | G_MACRO | G_VISC | G_HF, true))) return rc;
     h->curType ^= 1;
     h->typesFlipped = true;
     CU(cudaGetLastError());
@@ -213,30 +372,43 @@ int free_surface_step(LbGpuHandle* h) {
 }
 
 int coupling_step(LbGpuHandle* h, bool rescan) {
-    Dev d = dev_for(h, false);
-    const uint32_t B = h->blocks;
-    cudaStream_t s = h->stream;
+    cudaStream_t st = h->stream;
+    int rc;
     if (h->nParts == 0) {
-        if (rescan) { k_clear_p<<<B, BLOCK, 0, s>>>(d); ++h->launches; }
+        if (rescan) {
+            for (auto& sp : h->slabs) { k_clear_p<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get())); ++h->launches; }
+        }
         return 0;
     }
     const uint32_t wb = (h->nParts * 32 + BLOCK - 1) / BLOCK;
     if (rescan) {
-        k_clear_p<<<B, BLOCK, 0, s>>>(d);
-        k_rescan<0><<<wb, BLOCK, 0, s>>>(d);
-        k_rescan<1><<<wb, BLOCK, 0, s>>>(d);
-        h->launches += 3;
+        for (auto& sp : h->slabs) {
+            k_clear_p<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()));
+            k_rescan<0><<<wb, BLOCK, 0, st>>>(dev_for(h, sp.get()));
+            k_rescan<1><<<wb, BLOCK, 0, st>>>(dev_for(h, sp.get()));
+            h->launches += 3;
+        }
     }
-    k_find_new_active<<<B, BLOCK, 0, s>>>(d);
-    ++h->launches;
+    for (auto& sp : h->slabs) {
+        k_find_new_active<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()));
+        ++h->launches;
+    }
+    if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
+    Slab* s0 = h->slabs[0].get();
     for (int gen = 0; gen < 4096; ++gen) {
-        CU(cudaMemsetAsync(h->status.p + 1, 0, sizeof(uint32_t), s));
-        k_find_new_solid<<<B, BLOCK, 0, s>>>(d, h->status.p + 1);
-        k_commit_pending<<<B, BLOCK, 0, s>>>(d);
-        h->launches += 2;
-        CU(cudaMemcpyAsync(h->pinnedStatus, h->status.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            const Dev d = dev_for(h, s);
+            CU(cudaMemsetAsync(s->status.p + 1, 0, sizeof(uint32_t), st));
+            k_find_new_solid<<<own_blocks(s), BLOCK, 0, st>>>(d, s->status.p + 1);
+            k_commit_pending<<<own_blocks(s), BLOCK, 0, st>>>(d);
+            h->launches += 2;
+        }
+        for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_u32<<<1, 32, 0, st>>>(s0->status.p + 1, h->slabs[k]->status.p + 1, 1); ++h->launches; }
+        CU(cudaMemcpyAsync(h->pinnedStatus, s0->status.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         if (*h->pinnedStatus == 0) break;
+        if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
     }
     CU(cudaGetLastError());
     return 0;
@@ -247,37 +419,53 @@ int lb_step(LbGpuHandle* h) {
     const bool couple = h->nParts > 0;
     const bool macro = h->macroAlways;
     const bool fsOn = h->fs;
-    Dev d = dev_for(h, false);
-    // the streaming being evaluated happened under the type map of before this cycle's free-surface step
-    if (h->typesFlipped) d.typeOld = h->tbuf(h->curType ^ 1);
-    h->typesFlipped = false;
-    d.pull = !first;
-    const uint32_t B = h->blocks;
-    cudaStream_t s = h->stream;
+    cudaStream_t st = h->stream;
+    int rc;
     const int nSums = 1 + 3 * h->prm.nWalls;
-    if (h->dynWall) CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * (size_t)B * nSums, s));
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall);
     const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
-    CU(cudaEventRecord(h->kev0[ke], s));
-    k<<<B, BLOCK, 0, s>>>(d);
-    CU(cudaEventRecord(h->kev1[ke], s));
-    ++h->kevCount;
-    ++h->launches;
-    if (h->dynWall) {
-        k_reduce_partials<<<1, 1024, 0, s>>>(h->partial.p, B, nSums, h->sums.p + 4, 0);
+    if (h->dynWall)
+        for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
+    CU(cudaEventRecord(h->kev0[ke], st));
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        Dev d = dev_for(h, s);
+        // the streaming being evaluated happened under the type map of before this cycle's free-surface step
+        if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
+        d.pull = !first;
+        d.pStride = s->blocks; d.pBase = 0;
+        k<<<own_blocks(s), BLOCK, 0, st>>>(d);
         ++h->launches;
+    }
+    CU(cudaEventRecord(h->kev1[ke], st));
+    ++h->kevCount;
+    h->typesFlipped = false;
+    if ((rc = exchange(h, G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u)))) return rc;
+    Slab* s0 = h->slabs[0].get();
+    if (h->dynWall) {
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            for (int a = 0; a < nSums; ++a)
+                k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p + (size_t)a * s->blocks, own_blocks(s), 1, s->sums.p + 4 + a, 0);
+            h->launches += nSums;
+            if (s != s0) { k_add_arrays<<<(nSums + 31) / 32, 32, 0, st>>>(s0->sums.p + 4, s->sums.p + 4, nSums); ++h->launches; }
+        }
         if (fsOn) {
             // LB::redistributeMass(extraMass) at the end of LB::streaming (LB.cpp:1477)
-            k_extra_mass_finalize<<<1, 1, 0, s>>>(h->sums.p + 4, h->counters.p, h->scal.p + 2);
-            Dev dn = d;
-            k_redistribute<<<B, BLOCK, 0, s>>>(dn, h->scal.p + 2);
-            h->launches += 2;
+            k_extra_mass_finalize<<<1, 1, 0, st>>>(s0->sums.p + 4, s0->counters.p, s0->scal.p + 2);
+            ++h->launches;
+            for (auto& sp : h->slabs) { k_redistribute<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()), s0->scal.p + 2); ++h->launches; }
+            if ((rc = exchange(h, G_MASS))) return rc;
         }
     }
     if (h->nElmts > 0 && couple) {
         const uint32_t eb = (h->nElmts * 32 + BLOCK - 1) / BLOCK;
-        k_element_forces<<<eb, BLOCK, 0, s>>>(d, h->uForce, h->uTorque, h->uVolume, h->elemOut.p);
-        ++h->launches;
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            k_element_forces<<<eb, BLOCK, 0, st>>>(dev_for(h, s), h->uForce, h->uTorque, h->uVolume, s->elemOut.p);
+            ++h->launches;
+            if (s != s0) { k_add_arrays<<<(7 * h->nElmts + 127) / 128, 128, 0, st>>>(s0->elemOut.p, s->elemOut.p, 7 * h->nElmts); ++h->launches; }
+        }
     }
     CU(cudaGetLastError());
     h->cur ^= 1;
@@ -289,13 +477,154 @@ int lb_step(LbGpuHandle* h) {
 }
 
 int check_status(LbGpuHandle* h) {
-    CU(cudaMemcpyAsync(h->pinnedStatus, h->status.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    if (*h->pinnedStatus) {
-        const unsigned t = *h->pinnedStatus - 1;
-        CU(cudaMemsetAsync(h->status.p, 0, sizeof(uint32_t), h->stream));
-        return fail(LBGPU_ETYPE, "TYPE ERROR: an active cell links to a cell of type %u (LB.cpp:1458-1461)", t);
+    for (auto& sp : h->slabs) {
+        CU(cudaMemcpyAsync(h->pinnedStatus, sp->status.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*h->pinnedStatus) {
+            const unsigned t = *h->pinnedStatus - 1;
+            CU(cudaMemsetAsync(sp->status.p, 0, sizeof(uint32_t), h->stream));
+            return fail(LBGPU_ETYPE, "TYPE ERROR: an active cell links to a cell of type %u (LB.cpp:1458-1461)", t);
+        }
     }
+    return 0;
+}
+
+// Build one slab: allocate, upload planes [zBegin-1, zEnd+1) of the host arrays (which start at plane hostZ0), ghost lists.
+int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
+               const double* n, const double* u, const double* mass, const double* visc) {
+    const LbGpuParams* prm = &h->prm;
+    cudaStream_t st = h->stream;
+    const int X = prm->size[0], Y = prm->size[1], gZ = prm->size[2];
+    const int Zl = s->zEnd - s->zBegin + 2;
+    s->XY = (uint32_t)X * (uint32_t)Y;
+    s->N = s->XY * (uint32_t)Zl;
+    const uint32_t N = s->N;
+    s->stride = ((size_t)N + 31) / 32 * 32;
+    // tile loads of the async-copy kernel reach one plane + one row + 2 cells beyond either end of a population plane
+    s->pad = ((size_t)s->XY + X + 2 + 511) / 32 * 32;
+    s->blocks = (N + BLOCK - 1) / BLOCK;
+    const bool perZ = prm->boundary[4] == T_PERIODIC;
+    s->remoteLo = s->zBegin > 1 || (perZ && h->nSlabsGlobal > 1);
+    s->remoteHi = s->zEnd < gZ - 1 || (perZ && h->nSlabsGlobal > 1);
+    s->ownBegin = s->remoteLo ? s->XY : 0;
+    s->ownEnd = s->remoteHi ? N - s->XY : N;
+    const size_t hostOff = (size_t)(s->zBegin - 1 - hostZ0) * s->XY;
+
+    CU(s->fA.alloc(s->stride * Q + 2 * s->pad)); CU(s->fB.alloc(s->stride * Q + 2 * s->pad));
+    CU(cudaMemsetAsync(s->fA.p, 0, sizeof(double) * s->fA.n, st)); CU(cudaMemsetAsync(s->fB.p, 0, sizeof(double) * s->fB.n, st));
+    CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
+    CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
+    CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
+    CU(s->type0.alloc(N)); CU(s->solidIndex.alloc(N));
+    if (h->fs) { CU(s->type1.alloc(N)); CU(s->mark.alloc(N)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, N, st)); }
+    const int nSums = 1 + 3 * prm->nWalls;
+    const size_t nPartial = (size_t)s->blocks * (size_t)(3 > nSums ? 3 : nSums);
+    CU(s->partial.alloc(nPartial));
+    CU(s->sums.alloc(8 + 3 * 64)); CU(s->scal.alloc(8));
+    CU(s->counters.alloc(8)); CU(s->status.alloc(4));
+    CU(cudaMemsetAsync(s->shearRate.p, 0, sizeof(double) * N, st));
+    CU(cudaMemsetAsync(s->hfx.p, 0, sizeof(double) * N, st));
+    CU(cudaMemsetAsync(s->hfy.p, 0, sizeof(double) * N, st));
+    CU(cudaMemsetAsync(s->hfz.p, 0, sizeof(double) * N, st));
+    CU(cudaMemsetAsync(s->sums.p, 0, sizeof(double) * s->sums.n, st));
+    CU(cudaMemsetAsync(s->scal.p, 0, sizeof(double) * 8, st));
+    CU(cudaMemsetAsync(s->counters.p, 0, sizeof(unsigned long long) * 8, st));
+    CU(cudaMemsetAsync(s->status.p, 0, sizeof(uint32_t) * 4, st));
+    CU(cudaMemsetAsync(s->partial.p, 0, sizeof(double) * nPartial, st));
+
+    Dev& d = s->dev;
+    memset(&d, 0, sizeof d);
+    d.X = X; d.Y = Y; d.Z = Zl; d.N = N; d.stride = s->stride;
+    d.divX = make_div((uint32_t)X); d.divXY = make_div(s->XY);
+    for (int k = 0; k < 4; ++k) d.ghost[k] = prm->boundary[k] == T_PERIODIC;
+    d.ghost[4] = s->remoteLo || perZ; d.ghost[5] = s->remoteHi || perZ;
+    d.perZ = perZ; d.zOff = s->zBegin - 1; d.gZ = gZ;
+    for (int j = 0; j < Q; ++j) d.off[j] = CXh(j) + X * (CYh(j) + Y * CZh(j));
+    d.solidIndex = s->solidIndex.p;
+    d.n = s->n.p; d.ux = s->ux.p; d.uy = s->uy.p; d.uz = s->uz.p;
+    d.mass = s->mass.p; d.newMass = s->newMass.p; d.visc = s->visc.p; d.shearRate = s->shearRate.p;
+    d.hfx = s->hfx.p; d.hfy = s->hfy.p; d.hfz = s->hfz.p;
+    for (int k = 0; k < 3; ++k) { d.lbF[k] = prm->forceField ? prm->lbF[k] : 0.0; d.lbFInit[k] = prm->lbF[k]; }
+    d.initVisc = prm->initDynVisc; d.plasticVisc = prm->plasticVisc; d.yieldStress = prm->yieldStress;
+    d.turbConst = prm->turbConst;
+    d.S1 = prm->slipCoefficient; d.S2 = 1.0 - prm->slipCoefficient;
+    d.uAngVel = h->uAngVel;
+    d.omega0 = 1.0 / (0.5 + 3.0 * prm->initDynVisc);           // node::solveCollision (node.cpp:158-165)
+    d.omegaf0 = 1.0 - 1.0 / (1.0 + 6.0 * prm->initDynVisc);    // node::addForce (node.cpp:167-184)
+    d.nonNewtonian = prm->nonNewtonian; d.turbulence = prm->turbulence;
+    d.nWalls = prm->nWalls;
+    d.partial = s->partial.p; d.status = s->status.p; d.pStride = s->blocks; d.pBase = 0;
+    d.bulk = nullptr;
+
+    // local ghost list: cells of the periodic x/y shells (and of the z shells when z is periodic inside this slab)
+    // mirror the cell at the wrapped position (LB.cpp:438-472: per-axis wrap, diagonals wrap twice)
+    {
+        const bool gx = d.ghost[0], gy = d.ghost[2], gzLocal = perZ && !s->remoteLo;
+        std::vector<uint32_t> gd, gs, gp;
+        auto idx = [&](int x, int y, int z) { return (uint32_t)x + (uint32_t)X * ((uint32_t)y + (uint32_t)Y * (uint32_t)z); };
+        for (int z = 0; z < Zl; ++z) {
+            const bool zs = (z == 0 || z == Zl - 1);
+            // remote ghost planes arrive complete (including their x/y ghosts) from the neighbour slab
+            if ((z == 0 && s->remoteLo) || (z == Zl - 1 && s->remoteHi)) continue;
+            for (int y = 0; y < Y; ++y) {
+                const bool ys = (y == 0 || y == Y - 1);
+                for (int x = 0; x < X; ++x) {
+                    const bool xs = (x == 0 || x == X - 1);
+                    const bool isG = (xs && gx) || (ys && gy) || (zs && gzLocal);
+                    if (!isG) continue;
+                    int sx = x, sy = y, sz = z;
+                    if (gx) { if (x == 0) sx = X - 2; else if (x == X - 1) sx = 1; }
+                    if (gy) { if (y == 0) sy = Y - 2; else if (y == Y - 1) sy = 1; }
+                    if (gzLocal) { if (z == 0) sz = Zl - 2; else if (z == Zl - 1) sz = 1; }
+                    uint32_t pm = 0;
+                    for (int j = 1; j < Q; ++j) {
+                        // population j is pulled out of this ghost by the cell at ghost + c_j, if that is an interior cell
+                        const int tx = x + CXh(j), ty = y + CYh(j), tz = z + CZh(j);
+                        if (tx >= 1 && tx <= X - 2 && ty >= 1 && ty <= Y - 2 && tz >= 1 && tz <= Zl - 2) pm |= 1u << j;
+                    }
+                    if (h->slip) pm = (1u << Q) - 1u;
+                    gd.push_back(idx(x, y, z)); gs.push_back(idx(sx, sy, sz)); gp.push_back(pm);
+                }
+            }
+        }
+        s->nGhost = (uint32_t)gd.size();
+        if (s->nGhost) {
+            CU(s->gDst.alloc(s->nGhost)); CU(s->gSrc.alloc(s->nGhost)); CU(s->gPop.alloc(s->nGhost));
+            CU(cudaMemcpyAsync(s->gDst.p, gd.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s->gSrc.p, gs.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(s->gPop.p, gp.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));
+            s->ghostIdx = gd;
+            s->ghostType.resize(s->nGhost); s->ghostSolid.resize(s->nGhost);
+            for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]]; }
+        }
+    }
+
+    // staged upload: host (pageable) -> device scratch -> SoA
+    CU(cudaMemcpyAsync(s->type0.p, type_flags + hostOff, N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->solidIndex.p, solidIndex + hostOff, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->n.p, n + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->mass.p, mass + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(s->visc.p, visc + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    {
+        DevBuf<double> tmp;
+        CU(tmp.alloc((size_t)3 * N));
+        CU(cudaMemcpyAsync(tmp.p, u + 3 * hostOff, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+        k_split3<<<s->blocks, BLOCK, 0, st>>>(N, tmp.p, s->ux.p, s->uy.p, s->uz.p);
+        CU(cudaStreamSynchronize(st));
+    }
+    Dev dd = dev_all(h, s);
+    if (f) {
+        DevBuf<double> tmp;
+        CU(tmp.alloc((size_t)Q * N));
+        CU(cudaMemcpyAsync(tmp.p, f + (size_t)Q * hostOff, sizeof(double) * Q * N, cudaMemcpyHostToDevice, st));
+        k_upload_f<<<s->blocks, BLOCK, 0, st>>>(dd, tmp.p, s->fbuf(0), s->fbuf(1));
+        CU(cudaStreamSynchronize(st));
+    } else {
+        k_upload_f<<<s->blocks, BLOCK, 0, st>>>(dd, nullptr, s->fbuf(0), s->fbuf(1));
+    }
+    h->launches += 2;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -313,6 +642,15 @@ int lbGpuDeviceCount(void) {
     return n;
 }
 
+int lbGpuSlabRange(int32_t sizeZ, int32_t nSlabs, int32_t slab, int32_t* zBegin, int32_t* zEnd) {
+    if (sizeZ < 3 || nSlabs < 1 || slab < 0 || slab >= nSlabs || nSlabs > sizeZ - 2 || !zBegin || !zEnd)
+        return fail(LBGPU_EINVAL, "lbGpuSlabRange: bad arguments");
+    const long long inner = sizeZ - 2;
+    *zBegin = 1 + (int32_t)((long long)slab * inner / nSlabs);
+    *zEnd = 1 + (int32_t)((long long)(slab + 1) * inner / nSlabs);
+    return LBGPU_OK;
+}
+
 int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
               const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out) {
     if (!prm || !type_flags || !solidIndex || !n || !u || !mass || !visc || !out) return fail(LBGPU_EINVAL, "lbGpuInit: null argument");
@@ -324,21 +662,30 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     }
     for (int k = 0; k < 3; ++k)
         if (prm->size[k] < 3) return fail(LBGPU_EINVAL, "lbGpuInit: lbSize[%d]=%d < 3", k, prm->size[k]);
-    const unsigned long long N64 = (unsigned long long)prm->size[0] * prm->size[1] * prm->size[2];
-    if (N64 >= (1ull << 31)) return fail(LBGPU_EINVAL, "lbGpuInit: %llu cells exceed the 2^31 index range", N64);
     for (int a = 0; a < 3; ++a) {
         const bool lo = prm->boundary[2 * a] == T_PERIODIC, hi = prm->boundary[2 * a + 1] == T_PERIODIC;
         if (lo != hi) return fail(LBGPU_EINVAL, "lbGpuInit: boundary%d/%d must both be periodic (4) or neither", 2 * a, 2 * a + 1);
     }
-    if (prm->nSlabs > 1) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: slab decomposition is driven by lbGpuInitSlab");
     if (prm->nWalls < 0 || prm->nWalls > 64) return fail(LBGPU_EINVAL, "lbGpuInit: nWalls=%d out of range", prm->nWalls);
-    const uint32_t N = (uint32_t)N64;
-    bool anyDyn = false, anyGas = false, anyIface = false;
-    for (uint32_t i = 0; i < N; ++i) {
+    const int G = prm->nSlabs > 1 ? prm->nSlabs : 1;
+    const int first = G > 1 ? prm->slabIndex : 0;
+    const int nLocal = G > 1 ? (prm->nLocalSlabs > 0 ? prm->nLocalSlabs : 1) : 1;
+    if (G > 1 && prm->slabAxis != 2) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: slabs are cut along z (slabAxis=2)");
+    if (first < 0 || first + nLocal > G || G > prm->size[2] - 2) return fail(LBGPU_EINVAL, "lbGpuInit: slab %d+%d of %d", first, nLocal, G);
+    if (first != 0 || nLocal != G) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: slabs on other processes need lbGpuCommInit (not in this build)");
+    int32_t zLo, zHi, tmpz;
+    lbGpuSlabRange(prm->size[2], G, first, &zLo, &tmpz);
+    lbGpuSlabRange(prm->size[2], G, first + nLocal - 1, &tmpz, &zHi);
+    const unsigned long long XY = (unsigned long long)prm->size[0] * prm->size[1];
+    const unsigned long long Nh = XY * (unsigned long long)(zHi - zLo + 2);  // cells in the host arrays
+    if (Nh >= (1ull << 31)) return fail(LBGPU_EINVAL, "lbGpuInit: %llu cells exceed the 2^31 index range", Nh);
+    bool anyDyn = false, anyGas = false, anyIface = false, anySlip = false;
+    for (unsigned long long i = 0; i < Nh; ++i) {
         const int t = type_flags[i] & LBGPU_TYPE_MASK;
         if (t == T_CURVED) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: curved walls (type 9, LB.cpp:1278-1319) are not implemented");
-        if (t == 1 || t > 9) return fail(LBGPU_EINVAL, "lbGpuInit: cell %u has undefined type %d", i, t);
+        if (t == 1 || t > 9) return fail(LBGPU_EINVAL, "lbGpuInit: cell %llu has undefined type %d", i, t);
         anyDyn |= (t == T_DYN_WALL || t == T_SLIP_DYN);
+        anySlip |= (t == T_SLIP_STAT || t == T_SLIP_DYN);
         anyGas |= (t == T_GAS);
         anyIface |= (t == T_INTERFACE);
     }
@@ -346,7 +693,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     LbGpuHandle* h = new (std::nothrow) LbGpuHandle();
     if (!h) return fail(LBGPU_EINVAL, "out of host memory");
     h->prm = *prm;
-    h->N = N;
+    h->nSlabsGlobal = G; h->firstSlab = first;
     int rc = 0;
     auto body = [&]() -> int {
         if (prm->device >= 0) {
@@ -359,88 +706,48 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         CU(cudaEventCreate(&h->evB));
         h->kev0.resize(LbGpuHandle::KEV); h->kev1.resize(LbGpuHandle::KEV);
         for (uint32_t k = 0; k < LbGpuHandle::KEV; ++k) { CU(cudaEventCreate(&h->kev0[k])); CU(cudaEventCreate(&h->kev1[k])); }
-        h->stride = ((size_t)N + 31) / 32 * 32;
-        h->blocks = (N + BLOCK - 1) / BLOCK;
         h->fs = prm->freeSurface != 0;
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);
         h->dynWall = anyDyn;
+        h->slip = anySlip;
         h->macroAlways = h->fs || anyDyn || anyGas || anyIface;
         // measureUnits::setComposite (node.cpp:476-488)
         const double L = prm->unitLength, Tm = prm->unitTime, D = prm->unitDensity;
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
         h->uForce = D * L * L * L * L / Tm / Tm; h->uTorque = D * L * L * L * L * L / Tm / Tm;
-
-        CU(h->fA.alloc(h->stride * Q)); CU(h->fB.alloc(h->stride * Q));
-        CU(h->n.alloc(N)); CU(h->ux.alloc(N)); CU(h->uy.alloc(N)); CU(h->uz.alloc(N));
-        CU(h->mass.alloc(N)); CU(h->visc.alloc(N)); CU(h->shearRate.alloc(N));
-        CU(h->hfx.alloc(N)); CU(h->hfy.alloc(N)); CU(h->hfz.alloc(N));
-        CU(h->type0.alloc(N)); CU(h->solidIndex.alloc(N));
-        if (h->fs) { CU(h->type1.alloc(N)); CU(h->mark.alloc(N)); CU(h->newMass.alloc(N)); }
-        const size_t nPartial = (size_t)h->blocks * (size_t)(3 > 1 + 3 * prm->nWalls ? 3 : 1 + 3 * prm->nWalls);
-        CU(h->partial.alloc(nPartial));
-        CU(h->sums.alloc(8 + 3 * 64)); CU(h->scal.alloc(8)); CU(h->wallOut.alloc(3 * 64));
-        CU(h->counters.alloc(8)); CU(h->status.alloc(4));
         CU(cudaMallocHost((void**)&h->pinnedStatus, 64));
-        cudaStream_t s = h->stream;
-        CU(cudaMemsetAsync(h->shearRate.p, 0, sizeof(double) * N, s));
-        CU(cudaMemsetAsync(h->hfx.p, 0, sizeof(double) * N, s));
-        CU(cudaMemsetAsync(h->hfy.p, 0, sizeof(double) * N, s));
-        CU(cudaMemsetAsync(h->hfz.p, 0, sizeof(double) * N, s));
-        CU(cudaMemsetAsync(h->sums.p, 0, sizeof(double) * h->sums.n, s));
-        CU(cudaMemsetAsync(h->scal.p, 0, sizeof(double) * 8, s));
-        CU(cudaMemsetAsync(h->counters.p, 0, sizeof(unsigned long long) * 8, s));
-        CU(cudaMemsetAsync(h->status.p, 0, sizeof(uint32_t) * 4, s));
-        CU(cudaMemsetAsync(h->partial.p, 0, sizeof(double) * nPartial, s));
-
-        Dev& d = h->dev;
-        memset(&d, 0, sizeof d);
-        d.X = prm->size[0]; d.Y = prm->size[1]; d.Z = prm->size[2]; d.N = N; d.stride = h->stride;
-        d.divX = make_div((uint32_t)d.X); d.divXY = make_div((uint32_t)d.X * (uint32_t)d.Y);
-        for (int k = 0; k < 6; ++k) d.per[k] = prm->boundary[k] == T_PERIODIC;
-        d.solidIndex = h->solidIndex.p;
-        d.n = h->n.p; d.ux = h->ux.p; d.uy = h->uy.p; d.uz = h->uz.p;
-        d.mass = h->mass.p; d.newMass = h->newMass.p; d.visc = h->visc.p; d.shearRate = h->shearRate.p;
-        d.hfx = h->hfx.p; d.hfy = h->hfy.p; d.hfz = h->hfz.p;
-        for (int k = 0; k < 3; ++k) { d.lbF[k] = prm->forceField ? prm->lbF[k] : 0.0; d.lbFInit[k] = prm->lbF[k]; }
-        d.initVisc = prm->initDynVisc; d.plasticVisc = prm->plasticVisc; d.yieldStress = prm->yieldStress;
-        d.turbConst = prm->turbConst;
-        d.S1 = prm->slipCoefficient; d.S2 = 1.0 - prm->slipCoefficient;
-        d.uAngVel = h->uAngVel;
-        d.nonNewtonian = prm->nonNewtonian; d.turbulence = prm->turbulence;
-        d.nWalls = prm->nWalls;
-        d.partial = h->partial.p; d.status = h->status.p;
-
-        // staged upload: host (pageable) -> device scratch -> SoA
-        CU(cudaMemcpyAsync(h->type0.p, type_flags, N, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->solidIndex.p, solidIndex, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->n.p, n, sizeof(double) * N, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->mass.p, mass, sizeof(double) * N, cudaMemcpyHostToDevice, s));
-        CU(cudaMemcpyAsync(h->visc.p, visc, sizeof(double) * N, cudaMemcpyHostToDevice, s));
-        {
-            DevBuf<double> tmp;
-            CU(tmp.alloc((size_t)3 * N));
-            CU(cudaMemcpyAsync(tmp.p, u, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, s));
-            k_split3<<<h->blocks, BLOCK, 0, s>>>(N, tmp.p, h->ux.p, h->uy.p, h->uz.p);
-            CU(cudaStreamSynchronize(s));
+        for (int k = 0; k < nLocal; ++k) {
+            h->slabs.emplace_back(new Slab());
+            Slab* s = h->slabs.back().get();
+            s->index = first + k;
+            int32_t zb, ze;
+            lbGpuSlabRange(prm->size[2], G, first + k, &zb, &ze);
+            s->zBegin = zb; s->zEnd = ze;
+            if (int r = build_slab(h, s, zLo - 1, type_flags, solidIndex, f, n, u, mass, visc)) return r;
         }
-        Dev dd = dev_for(h, false);
-        if (f) {
-            // upload the populations in slices to bound the staging memory
-            DevBuf<double> tmp;
-            CU(tmp.alloc((size_t)Q * N));
-            CU(cudaMemcpyAsync(tmp.p, f, sizeof(double) * Q * N, cudaMemcpyHostToDevice, s));
-            k_upload_f<<<h->blocks, BLOCK, 0, s>>>(dd, tmp.p, h->fA.p, h->fB.p);
-            CU(cudaStreamSynchronize(s));
-        } else {
-            k_upload_f<<<h->blocks, BLOCK, 0, s>>>(dd, nullptr, h->fA.p, h->fB.p);
+        // ghosts of every field, both population buffers
+        if (int r = exchange(h, G_POPS | G_POPS_SRC | G_TYPE | G_SOLID | G_MASS | G_MACRO | G_VISC | G_HF)) return r;
+        cudaStream_t st = h->stream;
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            if (h->fs) CU(cudaMemcpyAsync(s->type1.p, s->type0.p, s->N, cudaMemcpyDeviceToDevice, st));
+            if (!h->fs) {
+                // cell activity never changes without a free surface: the bulk bitmap is built once
+                CU(s->bulk.alloc((size_t)s->blocks * (BLOCK / 32) + 1));
+                CU(cudaMemsetAsync(s->bulk.p, 0, sizeof(uint32_t) * s->bulk.n, st));
+                k_build_bulk<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
+                ++h->launches;
+                s->dev.bulk = s->bulk.p;
+            }
+            // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
+            k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
+            ++h->launches;
         }
-        h->launches += 2;
-        // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
-        k_count<<<h->blocks, BLOCK, 0, s>>>(dd, h->counters.p + 1);
-        CU(cudaMemcpyAsync(h->counters.p, h->counters.p + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
-        ++h->launches;
-        CU(cudaStreamSynchronize(s));
+        Slab* s0 = h->slabs[0].get();
+        for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_counters<<<1, 32, 0, st>>>(s0->counters.p + 1, h->slabs[k]->counters.p + 1, 3); ++h->launches; }
+        for (auto& sp : h->slabs) CU(cudaMemcpyAsync(sp->counters.p, s0->counters.p + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
         return 0;
     };
@@ -522,11 +829,12 @@ int lbGpuParticleForces(LbGpuHandle* h, double* FHydro, double* MHydro, double* 
     if (!h) return fail(LBGPU_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
     if (int rc = check_status(h)) return rc;
+    Slab* s0 = h->slabs[0].get();
     const uint32_t nE = h->nElmts;
     if (nE && (FHydro || MHydro || fluidVolume)) {
         std::vector<double> tmp((size_t)7 * nE, 0.0);
         if (h->lastStepCoupled) {
-            CU(cudaMemcpyAsync(tmp.data(), h->elemOut.p, sizeof(double) * 7 * nE, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(tmp.data(), s0->elemOut.p, sizeof(double) * 7 * nE, cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
         }
         for (uint32_t e = 0; e < nE; ++e) {
@@ -541,7 +849,7 @@ int lbGpuParticleForces(LbGpuHandle* h, double* FHydro, double* MHydro, double* 
         const int nW = h->prm.nWalls;
         std::vector<double> tmp((size_t)3 * nW, 0.0);
         if (h->dynWall && h->steps > 0) {
-            CU(cudaMemcpyAsync(tmp.data(), h->sums.p + 5, sizeof(double) * 3 * nW, cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(tmp.data(), s0->sums.p + 5, sizeof(double) * 3 * nW, cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
         }
         for (int k = 0; k < 3 * nW; ++k) wallFHydro[k] = tmp[k] * h->uForce;  // LB.cpp:1485-1487
@@ -554,60 +862,78 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
     if (!h) return fail(LBGPU_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
     if (int rc = check_status(h)) return rc;
-    cudaStream_t s = h->stream;
-    const uint32_t N = h->N, B = h->blocks;
-    Dev d = dev_for(h, false);
+    cudaStream_t st = h->stream;
+    const int zLoHost = h->slabs[0]->zBegin - 1;
     if (!h->macroValid && (n || u)) {
         // n and the shifted u of the last step, recomputed from the previous population buffer
-        Dev dm = d;
-        dm.fsrc = h->fbuf(h->cur ^ 1);
-        const bool force = h->force || h->lastStepCoupled, couple = h->lastStepCoupled;
-        dm.pull = !h->lastStepFirst;
-        if (couple) k_macro<true, true><<<B, BLOCK, 0, s>>>(dm);
-        else if (force) k_macro<true, false><<<B, BLOCK, 0, s>>>(dm);
-        else k_macro<false, false><<<B, BLOCK, 0, s>>>(dm);
-        ++h->launches;
+        for (auto& sp : h->slabs) {
+            Dev dm = dev_for(h, sp.get());
+            dm.fsrc = sp->fbuf(h->cur ^ 1);
+            for (int k = 0; k < Q; ++k) dm.fsrcK[k] = dm.fsrc + (size_t)k * sp->stride;
+            const bool force = h->force || h->lastStepCoupled, couple = h->lastStepCoupled;
+            dm.pull = !h->lastStepFirst;
+            const uint32_t B = own_blocks(sp.get());
+            if (couple) k_macro<true, true><<<B, BLOCK, 0, st>>>(dm);
+            else if (force) k_macro<true, false><<<B, BLOCK, 0, st>>>(dm);
+            else k_macro<false, false><<<B, BLOCK, 0, st>>>(dm);
+            ++h->launches;
+        }
         h->macroValid = true;
     }
-    if (type_flags) {
-        DevBuf<uint8_t> tmp;
-        CU(tmp.alloc(N));
-        k_fetch_types<<<B, BLOCK, 0, s>>>(d, tmp.p);
-        CU(cudaMemcpyAsync(type_flags, tmp.p, N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        const uint32_t B = s->blocks;
+        // every slab writes the planes it owns (plus the true shell planes at the ends of the lattice)
+        const uint32_t p0 = s->remoteLo ? 1u : 0u, p1 = (uint32_t)s->dev.Z - (s->remoteHi ? 1u : 0u);
+        const size_t cOff = (size_t)p0 * s->XY, cCnt = (size_t)(p1 - p0) * s->XY;
+        const size_t hBase = (size_t)(s->zBegin - 1 - zLoHost) * s->XY;  // host index of the slab's local cell 0
+        const size_t hOff = hBase + cOff;
+        Dev d = dev_all(h, s);
+        if (type_flags) {
+            DevBuf<uint8_t> tmp;
+            CU(tmp.alloc(s->N));
+            k_fetch_types<<<B, BLOCK, 0, st>>>(d, tmp.p);
+            CU(cudaMemcpyAsync(type_flags + hOff, tmp.p + cOff, cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (uint32_t k = 0; k < s->nGhost; ++k) type_flags[hBase + s->ghostIdx[k]] = s->ghostType[k];
+        }
+        if (solidIndex) {
+            CU(cudaMemcpyAsync(solidIndex + hOff, s->solidIndex.p + cOff, sizeof(uint32_t) * cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (uint32_t k = 0; k < s->nGhost; ++k) solidIndex[hBase + s->ghostIdx[k]] = s->ghostSolid[k];
+        }
+        DevBuf<double> tmp;
+        if (n || u || mass || visc || shearRate || hydroForce) CU(tmp.alloc((size_t)3 * s->N));
+        auto scalar = [&](const double* src, double* dst, int activeOnly) -> int {
+            k_fetch_scalar<<<B, BLOCK, 0, st>>>(d, src, tmp.p, activeOnly);
+            CU(cudaMemcpyAsync(dst + hOff, tmp.p + cOff, sizeof(double) * cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            return 0;
+        };
+        int rc;
+        if (n && (rc = scalar(s->n.p, n, 0))) return rc;
+        if (mass && (rc = scalar(s->mass.p, mass, 0))) return rc;
+        if (visc && (rc = scalar(s->visc.p, visc, 0))) return rc;
+        if (shearRate && (rc = scalar(s->shearRate.p, shearRate, 1))) return rc;
+        if (u) {
+            k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->ux.p, s->uy.p, s->uz.p, tmp.p, 0);
+            CU(cudaMemcpyAsync(u + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        if (hydroForce) {
+            k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->hfx.p, s->hfy.p, s->hfz.p, tmp.p, 1);
+            CU(cudaMemcpyAsync(hydroForce + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        if (f) {
+            DevBuf<double> tf;
+            CU(tf.alloc((size_t)Q * s->N));
+            k_download_f<<<B, BLOCK, 0, st>>>(d, s->fbuf(h->cur), tf.p);
+            CU(cudaMemcpyAsync(f + (size_t)Q * hOff, tf.p + (size_t)Q * cOff, sizeof(double) * Q * cCnt, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
     }
-    if (solidIndex) CU(cudaMemcpyAsync(solidIndex, h->solidIndex.p, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, s));
-    DevBuf<double> tmp;
-    if (n || u || mass || visc || shearRate || hydroForce) CU(tmp.alloc((size_t)3 * N));
-    auto scalar = [&](const double* src, double* dst, int activeOnly) -> int {
-        k_fetch_scalar<<<B, BLOCK, 0, s>>>(d, src, tmp.p, activeOnly);
-        CU(cudaMemcpyAsync(dst, tmp.p, sizeof(double) * N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-        return 0;
-    };
-    int rc;
-    if (n && (rc = scalar(h->n.p, n, 0))) return rc;
-    if (mass && (rc = scalar(h->mass.p, mass, 0))) return rc;
-    if (visc && (rc = scalar(h->visc.p, visc, 0))) return rc;
-    if (shearRate && (rc = scalar(h->shearRate.p, shearRate, 1))) return rc;
-    if (u) {
-        k_fetch_vec<<<B, BLOCK, 0, s>>>(d, h->ux.p, h->uy.p, h->uz.p, tmp.p, 0);
-        CU(cudaMemcpyAsync(u, tmp.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    if (hydroForce) {
-        k_fetch_vec<<<B, BLOCK, 0, s>>>(d, h->hfx.p, h->hfy.p, h->hfz.p, tmp.p, 1);
-        CU(cudaMemcpyAsync(hydroForce, tmp.p, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    if (f) {
-        DevBuf<double> tf;
-        CU(tf.alloc((size_t)Q * N));
-        k_download_f<<<B, BLOCK, 0, s>>>(d, h->fbuf(h->cur), tf.p);
-        CU(cudaMemcpyAsync(f, tf.p, sizeof(double) * Q * N, cudaMemcpyDeviceToHost, s));
-        CU(cudaStreamSynchronize(s));
-    }
-    CU(cudaStreamSynchronize(s));
+    CU(cudaStreamSynchronize(st));
     CU(cudaGetLastError());
     return LBGPU_OK;
 }
@@ -615,14 +941,18 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
 int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
     if (!h || !counts) return fail(LBGPU_EINVAL, "null argument");
     CU(cudaSetDevice(h->device));
-    Dev d = dev_for(h, false);
-    CU(cudaMemsetAsync(h->counters.p + 1, 0, sizeof(unsigned long long) * 3, h->stream));
-    k_count<<<h->blocks, BLOCK, 0, h->stream>>>(d, h->counters.p + 1);
-    ++h->launches;
-    unsigned long long tmp[3];
-    CU(cudaMemcpyAsync(tmp, h->counters.p + 1, sizeof tmp, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    counts[0] = tmp[0]; counts[1] = tmp[1]; counts[2] = tmp[2]; counts[3] = h->steps;
+    unsigned long long tot[3] = { 0, 0, 0 };
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        CU(cudaMemsetAsync(s->counters.p + 1, 0, sizeof(unsigned long long) * 3, h->stream));
+        k_count<<<own_blocks(s), BLOCK, 0, h->stream>>>(dev_for(h, s), s->counters.p + 1);
+        ++h->launches;
+        unsigned long long tmp[3];
+        CU(cudaMemcpyAsync(tmp, s->counters.p + 1, sizeof tmp, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < 3; ++k) tot[k] += tmp[k];
+    }
+    counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2]; counts[3] = h->steps;
     return LBGPU_OK;
 }
 
@@ -630,6 +960,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     if (!h) return LBGPU_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    h->slabs.clear();
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
     for (cudaEvent_t e : h->kev0) if (e) cudaEventDestroy(e);

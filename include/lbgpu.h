@@ -61,10 +61,12 @@ typedef struct {
     double unitLength, unitTime, unitDensity; /* LB.cpp:93-98; composites as measureUnits::setComposite */
     int32_t nWalls;       /* dem.walls.size(): length of the wall-force output */
     int32_t device;       /* CUDA device ordinal; -1 = current device */
-    /* slab decomposition (multi-GPU): this handle owns global planes [slabBegin, slabEnd) along
-     * slabAxis (0,1,2) plus one ghost plane on each cut side. nSlabs<=1: whole domain. */
-    int32_t slabAxis, nSlabs, slabIndex;
-    int32_t reserved[5];
+    /* slab decomposition: the interior planes 1..size[2]-2 are cut along z (slabAxis = 2, the slowest
+     * index, so halo planes are contiguous) into nSlabs slabs (lbGpuSlabRange). This handle owns slabs
+     * [slabIndex, slabIndex + nLocalSlabs); its host arrays cover the planes of those slabs plus one
+     * plane below and above.  nSlabs <= 1: the whole lattice in one slab. */
+    int32_t slabAxis, nSlabs, slabIndex, nLocalSlabs;
+    int32_t reserved[4];
 } LbGpuParams;
 
 typedef struct {
@@ -82,6 +84,8 @@ typedef struct LbGpuHandle LbGpuHandle;
 const char* lbGpuLastError(void);
 int lbGpuAbiVersion(void);
 int lbGpuDeviceCount(void);
+/* global planes [zBegin, zEnd) owned by slab `slab` of `nSlabs` for a lattice of sizeZ planes */
+int lbGpuSlabRange(int32_t sizeZ, int32_t nSlabs, int32_t slab, int32_t* zBegin, int32_t* zEnd);
 
 /* Upload the state LB::latticeBolzmannInit produced.
  *   type_flags  N bytes: t | p<<4 | node<<5
