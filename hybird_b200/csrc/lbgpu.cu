@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <new>
@@ -83,7 +84,8 @@ struct Slab {
     Dev dev;                             // template for kernel parameters (pointers filled per launch)
     DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
     DevBuf<uint8_t> type0, type1, mark;
-    DevBuf<uint32_t> solidIndex, bulk;
+    DevBuf<uint32_t> solidIndex, bulk, tiles;
+    uint32_t nTiles = 0;
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
     DevBuf<double> partial, sums, scal, elemOut;
@@ -125,6 +127,8 @@ struct LbGpuHandle {
     static constexpr uint32_t KEV = 512;
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
+    int numSMs = 148, tileCtasPerSM = 0;
+    bool useTiles = true;
 };
 
 namespace {
@@ -151,6 +155,16 @@ StepKernel select_step(bool force, bool shear, bool macro, bool couple, bool fsO
     // the full variants always carry the force path (exact when the force is zero)
     if (couple) return shear ? pick_step<true, true, true, true>(fsOn, dyn) : pick_step<true, false, true, true>(fsOn, dyn);
     return shear ? pick_step<true, true, true, false>(fsOn, dyn) : pick_step<true, false, true, false>(fsOn, dyn);
+}
+
+StepKernel select_tile(bool force, bool shear, bool macro, bool couple) {
+    if (couple) {
+        if (macro) return shear ? k_step_tile<true, true, true, true> : k_step_tile<true, false, true, true>;
+        return shear ? k_step_tile<true, true, false, true> : k_step_tile<true, false, false, true>;
+    }
+    if (macro) return shear ? k_step_tile<true, true, true, false> : k_step_tile<true, false, true, false>;
+    if (force) return shear ? k_step_tile<true, true, false, false> : k_step_tile<true, false, false, false>;
+    return shear ? k_step_tile<false, true, false, false> : k_step_tile<false, false, false, false>;
 }
 
 // kernel parameters of slab s for the current buffers; per-cell kernels cover the owned planes
@@ -423,6 +437,16 @@ int lb_step(LbGpuHandle* h) {
     int rc;
     const int nSums = 1 + 3 * h->prm.nWalls;
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall);
+    // the asynchronously fed tile kernel serves every step but the first (which collides in place) of a lattice
+    // without free surface or moving walls
+    const bool tiled = h->useTiles && !first && !fsOn && !h->dynWall;
+    StepKernel kt = tiled ? select_tile(h->force || macro, h->shear, macro, couple) : nullptr;
+    if (tiled && h->tileCtasPerSM == 0) {
+        int nb = 0;
+        CU(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kt, BLOCK, TILE_SMEM_BYTES));
+        h->tileCtasPerSM = nb > 0 ? nb : 1;
+    }
     const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
@@ -434,7 +458,13 @@ int lb_step(LbGpuHandle* h) {
         if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
         d.pull = !first;
         d.pStride = s->blocks; d.pBase = 0;
-        k<<<own_blocks(s), BLOCK, 0, st>>>(d);
+        if (tiled && s->nTiles) {
+            d.tiles = s->tiles.p; d.nTiles = s->nTiles;
+            const uint32_t cap = (uint32_t)(h->numSMs * h->tileCtasPerSM);
+            kt<<<s->nTiles < cap ? s->nTiles : cap, BLOCK, TILE_SMEM_BYTES, st>>>(d);
+        } else {
+            k<<<own_blocks(s), BLOCK, 0, st>>>(d);
+        }
         ++h->launches;
     }
     CU(cudaEventRecord(h->kev1[ke], st));
@@ -515,8 +545,10 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
     CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
     CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
-    CU(s->type0.alloc(N)); CU(s->solidIndex.alloc(N));
-    if (h->fs) { CU(s->type1.alloc(N)); CU(s->mark.alloc(N)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, N, st)); }
+    const size_t NT = ((size_t)N + TILE - 1) / TILE * TILE + TILE;  // tile loads read whole tiles
+    CU(s->type0.alloc(NT)); CU(s->solidIndex.alloc(N));
+    CU(cudaMemsetAsync(s->type0.p, T_STAT_WALL, NT, st));
+    if (h->fs) { CU(s->type1.alloc(NT)); CU(s->mark.alloc(N)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, N, st)); }
     const int nSums = 1 + 3 * prm->nWalls;
     const size_t nPartial = (size_t)s->blocks * (size_t)(3 > nSums ? 3 : nSums);
     CU(s->partial.alloc(nPartial));
@@ -701,6 +733,8 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
             CU(cudaSetDevice(prm->device));
         }
         CU(cudaGetDevice(&h->device));
+        CU(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->device));
+        if (const char* e = getenv("LBGPU_NO_TILES")) h->useTiles = !(e[0] == '1');
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
@@ -739,6 +773,22 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
                 k_build_bulk<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
                 ++h->launches;
                 s->dev.bulk = s->bulk.p;
+                // tiles with at least one owned active cell, ascending (cell activity is static here)
+                DevBuf<uint8_t> flags;
+                CU(flags.alloc(s->blocks));
+                k_tile_flags<<<s->blocks, BLOCK, 0, st>>>(dev_for(h, s), flags.p);
+                ++h->launches;
+                std::vector<uint8_t> hf(s->blocks);
+                CU(cudaMemcpyAsync(hf.data(), flags.p, s->blocks, cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                std::vector<uint32_t> list;
+                for (uint32_t t = 0; t < s->blocks; ++t) if (hf[t]) list.push_back(t);
+                s->nTiles = (uint32_t)list.size();
+                if (s->nTiles) {
+                    CU(s->tiles.alloc(s->nTiles));
+                    CU(cudaMemcpyAsync(s->tiles.p, list.data(), 4 * (size_t)s->nTiles, cudaMemcpyHostToDevice, st));
+                    CU(cudaStreamSynchronize(st));
+                }
             }
             // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
