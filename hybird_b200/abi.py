@@ -33,7 +33,7 @@ class LbGpuParams(C.Structure):
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuStep", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
-           "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuFinalize")
+           "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize")
 
 _lib = None
 
@@ -79,6 +79,8 @@ def load_library(build_if_missing=True):
     L.lbGpuLastKernelMs.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]
     L.lbGpuLaunchCount.restype = C.c_int
     L.lbGpuLaunchCount.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.lbGpuSelfTest.restype = C.c_int
+    L.lbGpuSelfTest.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64 * 3)]
     L.lbGpuFinalize.restype = C.c_int
     L.lbGpuFinalize.argtypes = [vp]
     _lib = L

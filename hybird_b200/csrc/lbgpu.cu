@@ -128,7 +128,7 @@ struct LbGpuHandle {
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
     int numSMs = 148, tileCtasPerSM = 0;
-    bool useTiles = true;
+    bool useTiles = false;
 };
 
 namespace {
@@ -168,11 +168,21 @@ StepKernel select_tile(bool force, bool shear, bool macro, bool couple) {
 }
 
 // kernel parameters of slab s for the current buffers; per-cell kernels cover the owned planes
+// source populations of a launch: buffer `buf`, pulled through the links (pull) or taken in place
+void set_src(Dev& d, Slab* s, int buf, bool pull) {
+    d.fsrc = s->fbuf(buf);
+    d.pull = pull ? 1 : 0;
+    for (int k = 0; k < Q; ++k) {
+        d.fsrcK[k] = d.fsrc + (size_t)k * s->stride;
+        d.fsrcP[k] = d.fsrcK[k] - (pull ? d.off[k] : 0);
+    }
+}
+
 Dev dev_for(LbGpuHandle* h, Slab* s) {
     Dev d = s->dev;
-    d.fsrc = s->fbuf(h->cur);
+    set_src(d, s, h->cur, h->steps > 0);
     d.fdst = s->fbuf(h->cur ^ 1);
-    for (int k = 0; k < Q; ++k) { d.fsrcK[k] = d.fsrc + (size_t)k * s->stride; d.fdstK[k] = d.fdst + (size_t)k * s->stride; }
+    for (int k = 0; k < Q; ++k) d.fdstK[k] = d.fdst + (size_t)k * s->stride;
     d.typeOld = s->tbuf(h->curType);
     d.type = s->tbuf(h->curType);
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
@@ -328,7 +338,6 @@ int free_surface_step(LbGpuHandle* h) {
     auto fsdev = [&](Slab* s) {
         Dev d = dev_for(h, s);
         d.type = s->tbuf(h->curType ^ 1);
-        d.pull = h->steps > 0;
         return d;
     };
     for (auto& sp : h->slabs) {
@@ -456,7 +465,6 @@ int lb_step(LbGpuHandle* h) {
         Dev d = dev_for(h, s);
         // the streaming being evaluated happened under the type map of before this cycle's free-surface step
         if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
-        d.pull = !first;
         d.pStride = s->blocks; d.pBase = 0;
         if (tiled && s->nTiles) {
             d.tiles = s->tiles.p; d.nTiles = s->nTiles;
@@ -734,7 +742,8 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         }
         CU(cudaGetDevice(&h->device));
         CU(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->device));
-        if (const char* e = getenv("LBGPU_NO_TILES")) h->useTiles = !(e[0] == '1');
+        // the cp.async.bulk fed tile kernel is the alternative bulk path (A/B switch; see DESIGN.md for the measurements)
+        if (const char* e = getenv("LBGPU_TILES")) h->useTiles = (e[0] == '1');
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
@@ -918,10 +927,8 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         // n and the shifted u of the last step, recomputed from the previous population buffer
         for (auto& sp : h->slabs) {
             Dev dm = dev_for(h, sp.get());
-            dm.fsrc = sp->fbuf(h->cur ^ 1);
-            for (int k = 0; k < Q; ++k) dm.fsrcK[k] = dm.fsrc + (size_t)k * sp->stride;
+            set_src(dm, sp.get(), h->cur ^ 1, !h->lastStepFirst);
             const bool force = h->force || h->lastStepCoupled, couple = h->lastStepCoupled;
-            dm.pull = !h->lastStepFirst;
             const uint32_t B = own_blocks(sp.get());
             if (couple) k_macro<true, true><<<B, BLOCK, 0, st>>>(dm);
             else if (force) k_macro<true, false><<<B, BLOCK, 0, st>>>(dm);
@@ -1003,6 +1010,21 @@ int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
         for (int k = 0; k < 3; ++k) tot[k] += tmp[k];
     }
     counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2]; counts[3] = h->steps;
+    return LBGPU_OK;
+}
+
+int lbGpuSelfTest(uint64_t count, uint64_t seed, uint64_t result[3]) {
+    if (!result) return fail(LBGPU_EINVAL, "null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(LBGPU_ENODEVICE, "lbGpuSelfTest: no CUDA device"); }
+    DevBuf<unsigned long long> out;
+    CU(out.alloc(3));
+    CU(cudaMemset(out.p, 0, 3 * sizeof(unsigned long long)));
+    k_selftest_div<<<148 * 8, 256>>>(count, seed, out.p);
+    CU(cudaGetLastError());
+    unsigned long long r[3];
+    CU(cudaMemcpy(r, out.p, sizeof r, cudaMemcpyDeviceToHost));
+    result[0] = r[0]; result[1] = r[1]; result[2] = r[2];
     return LBGPU_OK;
 }
 

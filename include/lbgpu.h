@@ -125,6 +125,10 @@ int lbGpuLastStepMs(LbGpuHandle* h, float* ms);
 int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches);
 /* number of kernels this handle launched so far */
 int lbGpuLaunchCount(LbGpuHandle* h, uint64_t* launches);
+/* device self-test of the engine's shared-reciprocal fp64 division against IEEE division on `count`
+ * pseudo-random operand pairs: result[0] = mismatches (must be 0), [1] = quotients compared, [2] = operand
+ * pairs outside the fast-path domain (handled by the ordinary division in the kernels) */
+int lbGpuSelfTest(uint64_t count, uint64_t seed, uint64_t result[3]);
 int lbGpuFinalize(LbGpuHandle* h);
 
 #ifdef __cplusplus
