@@ -84,8 +84,7 @@ struct Slab {
     Dev dev;                             // template for kernel parameters (pointers filled per launch)
     DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
     DevBuf<uint8_t> type0, type1, mark;
-    DevBuf<uint32_t> solidIndex, bulk, tiles;
-    uint32_t nTiles = 0;
+    DevBuf<uint32_t> solidIndex, bulk;
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
     DevBuf<double> partial, sums, scal, elemOut;
@@ -127,8 +126,7 @@ struct LbGpuHandle {
     static constexpr uint32_t KEV = 512;
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
-    int numSMs = 148, tileCtasPerSM = 0;
-    bool useTiles = false;
+    int numSMs = 148;
 };
 
 namespace {
@@ -157,17 +155,6 @@ StepKernel select_step(bool force, bool shear, bool macro, bool couple, bool fsO
     return shear ? pick_step<true, true, true, false>(fsOn, dyn) : pick_step<true, false, true, false>(fsOn, dyn);
 }
 
-StepKernel select_tile(bool force, bool shear, bool macro, bool couple) {
-    if (couple) {
-        if (macro) return shear ? k_step_tile<true, true, true, true> : k_step_tile<true, false, true, true>;
-        return shear ? k_step_tile<true, true, false, true> : k_step_tile<true, false, false, true>;
-    }
-    if (macro) return shear ? k_step_tile<true, true, true, false> : k_step_tile<true, false, true, false>;
-    if (force) return shear ? k_step_tile<true, true, false, false> : k_step_tile<true, false, false, false>;
-    return shear ? k_step_tile<false, true, false, false> : k_step_tile<false, false, false, false>;
-}
-
-// kernel parameters of slab s for the current buffers; per-cell kernels cover the owned planes
 // source populations of a launch: buffer `buf`, pulled through the links (pull) or taken in place
 void set_src(Dev& d, Slab* s, int buf, bool pull) {
     d.fsrc = s->fbuf(buf);
@@ -259,14 +246,16 @@ int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32
 }
 
 // typeNew: the type buffer being written by a free-surface step (curType^1) instead of the current one
-int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false) {
+// popsPushed: the destination populations of the local mirrors were already written by the step kernel (ghost push)
+int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushed = false) {
     cudaStream_t st = h->stream;
+    const uint32_t local = popsPushed ? (what & ~(uint32_t)G_POPS) : what;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
-        if (!s->nGhost) continue;
+        if (!s->nGhost || !local) continue;
         Dev d = dev_for(h, s);
         if (typeNew) d.type = s->tbuf(h->curType ^ 1);
-        k_fill_ghosts<<<(s->nGhost + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d, s->gDst.p, s->gSrc.p, s->gPop.p, 0, s->nGhost, what, s->mark.p);
+        k_fill_ghosts<<<(s->nGhost + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d, s->gDst.p, s->gSrc.p, s->gPop.p, 0, s->nGhost, local, s->mark.p);
         ++h->launches;
     }
     const int G = (int)h->slabs.size();
@@ -446,16 +435,6 @@ int lb_step(LbGpuHandle* h) {
     int rc;
     const int nSums = 1 + 3 * h->prm.nWalls;
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall);
-    // the asynchronously fed tile kernel serves every step but the first (which collides in place) of a lattice
-    // without free surface or moving walls
-    const bool tiled = h->useTiles && !first && !fsOn && !h->dynWall;
-    StepKernel kt = tiled ? select_tile(h->force || macro, h->shear, macro, couple) : nullptr;
-    if (tiled && h->tileCtasPerSM == 0) {
-        int nb = 0;
-        CU(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TILE_SMEM_BYTES));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kt, BLOCK, TILE_SMEM_BYTES));
-        h->tileCtasPerSM = nb > 0 ? nb : 1;
-    }
     const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
@@ -466,19 +445,13 @@ int lb_step(LbGpuHandle* h) {
         // the streaming being evaluated happened under the type map of before this cycle's free-surface step
         if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
         d.pStride = s->blocks; d.pBase = 0;
-        if (tiled && s->nTiles) {
-            d.tiles = s->tiles.p; d.nTiles = s->nTiles;
-            const uint32_t cap = (uint32_t)(h->numSMs * h->tileCtasPerSM);
-            kt<<<s->nTiles < cap ? s->nTiles : cap, BLOCK, TILE_SMEM_BYTES, st>>>(d);
-        } else {
-            k<<<own_blocks(s), BLOCK, 0, st>>>(d);
-        }
+        k<<<own_blocks(s), BLOCK, 0, st>>>(d);
         ++h->launches;
     }
     CU(cudaEventRecord(h->kev1[ke], st));
     ++h->kevCount;
     h->typesFlipped = false;
-    if ((rc = exchange(h, G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u)))) return rc;
+    if ((rc = exchange(h, G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u), false, true))) return rc;
     Slab* s0 = h->slabs[0].get();
     if (h->dynWall) {
         for (auto& sp : h->slabs) {
@@ -538,7 +511,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     s->N = s->XY * (uint32_t)Zl;
     const uint32_t N = s->N;
     s->stride = ((size_t)N + 31) / 32 * 32;
-    // tile loads of the async-copy kernel reach one plane + one row + 2 cells beyond either end of a population plane
+    // the speculative pulls of the step kernel reach one plane + one row + 1 cell (+ the tail of the last block) beyond
+    // either end of a population plane
     s->pad = ((size_t)s->XY + X + 2 + 511) / 32 * 32;
     s->blocks = (N + BLOCK - 1) / BLOCK;
     const bool perZ = prm->boundary[4] == T_PERIODIC;
@@ -553,7 +527,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
     CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
     CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
-    const size_t NT = ((size_t)N + TILE - 1) / TILE * TILE + TILE;  // tile loads read whole tiles
+    const size_t NT = ((size_t)N + BLOCK - 1) / BLOCK * BLOCK + BLOCK;  // the last block reads whole
     CU(s->type0.alloc(NT)); CU(s->solidIndex.alloc(N));
     CU(cudaMemsetAsync(s->type0.p, T_STAT_WALL, NT, st));
     if (h->fs) { CU(s->type1.alloc(NT)); CU(s->mark.alloc(N)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, N, st)); }
@@ -579,6 +553,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     for (int k = 0; k < 4; ++k) d.ghost[k] = prm->boundary[k] == T_PERIODIC;
     d.ghost[4] = s->remoteLo || perZ; d.ghost[5] = s->remoteHi || perZ;
     d.perZ = perZ; d.zOff = s->zBegin - 1; d.gZ = gZ;
+    // periodic wraps served inside this lattice: the step kernel pushes into the mirroring ghost cells itself
+    d.push = (d.ghost[0] ? 1 : 0) | (d.ghost[2] ? 2 : 0) | ((perZ && !s->remoteLo) ? 4 : 0);
     for (int j = 0; j < Q; ++j) d.off[j] = CXh(j) + X * (CYh(j) + Y * CZh(j));
     d.solidIndex = s->solidIndex.p;
     d.n = s->n.p; d.ux = s->ux.p; d.uy = s->uy.p; d.uz = s->uz.p;
@@ -742,8 +718,6 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         }
         CU(cudaGetDevice(&h->device));
         CU(cudaDeviceGetAttribute(&h->numSMs, cudaDevAttrMultiProcessorCount, h->device));
-        // the cp.async.bulk fed tile kernel is the alternative bulk path (A/B switch; see DESIGN.md for the measurements)
-        if (const char* e = getenv("LBGPU_TILES")) h->useTiles = (e[0] == '1');
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
@@ -782,22 +756,6 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
                 k_build_bulk<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
                 ++h->launches;
                 s->dev.bulk = s->bulk.p;
-                // tiles with at least one owned active cell, ascending (cell activity is static here)
-                DevBuf<uint8_t> flags;
-                CU(flags.alloc(s->blocks));
-                k_tile_flags<<<s->blocks, BLOCK, 0, st>>>(dev_for(h, s), flags.p);
-                ++h->launches;
-                std::vector<uint8_t> hf(s->blocks);
-                CU(cudaMemcpyAsync(hf.data(), flags.p, s->blocks, cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                std::vector<uint32_t> list;
-                for (uint32_t t = 0; t < s->blocks; ++t) if (hf[t]) list.push_back(t);
-                s->nTiles = (uint32_t)list.size();
-                if (s->nTiles) {
-                    CU(s->tiles.alloc(s->nTiles));
-                    CU(cudaMemcpyAsync(s->tiles.p, list.data(), 4 * (size_t)s->nTiles, cudaMemcpyHostToDevice, st));
-                    CU(cudaStreamSynchronize(st));
-                }
             }
             // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
