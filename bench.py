@@ -200,6 +200,7 @@ def main_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        slabs.init_comm(rank, world, local_rank, dist)  # the engine's own NCCL communicator (halo send/recv, sums)
 
     case = workload_case(args.workload, world)
     t_init = time.time()

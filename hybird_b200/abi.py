@@ -33,7 +33,8 @@ class LbGpuParams(C.Structure):
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuStep", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
-           "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize")
+           "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
+           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize")
 
 _lib = None
 
@@ -81,6 +82,14 @@ def load_library(build_if_missing=True):
     L.lbGpuLaunchCount.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.lbGpuSelfTest.restype = C.c_int
     L.lbGpuSelfTest.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64 * 3)]
+    L.lbGpuCommUniqueId.restype = C.c_int
+    L.lbGpuCommUniqueId.argtypes = [vp]
+    L.lbGpuCommInit.restype = C.c_int
+    L.lbGpuCommInit.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.lbGpuCommInfo.restype = C.c_int
+    L.lbGpuCommInfo.argtypes = [C.POINTER(C.c_int32)] * 3
+    L.lbGpuCommFinalize.restype = C.c_int
+    L.lbGpuCommFinalize.argtypes = []
     L.lbGpuFinalize.restype = C.c_int
     L.lbGpuFinalize.argtypes = [vp]
     _lib = L

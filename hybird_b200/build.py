@@ -9,14 +9,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("LBGPU_LIB") or os.path.join(HERE, "liblbgpu.so")  # LBGPU_LIB: A/B experiments with alternative builds
 SOURCES = [os.path.join(HERE, "csrc", "lbgpu.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("lb_kernels.cuh", "lb_d3q19.cuh")] + \
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("lb_kernels.cuh", "lb_d3q19.cuh", "lbgpu_comm.h")] + \
     [os.path.join(ROOT, "include", "lbgpu.h")]
 
 # -fmad=false: the reference is built for x86-64 without FMA contraction; fusing a*b+c on the
 # device would change results in the last bit and, through the free-surface thresholds
 # (mass > n, mass < 0), the cell-type map.  fp64 division and sqrt are IEEE-rounded by default.
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def nvcc_path():

@@ -21,9 +21,11 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "lb_kernels.cuh"
+#include "lbgpu_comm.h"
 
 namespace {
 
@@ -43,6 +45,12 @@ int fail(int code, const char* fmt, ...) {
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
         if (e_ != cudaSuccess) return fail(LBGPU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        int r_ = (call);                                                                                 \
+        if (r_ != lbcomm::ncclSuccess) return fail(LBGPU_ECOMM, "%s failed: %s (%s:%d)", #call, lbcomm::api().GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
 
 lb::FastDiv make_div(uint32_t d) {
@@ -93,6 +101,10 @@ struct Slab {
     // host copies of what lbGpuInit received for the ghost cells (they are dead cells of the reference)
     std::vector<uint32_t> ghostIdx, ghostSolid;
     std::vector<uint8_t> ghostType;
+    // z-periodic lattice cut into several slabs: the reference's shell planes z=0 / z=Z-1 are replaced by remote ghost
+    // planes on the device; what lbGpuInit received for them is kept for lbGpuFetchFields
+    std::vector<uint8_t> shellTypeLo, shellTypeHi;
+    std::vector<uint32_t> shellSolidLo, shellSolidHi;
     bool remoteLo = false, remoteHi = false;  // the z-/z+ ghost plane belongs to another slab
     double* fbuf(int k) { return (k == 0 ? fA.p : fB.p) + pad; }
     uint8_t* tbuf(int k) { return k == 0 ? type0.p : type1.p; }
@@ -105,6 +117,8 @@ struct LbGpuHandle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t evA = nullptr, evB = nullptr;
+    cudaStream_t commStream = nullptr;  // halo transport to other processes, overlapped with the interior update
+    cudaEvent_t evFaces = nullptr, evHalo = nullptr;
     std::vector<std::unique_ptr<Slab>> slabs;
     int nSlabsGlobal = 1, firstSlab = 0;
     DevBuf<lb::RawParticle> rawParts;
@@ -246,10 +260,80 @@ int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32
 }
 
 // typeNew: the type buffer being written by a free-surface step (curType^1) instead of the current one
-// popsPushed: the destination populations of the local mirrors were already written by the step kernel (ghost push)
-int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushed = false) {
+// ---------------------------------------------------------------------------------------------
+// Slabs of other processes: NCCL send/recv of the face planes (every field plane is contiguous, so the planes are
+// sent straight out of / received straight into the SoA arrays, no packing), one group per exchange.
+// ---------------------------------------------------------------------------------------------
+struct Xfer { void* ptr; size_t bytes; };
+
+// field planes exchanged with the slab above (up) or below: what this slab sends and where it receives
+void face_planes(LbGpuHandle* h, Slab* s, uint32_t what, bool up, bool typeNew, std::vector<Xfer>& snd, std::vector<Xfer>& rcv) {
+    const size_t XY = s->XY;
+    const size_t sp = up ? (size_t)s->dev.Z - 2 : 1, dp = up ? (size_t)s->dev.Z - 1 : 0;
+    auto add2 = [&](char* sendBase, char* recvBase, size_t elem) {
+        snd.push_back({ sendBase + sp * XY * elem, XY * elem });
+        rcv.push_back({ recvBase + dp * XY * elem, XY * elem });
+    };
+    auto add = [&](void* base, size_t elem) { add2((char*)base, (char*)base, elem); };
+    if (what & G_POPS) {
+        double* f = s->fbuf(h->cur ^ 1);
+        if (h->slip) { for (int k = 0; k < Q; ++k) add(f + (size_t)k * s->stride, 8); }
+        else {
+            // the populations moving towards the neighbour leave, the ones moving away from it arrive
+            const int* out = up ? POPS_UP : POPS_DOWN; const int* in = up ? POPS_DOWN : POPS_UP;
+            for (int q = 0; q < 5; ++q) add2((char*)(f + (size_t)out[q] * s->stride), (char*)(f + (size_t)in[q] * s->stride), 8);
+        }
+    }
+    if (what & G_POPS_SRC) { double* f = s->fbuf(h->cur); for (int k = 0; k < Q; ++k) add(f + (size_t)k * s->stride, 8); }
+    if (what & G_TYPE) add(s->tbuf(typeNew ? (h->curType ^ 1) : h->curType), 1);
+    if (what & G_SOLID) add(s->solidIndex.p, 4);
+    if (what & G_MASS) add(s->mass.p, 8);
+    if (what & G_MACRO) { add(s->n.p, 8); add(s->ux.p, 8); add(s->uy.p, 8); add(s->uz.p, 8); }
+    if (what & G_VISC) add(s->visc.p, 8);
+    if (what & G_HF) { add(s->hfx.p, 8); add(s->hfy.p, 8); add(s->hfz.p, 8); }
+    if ((what & G_MARK) && s->mark.p) add(s->mark.p, 1);
+}
+
+// ranks holding the slab below the handle's first / above its last slab (-1: a true lattice boundary)
+void neighbour_ranks(LbGpuHandle* h, int* down, int* up) {
+    const lbcomm::Comm& c = lbcomm::comm();
+    const bool ring = h->prm.boundary[4] == T_PERIODIC;
+    *down = c.rank > 0 ? c.rank - 1 : (ring ? c.world - 1 : -1);
+    *up = c.rank + 1 < c.world ? c.rank + 1 : (ring ? 0 : -1);
+}
+
+int exchange_remote(LbGpuHandle* h, uint32_t what, bool typeNew, cudaStream_t st) {
+    lbcomm::Api& A = lbcomm::api();
+    const lbcomm::Comm& c = lbcomm::comm();
+    int down, up;
+    neighbour_ranks(h, &down, &up);
+    std::vector<Xfer> sUp, rUp, sDn, rDn;
+    if (up >= 0) face_planes(h, h->slabs.back().get(), what, true, typeNew, sUp, rUp);
+    if (down >= 0) face_planes(h, h->slabs.front().get(), what, false, typeNew, sDn, rDn);
+    // posting order send-up, send-down, recv-down, recv-up pairs every send with its receive even when both
+    // neighbours are the same rank (two ranks on a periodic axis)
+    NC(A.GroupStart());
+    for (const Xfer& x : sUp) NC(A.Send(x.ptr, x.bytes, lbcomm::ncclUint8, up, c.comm, st));
+    for (const Xfer& x : sDn) NC(A.Send(x.ptr, x.bytes, lbcomm::ncclUint8, down, c.comm, st));
+    for (const Xfer& x : rDn) NC(A.Recv(x.ptr, x.bytes, lbcomm::ncclUint8, down, c.comm, st));
+    for (const Xfer& x : rUp) NC(A.Recv(x.ptr, x.bytes, lbcomm::ncclUint8, up, c.comm, st));
+    NC(A.GroupEnd());
+    return 0;
+}
+
+// in-place sum over the ranks of a small device array (no-op in a single-process run)
+int allreduce_sum(LbGpuHandle* h, void* buf, size_t count, int dtype) {
+    if (!lbcomm::active() || count == 0) return 0;
+    NC(lbcomm::api().AllReduce(buf, buf, count, dtype, lbcomm::ncclSum, lbcomm::comm().comm, h->stream));
+    return 0;
+}
+
+// popsPushed: the local mirrors of everything the step kernel stores (populations, n, u, visc, hydroForce) were
+// already written by that kernel (ghost push)
+// remote: also move the planes shared with other processes (false when the caller overlaps that transport itself)
+int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushed = false, bool remote = true) {
     cudaStream_t st = h->stream;
-    const uint32_t local = popsPushed ? (what & ~(uint32_t)G_POPS) : what;
+    const uint32_t local = popsPushed ? (what & ~(uint32_t)(G_POPS | G_MACRO | G_VISC | G_HF)) : what;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
         if (!s->nGhost || !local) continue;
@@ -259,11 +343,12 @@ int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushe
         ++h->launches;
     }
     const int G = (int)h->slabs.size();
+    const bool ring = h->prm.boundary[4] == T_PERIODIC;
+    const bool multiProc = lbcomm::active();
     if (G > 1) {
-        const bool ring = h->prm.boundary[4] == T_PERIODIC;
         for (int k = 0; k < G; ++k) {
             Slab* a = h->slabs[k].get();
-            const int ku = (k + 1 < G) ? k + 1 : (ring ? 0 : -1);
+            const int ku = (k + 1 < G) ? k + 1 : ((ring && !multiProc) ? 0 : -1);
             if (ku < 0) continue;
             Slab* b = h->slabs[ku].get();
             int rc;
@@ -272,6 +357,7 @@ int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushe
             if ((rc = copy_face(h, b, 1, a, (uint32_t)a->dev.Z - 1, what, false, typeNew))) return rc;
         }
     }
+    if (multiProc && remote) { if (int rc = exchange_remote(h, what, typeNew, st)) return rc; }
     CU(cudaGetLastError());
     return 0;
 }
@@ -367,6 +453,8 @@ int free_surface_step(LbGpuHandle* h) {
         k_add_counters<<<1, 32, 0, st>>>(s0->counters.p, h->slabs[k]->counters.p, 1);
         h->launches += 2;
     }
+    if ((rc = allreduce_sum(h, s0->sums.p, 3, lbcomm::ncclFloat64))) return rc;
+    if ((rc = allreduce_sum(h, s0->counters.p, 1, lbcomm::ncclUint64))) return rc;
     k_fs_finalize<<<1, 1, 0, st>>>(s0->sums.p, s0->counters.p, s0->scal.p);
     ++h->launches;
     for (auto& sp : h->slabs) {
@@ -417,6 +505,7 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
             h->launches += 2;
         }
         for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_u32<<<1, 32, 0, st>>>(s0->status.p + 1, h->slabs[k]->status.p + 1, 1); ++h->launches; }
+        if ((rc = allreduce_sum(h, s0->status.p + 1, 1, lbcomm::ncclUint32))) return rc;
         CU(cudaMemcpyAsync(h->pinnedStatus, s0->status.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*h->pinnedStatus == 0) break;
@@ -439,19 +528,43 @@ int lb_step(LbGpuHandle* h) {
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
     CU(cudaEventRecord(h->kev0[ke], st));
-    for (auto& sp : h->slabs) {
-        Slab* s = sp.get();
+    const uint32_t what = G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u);
+    // Slabs of other processes: the two face planes are updated first and travel (NCCL, comm stream) while the
+    // interior is updated.  Moving walls keep the plain order (their per-block partial sums are indexed by block).
+    int down = -1, up = -1;
+    if (lbcomm::active()) neighbour_ranks(h, &down, &up);
+    const bool overlap = lbcomm::active() && !h->dynWall;
+    auto launch = [&](Slab* s, uint32_t begin, uint32_t end) {
+        if (end <= begin) return;
         Dev d = dev_for(h, s);
         // the streaming being evaluated happened under the type map of before this cycle's free-surface step
         if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
         d.pStride = s->blocks; d.pBase = 0;
-        k<<<own_blocks(s), BLOCK, 0, st>>>(d);
+        d.cellBegin = begin; d.cellEnd = end;
+        k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
         ++h->launches;
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> rest(h->slabs.size());
+    for (size_t q = 0; q < h->slabs.size(); ++q) {
+        Slab* s = h->slabs[q].get();
+        uint32_t b = s->ownBegin, e = s->ownEnd;
+        const bool thick = s->dev.Z >= 5;  // at least three owned planes
+        if (overlap && thick && q == 0 && down >= 0) { launch(s, b, b + s->XY); b += s->XY; }
+        if (overlap && thick && q + 1 == h->slabs.size() && up >= 0) { launch(s, e - s->XY, e); e -= s->XY; }
+        rest[q] = { b, e };
     }
+    if (overlap) {
+        CU(cudaEventRecord(h->evFaces, st));
+        CU(cudaStreamWaitEvent(h->commStream, h->evFaces, 0));
+        if ((rc = exchange_remote(h, what, false, h->commStream))) return rc;
+        CU(cudaEventRecord(h->evHalo, h->commStream));
+    }
+    for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
     CU(cudaEventRecord(h->kev1[ke], st));
     ++h->kevCount;
     h->typesFlipped = false;
-    if ((rc = exchange(h, G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u), false, true))) return rc;
+    if ((rc = exchange(h, what, false, true, !overlap))) return rc;
+    if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
     Slab* s0 = h->slabs[0].get();
     if (h->dynWall) {
         for (auto& sp : h->slabs) {
@@ -461,6 +574,7 @@ int lb_step(LbGpuHandle* h) {
             h->launches += nSums;
             if (s != s0) { k_add_arrays<<<(nSums + 31) / 32, 32, 0, st>>>(s0->sums.p + 4, s->sums.p + 4, nSums); ++h->launches; }
         }
+        if ((rc = allreduce_sum(h, s0->sums.p + 4, (size_t)nSums, lbcomm::ncclFloat64))) return rc;
         if (fsOn) {
             // LB::redistributeMass(extraMass) at the end of LB::streaming (LB.cpp:1477)
             k_extra_mass_finalize<<<1, 1, 0, st>>>(s0->sums.p + 4, s0->counters.p, s0->scal.p + 2);
@@ -477,6 +591,8 @@ int lb_step(LbGpuHandle* h) {
             ++h->launches;
             if (s != s0) { k_add_arrays<<<(7 * h->nElmts + 127) / 128, 128, 0, st>>>(s0->elemOut.p, s->elemOut.p, 7 * h->nElmts); ++h->launches; }
         }
+        // every rank ends up with the forces of all elements (LB::computeHydroForces sums over the whole lattice)
+        if ((rc = allreduce_sum(h, s0->elemOut.p, (size_t)7 * h->nElmts, lbcomm::ncclFloat64))) return rc;
     }
     CU(cudaGetLastError());
     h->cur ^= 1;
@@ -616,6 +732,15 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         }
     }
 
+    if (perZ && s->remoteLo && s->zBegin == 1) {
+        s->shellTypeLo.assign(type_flags + hostOff, type_flags + hostOff + s->XY);
+        s->shellSolidLo.assign(solidIndex + hostOff, solidIndex + hostOff + s->XY);
+    }
+    if (perZ && s->remoteHi && s->zEnd == gZ - 1) {
+        const size_t o = hostOff + (size_t)(Zl - 1) * s->XY;
+        s->shellTypeHi.assign(type_flags + o, type_flags + o + s->XY);
+        s->shellSolidHi.assign(solidIndex + o, solidIndex + o + s->XY);
+    }
     // staged upload: host (pageable) -> device scratch -> SoA
     CU(cudaMemcpyAsync(s->type0.p, type_flags + hostOff, N, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(s->solidIndex.p, solidIndex + hostOff, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
@@ -688,7 +813,14 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     const int nLocal = G > 1 ? (prm->nLocalSlabs > 0 ? prm->nLocalSlabs : 1) : 1;
     if (G > 1 && prm->slabAxis != 2) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: slabs are cut along z (slabAxis=2)");
     if (first < 0 || first + nLocal > G || G > prm->size[2] - 2) return fail(LBGPU_EINVAL, "lbGpuInit: slab %d+%d of %d", first, nLocal, G);
-    if (first != 0 || nLocal != G) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: slabs on other processes need lbGpuCommInit (not in this build)");
+    if (first != 0 || nLocal != G) {
+        const lbcomm::Comm& c = lbcomm::comm();
+        if (!lbcomm::active()) return fail(LBGPU_ECOMM, "lbGpuInit: slabs %d..%d of %d live in other processes: call lbGpuCommInit first", first, first + nLocal - 1, G);
+        if (c.world * nLocal != G || first != c.rank * nLocal)
+            return fail(LBGPU_EINVAL, "lbGpuInit: rank %d of %d must own slabs [%d, %d) of %d", c.rank, c.world, c.rank * nLocal, (c.rank + 1) * nLocal, c.world * nLocal);
+    } else if (lbcomm::active() && G > 1) {
+        return fail(LBGPU_EINVAL, "lbGpuInit: a communicator of %d ranks is active but this handle claims every slab", lbcomm::comm().world);
+    }
     int32_t zLo, zHi, tmpz;
     lbGpuSlabRange(prm->size[2], G, first, &zLo, &tmpz);
     lbGpuSlabRange(prm->size[2], G, first + nLocal - 1, &tmpz, &zHi);
@@ -721,6 +853,9 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
+        CU(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->evFaces, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->evHalo, cudaEventDisableTiming));
         h->kev0.resize(LbGpuHandle::KEV); h->kev1.resize(LbGpuHandle::KEV);
         for (uint32_t k = 0; k < LbGpuHandle::KEV; ++k) { CU(cudaEventCreate(&h->kev0[k])); CU(cudaEventCreate(&h->kev1[k])); }
         h->fs = prm->freeSurface != 0;
@@ -763,6 +898,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         }
         Slab* s0 = h->slabs[0].get();
         for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_counters<<<1, 32, 0, st>>>(s0->counters.p + 1, h->slabs[k]->counters.p + 1, 3); ++h->launches; }
+        if (int r = allreduce_sum(h, s0->counters.p + 1, 3, lbcomm::ncclUint64)) return r;
         for (auto& sp : h->slabs) CU(cudaMemcpyAsync(sp->counters.p, s0->counters.p + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
@@ -904,6 +1040,12 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         const size_t hBase = (size_t)(s->zBegin - 1 - zLoHost) * s->XY;  // host index of the slab's local cell 0
         const size_t hOff = hBase + cOff;
         Dev d = dev_all(h, s);
+        // periodic shell planes that exist only as remote ghosts on the device: dead cells of the reference
+        const size_t hTop = hBase + (size_t)(s->dev.Z - 1) * s->XY;
+        auto shell_zero = [&](double* dst, int comps) {
+            if (!s->shellTypeLo.empty()) memset(dst + comps * hBase, 0, sizeof(double) * comps * s->XY);
+            if (!s->shellTypeHi.empty()) memset(dst + comps * hTop, 0, sizeof(double) * comps * s->XY);
+        };
         if (type_flags) {
             DevBuf<uint8_t> tmp;
             CU(tmp.alloc(s->N));
@@ -911,11 +1053,15 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             CU(cudaMemcpyAsync(type_flags + hOff, tmp.p + cOff, cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             for (uint32_t k = 0; k < s->nGhost; ++k) type_flags[hBase + s->ghostIdx[k]] = s->ghostType[k];
+            if (!s->shellTypeLo.empty()) memcpy(type_flags + hBase, s->shellTypeLo.data(), s->XY);
+            if (!s->shellTypeHi.empty()) memcpy(type_flags + hTop, s->shellTypeHi.data(), s->XY);
         }
         if (solidIndex) {
             CU(cudaMemcpyAsync(solidIndex + hOff, s->solidIndex.p + cOff, sizeof(uint32_t) * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             for (uint32_t k = 0; k < s->nGhost; ++k) solidIndex[hBase + s->ghostIdx[k]] = s->ghostSolid[k];
+            if (!s->shellSolidLo.empty()) memcpy(solidIndex + hBase, s->shellSolidLo.data(), sizeof(uint32_t) * s->XY);
+            if (!s->shellSolidHi.empty()) memcpy(solidIndex + hTop, s->shellSolidHi.data(), sizeof(uint32_t) * s->XY);
         }
         DevBuf<double> tmp;
         if (n || u || mass || visc || shearRate || hydroForce) CU(tmp.alloc((size_t)3 * s->N));
@@ -923,6 +1069,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             k_fetch_scalar<<<B, BLOCK, 0, st>>>(d, src, tmp.p, activeOnly);
             CU(cudaMemcpyAsync(dst + hOff, tmp.p + cOff, sizeof(double) * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            shell_zero(dst, 1);
             return 0;
         };
         int rc;
@@ -934,11 +1081,13 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->ux.p, s->uy.p, s->uz.p, tmp.p, 0);
             CU(cudaMemcpyAsync(u + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            shell_zero(u, 3);
         }
         if (hydroForce) {
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->hfx.p, s->hfy.p, s->hfz.p, tmp.p, 1);
             CU(cudaMemcpyAsync(hydroForce + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            shell_zero(hydroForce, 3);
         }
         if (f) {
             DevBuf<double> tf;
@@ -946,6 +1095,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             k_download_f<<<B, BLOCK, 0, st>>>(d, s->fbuf(h->cur), tf.p);
             CU(cudaMemcpyAsync(f + (size_t)Q * hOff, tf.p + (size_t)Q * cOff, sizeof(double) * Q * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
+            shell_zero(f, Q);
         }
     }
     CU(cudaStreamSynchronize(st));
@@ -967,7 +1117,58 @@ int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
         CU(cudaStreamSynchronize(h->stream));
         for (int k = 0; k < 3; ++k) tot[k] += tmp[k];
     }
+    if (lbcomm::active()) {
+        Slab* s0 = h->slabs[0].get();
+        CU(cudaMemcpyAsync(s0->counters.p + 4, tot, sizeof tot, cudaMemcpyHostToDevice, h->stream));
+        if (int rc = allreduce_sum(h, s0->counters.p + 4, 3, lbcomm::ncclUint64)) return rc;
+        CU(cudaMemcpyAsync(tot, s0->counters.p + 4, sizeof tot, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2]; counts[3] = h->steps;
+    return LBGPU_OK;
+}
+
+int lbGpuCommUniqueId(uint8_t id[128]) {
+    if (!id) return fail(LBGPU_EINVAL, "null argument");
+    const std::string e = lbcomm::load();
+    if (!e.empty()) return fail(LBGPU_ECOMM, "lbGpuCommUniqueId: %s", e.c_str());
+    lbcomm::ncclUniqueId u;
+    NC(lbcomm::api().GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return LBGPU_OK;
+}
+
+int lbGpuCommInit(const uint8_t id[128], int32_t rank, int32_t world, int32_t device) {
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(LBGPU_EINVAL, "lbGpuCommInit: bad arguments");
+    lbcomm::Comm& c = lbcomm::comm();
+    if (c.comm) return fail(LBGPU_EINVAL, "lbGpuCommInit: a communicator is already active");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(LBGPU_ENODEVICE, "lbGpuCommInit: no CUDA device"); }
+    if (device >= ndev) return fail(LBGPU_EINVAL, "lbGpuCommInit: device %d of %d", device, ndev);
+    if (device >= 0) CU(cudaSetDevice(device));
+    CU(cudaGetDevice(&c.device));
+    c.rank = rank; c.world = world;
+    if (world == 1) return LBGPU_OK;  // nothing to talk to
+    const std::string e = lbcomm::load();
+    if (!e.empty()) return fail(LBGPU_ECOMM, "lbGpuCommInit: %s", e.c_str());
+    lbcomm::ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NC(lbcomm::api().CommInitRank(&c.comm, world, u, rank));
+    return LBGPU_OK;
+}
+
+int lbGpuCommInfo(int32_t* rank, int32_t* world, int32_t* ncclVersion) {
+    const lbcomm::Comm& c = lbcomm::comm();
+    if (rank) *rank = c.rank;
+    if (world) *world = c.comm ? c.world : 1;
+    if (ncclVersion) { int v = 0; if (lbcomm::api().GetVersion) lbcomm::api().GetVersion(&v); *ncclVersion = v; }
+    return LBGPU_OK;
+}
+
+int lbGpuCommFinalize(void) {
+    lbcomm::Comm& c = lbcomm::comm();
+    if (c.comm) { lbcomm::api().CommDestroy(c.comm); c.comm = nullptr; }
+    c.rank = 0; c.world = 1; c.device = -1;
     return LBGPU_OK;
 }
 
@@ -993,6 +1194,9 @@ int lbGpuFinalize(LbGpuHandle* h) {
     h->slabs.clear();
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);
+    if (h->evFaces) cudaEventDestroy(h->evFaces);
+    if (h->evHalo) cudaEventDestroy(h->evHalo);
+    if (h->commStream) { cudaStreamSynchronize(h->commStream); cudaStreamDestroy(h->commStream); }
     for (cudaEvent_t e : h->kev0) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->kev1) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);

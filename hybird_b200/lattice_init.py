@@ -96,24 +96,36 @@ def make_walls(params: dict, wall_vel=()) -> list:
     return walls
 
 
-def coords(size):
+def coords(size, planes=None):
+    """x, y, z of every cell in the reference's order; with `planes` (global z of each stored plane) z is global."""
     X, Y, Z = size
-    i = np.arange(X * Y * Z, dtype=np.int64)
-    return i % X, (i // X) % Y, i // (X * Y)
+    nz = Z if planes is None else len(planes)
+    i = np.arange(X * Y * nz, dtype=np.int64)
+    zl = i // (X * Y)
+    return i % X, (i // X) % Y, (zl if planes is None else np.asarray(planes, dtype=np.int64)[zl])
 
 
 class Neighbors:
     """neighbors[i].d[j] as LB::initializeLatticeBoundaries builds it (LB.cpp:377-472): shell cells point to
     themselves, interior cells get i+ne[j] with a per-axis wrap when that side is periodic; d[0] of interior
-    cells is never assigned and stays 0.  One direction is materialised at a time (large domains)."""
+    cells is never assigned and stays 0.  One direction is materialised at a time (large domains).
 
-    def __init__(self, size, boundary):
+    `planes` restricts the table to a set of global z planes (a slab window plus its stencil margin): indices are
+    then local to that set, and a link that leaves the set points back to the cell itself (only margin cells,
+    whose results are discarded, have such links)."""
+
+    def __init__(self, size, boundary, planes=None):
         self.size = size
         self.boundary = boundary
         X, Y, Z = size
-        self.x, self.y, self.z = coords(size)
+        self.planes = np.arange(Z, dtype=np.int64) if planes is None else np.asarray(planes, dtype=np.int64)
+        self.x, self.y, self.z = coords(size, None if planes is None else self.planes)
+        self.zl = np.arange(X * Y * len(self.planes), dtype=np.int64) // (X * Y)
         self.shell = (self.x == 0) | (self.x == X - 1) | (self.y == 0) | (self.y == Y - 1) | (self.z == 0) | (self.z == Z - 1)
-        self.idx = np.arange(X * Y * Z, dtype=np.int64)
+        self.idx = np.arange(X * Y * len(self.planes), dtype=np.int64)
+        # local plane holding global plane g (-1: not stored)
+        self.local_of = np.full(Z, -1, dtype=np.int64)
+        self.local_of[self.planes] = np.arange(len(self.planes))
 
     def __getitem__(self, j):
         X, Y, Z = self.size
@@ -130,7 +142,23 @@ class Neighbors:
         if CZ[j]:
             if b[5] == PERIODIC: zs = np.where(zs == Z - 1, 1, zs)
             if b[4] == PERIODIC: zs = np.where(zs == 0, Z - 2, zs)
-        return np.where(self.shell, self.idx, xs + X * (ys + Y * zs))
+        zt = self.local_of[np.clip(zs, 0, Z - 1)]
+        link = np.where(zt >= 0, xs + X * (ys + Y * zt), self.idx)
+        return np.where(self.shell, self.idx, link)
+
+
+def window_planes(Z, periodic_z, zlo, zhi, margin=2):
+    """Global planes a slab window [zlo, zhi) needs for the init stencils: the window itself plus `margin` planes
+    on either side, wrapped through the periodic boundary (LB.cpp:438-472) or clipped at a wall."""
+    want = set(range(zlo, zhi))
+    for g in list(range(zlo - margin, zlo)) + list(range(zhi, zhi + margin)):
+        if periodic_z:
+            while g < 1: g += Z - 2
+            while g > Z - 2: g -= Z - 2
+            want.add(g)
+        elif 0 <= g < Z:
+            want.add(g)
+    return np.array(sorted(want), dtype=np.int64)
 
 
 def neighbor_table(size, boundary):
@@ -158,18 +186,30 @@ def advance_kinematic(parts, elmts, x0_elmt, dt):
     return parts
 
 
-def build_state(case: dict, parts=None) -> LatticeState:
-    """LB::latticeBolzmannInit (LB.cpp:190-219) for a box case (see oracle/cases.py for the keys)."""
+def build_state(case: dict, parts=None, window=None, reduce_max=None) -> LatticeState:
+    """LB::latticeBolzmannInit (LB.cpp:190-219) for a box case (see oracle/cases.py for the keys).
+
+    window=(zlo, zhi): build only the global planes [zlo, zhi) (a slab plus its two halo planes) -- the arrays
+    returned cover exactly those planes, in the reference's cell order within the window; the rest of the lattice
+    is never materialised.  reduce_max(v) must then return the element-wise maximum of the 3-vector v over all
+    ranks (the hydrostatic reference height is a global quantity, LB.cpp:909-944)."""
     prm = params_from_case(case)
     X, Y, Z = prm["size"]
-    N = X * Y * Z
     bnd = prm["boundary"]
     for b in bnd:
         if b not in (4, 5, 6, 7, 8):
             raise ValueError("boundary type %d not supported" % b)
     L = prm["unitLength"]
     speed = L / prm["unitTime"]
-    x, y, z = coords(prm["size"])
+    planes = None
+    if window is not None:
+        zlo, zhi = int(window[0]), int(window[1])
+        if not (0 <= zlo < zhi <= Z):
+            raise ValueError("window [%d, %d) outside the lattice" % (zlo, zhi))
+        planes = window_planes(Z, bnd[4] == PERIODIC, zlo, zhi)
+    nb = Neighbors(prm["size"], bnd, planes)
+    x, y, z = nb.x, nb.y, nb.z
+    N = x.size
     t = np.zeros(N, dtype=np.uint8)  # initializeNodes: all fluid
 
     def is_wall(a):
@@ -180,7 +220,6 @@ def build_state(case: dict, parts=None) -> LatticeState:
         t[lo] = bnd[2 * axis]
         hi = (c == n_ - 1) & ~is_wall(t)  # `else if`: a cell is never on both planes of one axis
         t[hi] = bnd[2 * axis + 1]
-    nb = Neighbors(prm["size"], bnd)
 
     # initializeParticleBoundaries (LB.cpp:475-495): active cells, highest particle index wins
     pflag = np.zeros(N, dtype=bool)
@@ -243,7 +282,12 @@ def build_state(case: dict, parts=None) -> LatticeState:
     active = (t == FLUID) | (t == INTERFACE)
     lbF = prm["lbF"]
     n = np.zeros(N); u = np.zeros((N, 3)); mass = np.zeros(N); visc = np.zeros(N)
-    if active.any():
+    if window is not None:
+        own = active & (z >= zlo) & (z < zhi)
+        loc = np.array([x[own].max(), y[own].max(), z[own].max()] if own.any() else [-1.0, -1.0, -1.0], dtype=np.float64)
+        glob = np.asarray(reduce_max(loc) if reduce_max is not None else loc, dtype=np.float64)
+        maxP = tuple(float(v) for v in glob) if glob.max() >= 0 else (0.0, 0.0, 0.0)
+    elif active.any():
         maxP = (float(x[active].max()), float(y[active].max()), float(z[active].max()))
     else:
         maxP = (0.0, 0.0, 0.0)
@@ -276,4 +320,8 @@ def build_state(case: dict, parts=None) -> LatticeState:
 
     tf = (t | (pflag.astype(np.uint8) * P_BIT) | (node.astype(np.uint8) * NODE_BIT)).astype(np.uint8)
     prm["nWalls"] = len(walls)
+    if window is not None:
+        # keep the window's planes, in global order
+        keep = np.concatenate([np.arange(X * Y, dtype=np.int64) + X * Y * int(nb.local_of[g]) for g in range(zlo, zhi)])
+        tf, solid, n, u, mass, visc = tf[keep], solid[keep], n[keep], u[keep], mass[keep], visc[keep]
     return LatticeState(params=prm, type_flags=tf, solidIndex=solid, n=n, u=u, mass=mass, visc=visc, walls=walls)

@@ -28,7 +28,20 @@ class LB:
         self.lib = abi.load_library()
         self.P = abi.make_params(params, device)
         self.h = C.c_void_p()
-        self.N = int(np.prod(params["size"]))
+        # cells in the host arrays: the whole lattice, or the planes of this handle's slabs plus one plane below and
+        # above when the other slabs live in other processes (include/lbgpu.h, LbGpuParams)
+        X, Y, Z = (int(v) for v in params["size"])
+        G = int(params.get("nSlabs", 1))
+        nLocal = int(params.get("nLocalSlabs", G))
+        first = int(params.get("slabIndex", 0))
+        if G > 1 and nLocal < G:
+            inner = Z - 2
+            zlo = 1 + (first * inner) // G
+            zhi = 1 + ((first + nLocal) * inner) // G
+            self.planes = (zlo - 1, zhi + 1)
+        else:
+            self.planes = (0, Z)
+        self.N = X * Y * (self.planes[1] - self.planes[0])
         self.nWalls = int(params.get("nWalls", 0))
         self.freeSurface = bool(params["freeSurface"])
         self._fs_requested = False

@@ -87,6 +87,17 @@ int lbGpuDeviceCount(void);
 /* global planes [zBegin, zEnd) owned by slab `slab` of `nSlabs` for a lattice of sizeZ planes */
 int lbGpuSlabRange(int32_t sizeZ, int32_t nSlabs, int32_t slab, int32_t* zBegin, int32_t* zEnd);
 
+/* Multi-GPU: one process per GPU, each owning nLocalSlabs consecutive slabs (rank r: slabs [r*nLocalSlabs,
+ * (r+1)*nLocalSlabs)).  The reference is a single process (no communication backend), so these
+ * entry points replace nothing upstream; they carry the face halo of SURVEY.md 8e over NCCL send/recv and the
+ * three small sums (mass surplus, interface count, per-element forces) over ncclAllReduce.  Rank 0 obtains the
+ * id, the host runtime (torch.distributed in hybird_b200/slabs.py, MPI in a C++ driver) broadcasts it, every rank
+ * calls lbGpuCommInit BEFORE lbGpuInit.  NCCL is loaded at run time (libnccl.so.2; override with LBGPU_NCCL_LIB). */
+int lbGpuCommUniqueId(uint8_t id[128]);
+int lbGpuCommInit(const uint8_t id[128], int32_t rank, int32_t world, int32_t device);
+int lbGpuCommInfo(int32_t* rank, int32_t* world, int32_t* ncclVersion);
+int lbGpuCommFinalize(void);
+
 /* Upload the state LB::latticeBolzmannInit produced.
  *   type_flags  N bytes: t | p<<4 | node<<5
  *   solidIndex  N

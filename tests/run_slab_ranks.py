@@ -1,0 +1,41 @@
+"""One rank of a multi-process slab run (launched by torch.distributed.run from tests/test_gpu_slabs.py):
+a golden case cut into WORLD_SIZE z-slabs, one GPU per rank, replayed with the recorded particle inputs;
+rank 0 gathers the fields and writes them to OUT.   python run_slab_ranks.py CASE OUT"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import common  # noqa: F401
+import golden_util as gu
+from hybird_b200 import LB, slabs
+
+name, out = sys.argv[1], sys.argv[2]
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+slabs.init_comm(rank, world, local, dist)
+g = gu.Golden(name)
+prm = dict(g.params)
+X, Y, Z = prm["size"]
+prm.update(nSlabs=world, slabIndex=rank, nLocalSlabs=1)
+lo, hi = slabs.window_of(Z, world, rank)
+sl = slice(lo * X * Y, hi * X * Y)
+tf, si, n, u, mass, visc = g.init_arrays()
+lb = LB(prm, device=local)
+lb.latticeBolzmannInit(tf[sl], si[sl], n[sl], u[sl], mass[sl], visc[sl])
+steps = min(g.steps, 30)
+Fs, Ms = [], []
+for s, F, M, V, W in gu.replay(g, lb, None):
+    Fs.append(F.copy()); Ms.append(M.copy())
+    if s == steps:
+        break
+fields = slabs.gather_fields(lb, rank, world, dist, ("type_flags", "n", "u", "mass", "f"))
+cnt = lb.counts()
+if rank == 0:
+    np.savez(out, steps=steps, F=np.stack(Fs), M=np.stack(Ms), fluid=cnt["fluid"], **fields)
+lb.close()
+slabs.finalize_comm()
+dist.destroy_process_group()
