@@ -31,7 +31,7 @@ class LbGpuParams(C.Structure):
 
 
 # every symbol include/lbgpu.h declares
-EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuStep", "lbGpuRun",
+EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
            "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize")
@@ -64,6 +64,8 @@ def load_library(build_if_missing=True):
     L.lbGpuInit.argtypes = [C.POINTER(LbGpuParams), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
     L.lbGpuStep.restype = C.c_int
     L.lbGpuStep.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
+    L.lbGpuCouple.restype = C.c_int
+    L.lbGpuCouple.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, C.c_uint32, vp, C.c_uint32]
     L.lbGpuRun.restype = C.c_int
     L.lbGpuRun.argtypes = [vp, C.c_int, C.c_uint32]
     L.lbGpuParticleForces.restype = C.c_int

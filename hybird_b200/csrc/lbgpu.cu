@@ -928,6 +928,16 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
     return LBGPU_OK;
 }
 
+int lbGpuCouple(LbGpuHandle* h, int rescanParticles, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
+                uint32_t nElmts, const uint32_t* components, uint32_t nComponents) {
+    if (!h) return fail(LBGPU_EINVAL, "lbGpuCouple: null handle");
+    if (nParts && (!parts || !elmts || !components)) return fail(LBGPU_EINVAL, "lbGpuCouple: particle arrays missing");
+    CU(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = upload_particles(h, parts, nParts, elmts, nElmts, components, nComponents))) return rc;
+    return coupling_step(h, rescanParticles != 0);
+}
+
 int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     if (!h) return fail(LBGPU_EINVAL, "lbGpuRun: null handle");
     CU(cudaSetDevice(h->device));

@@ -1,0 +1,272 @@
+// LB_gpu.cpp -- drop-in replacement of the reference's LB time-step methods on top of liblbgpu.so.
+//
+// The reference (gnomeCreative/hybird) is built UNMODIFIED: hybird.cpp, DEM.cpp, IO.cpp, elmt.cpp, utils.cpp,
+// vector.cpp, node.cpp and LB.cpp are compiled where they lie.  In LB.o the five methods that form the boundary of
+// the hot path are renamed with objcopy (see Makefile) to plain symbols LB_ref_*; this translation unit defines the
+// methods under their original names, so every call site of the reference (hybird.cpp:47-59,193,310) binds here:
+//
+//   LB::latticeBoltzmannGet            reference parse, plus the export cadence IO will use (screenExpTime, fluidExpTime)
+//   LB::latticeBolzmannInit            reference host init (LB.cpp:190-219), then lbGpuInit uploads the state
+//   LB::latticeBoltzmannFreeSurfaceStep  records the request                       (LB.cpp:235-245)
+//   LB::latticeBoltzmannCouplingStep   packs particles/elements, resets the flag   (LB.cpp:247-280)
+//   LB::latticeBolzmannStep            lbGpuStep + lbGpuParticleForces -> elmts[].FHydro/MHydro/fluidVolume,
+//                                      walls[].FHydro; refreshes the host mirrors IO reads when an export is due
+//
+// LBGPU_VERIFY=1 additionally runs the reference's own step on the host state every cycle and compares the fields
+// (integration check; the forces handed to DEM are always the device's).
+// Built with -fno-access-control like the oracle harness: LB's members are "public: //private" (LB.h:36) but
+// nodeType's are private.
+#include "../../include/lbgpu.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "LB.h"
+
+extern "C" {
+void LB_ref_latticeBoltzmannGet(LB*, GetPot&, GetPot&);
+void LB_ref_latticeBolzmannInit(LB*, cylinderList&, wallList&, particleList&, objectList&);
+void LB_ref_latticeBolzmannStep(LB*, elmtList&, particleList&, wallList&);
+void LB_ref_latticeBoltzmannCouplingStep(LB*, bool&, elmtList&, particleList&);
+void LB_ref_latticeBoltzmannFreeSurfaceStep(LB*);
+}
+
+namespace {
+
+struct GpuState {
+    LbGpuHandle* h = nullptr;
+    bool fsRequested = false, couplePending = false, rescan = false, verify = false;
+    std::vector<LbGpuParticle> parts;
+    std::vector<LbGpuElement> elmts;
+    std::vector<uint32_t> comps;
+    double screenExpTime = 0.0, fluidExpTime = 0.0;
+    unsigned int lastScreenExp = 0, lastFluidExp = 0;
+    unsigned long long steps = 0, fetches = 0;
+    double worst = 0.0;
+    // fetch buffers
+    std::vector<uint8_t> tf;
+    std::vector<uint32_t> solid;
+    std::vector<double> n, u, mass, visc, shear;
+};
+
+std::map<LB*, GpuState>& states() {
+    static std::map<LB*, GpuState> m;
+    return m;
+}
+
+void die(const char* what) {
+    // the reference's convention for fatal conditions on this path: message on cout, exit(1) (macros.h:8)
+    cout << "lbgpu shim: ERROR in " << what << ": " << lbGpuLastError() << endl;
+    exit(1);
+}
+
+void pack(GpuState& st, elmtList& elmts, particleList& particles) {
+    st.parts.resize(particles.size());
+    for (size_t k = 0; k < particles.size(); ++k) {
+        const particle& p = particles[k];
+        LbGpuParticle& o = st.parts[k];
+        o.x0[0] = p.x0.x; o.x0[1] = p.x0.y; o.x0[2] = p.x0.z;
+        o.r = p.r;
+        o.radiusVec[0] = p.radiusVec.x; o.radiusVec[1] = p.radiusVec.y; o.radiusVec[2] = p.radiusVec.z;
+        o.clusterIndex = p.clusterIndex; o.particleIndex = p.particleIndex;
+    }
+    st.elmts.resize(elmts.size());
+    st.comps.clear();
+    for (size_t e = 0; e < elmts.size(); ++e) {
+        const elmt& el = elmts[e];
+        LbGpuElement& o = st.elmts[e];
+        o.x1[0] = el.x1.x; o.x1[1] = el.x1.y; o.x1[2] = el.x1.z;
+        o.wGlobal[0] = el.wGlobal.x; o.wGlobal[1] = el.wGlobal.y; o.wGlobal[2] = el.wGlobal.z;
+        o.compBegin = (uint32_t)st.comps.size();
+        for (size_t c = 0; c < el.components.size(); ++c) st.comps.push_back((uint32_t)el.components[c]);
+        o.compEnd = (uint32_t)st.comps.size();
+    }
+}
+
+// device state -> the host mirrors IO reads (IO.cpp:698-831, 835-895): types, node existence, n, u, visc, mass,
+// shearRate, and the node lists (activeNodes is what exportMaxSpeedFluid / exportTotalMass walk)
+void refresh_mirrors(LB* lb, GpuState& st) {
+    const size_t N = lb->totNodes;
+    st.tf.resize(N); st.solid.resize(N); st.n.resize(N); st.u.resize(3 * N); st.mass.resize(N); st.visc.resize(N); st.shear.resize(N);
+    if (lbGpuFetchFields(st.h, st.tf.data(), st.solid.data(), st.n.data(), st.u.data(), st.mass.data(), st.visc.data(),
+                         st.shear.data(), nullptr, nullptr))
+        die("lbGpuFetchFields");
+    ++st.fetches;
+    lb->fluidNodes.clear(); lb->interfaceNodes.clear(); lb->particleNodes.clear(); lb->activeNodes.clear();
+    for (size_t i = 0; i < N; ++i) {
+        const uint8_t b = st.tf[i];
+        unsigned int t = b & LBGPU_TYPE_MASK;
+        nodeType& ty = lb->types[i];
+        ty.setType(t);
+        if (b & LBGPU_P_BIT) ty.setInsideParticle(); else ty.setOutsideParticle();
+        unsigned int si = st.solid[i];
+        ty.setSolidIndex(si);
+        const bool has = (b & LBGPU_NODE_BIT) != 0;
+        if (has && lb->nodes[i] == 0) lb->nodes[i] = new node;
+        if (!has && lb->nodes[i] != 0) { delete lb->nodes[i]; lb->nodes[i] = 0; }
+        if (has) {
+            node* nd = lb->nodes[i];
+            nd->n = st.n[i];
+            nd->u = tVect(st.u[3 * i], st.u[3 * i + 1], st.u[3 * i + 2]);
+            nd->mass = st.mass[i];
+            nd->visc = st.visc[i];
+            nd->shearRate = st.shear[i];
+        }
+        if (t == 0) { lb->fluidNodes.push_back((unsigned int)i); lb->activeNodes.push_back((unsigned int)i); }
+        else if (t == 3) { lb->interfaceNodes.push_back((unsigned int)i); lb->activeNodes.push_back((unsigned int)i); }
+        if ((b & LBGPU_P_BIT) && (t == 0 || t == 3)) lb->particleNodes.push_back((unsigned int)i);
+    }
+}
+
+// Will IO::outputStep of the NEXT cycle read the fluid state?  It tests uint(realTime/expTime)+1 > last with
+// realTime = dem.demTime (IO.cpp:134,148-149,254-255), which by then equals lb.time * unit.Time up to the rounding of
+// DEM's accumulated sub-steps; both sides of that rounding are tested, so an export is never missed (an extra
+// refresh costs time only).
+bool export_due(LB* lb, GpuState& st) {
+    const double t = (double)lb->time * lb->unit.Time;
+    const double lo = t * (1.0 - 1e-7), hi = t * (1.0 + 1e-7);
+    bool due = false;
+    if (st.screenExpTime > 0) {
+        const unsigned int cLo = (unsigned int)(lo / st.screenExpTime) + 1, cHi = (unsigned int)(hi / st.screenExpTime) + 1;
+        if (cHi > st.lastScreenExp) { due = true; st.lastScreenExp = cLo > st.lastScreenExp ? cLo : st.lastScreenExp; }
+    }
+    if (st.fluidExpTime > 0) {
+        const unsigned int cLo = (unsigned int)(lo / st.fluidExpTime) + 1, cHi = (unsigned int)(hi / st.fluidExpTime) + 1;
+        if (cHi > st.lastFluidExp) { due = true; st.lastFluidExp = cLo > st.lastFluidExp ? cLo : st.lastFluidExp; }
+    }
+    return due;
+}
+
+double rel_diff(double a, double b) {
+    const double s = fmax(fabs(a), fabs(b));
+    return s > 0 ? fabs(a - b) / s : 0.0;
+}
+
+// LBGPU_VERIFY: host state (just advanced by the reference's own step) against the device state
+void verify_against_host(LB* lb, GpuState& st, const std::vector<tVect>& refF, elmtList& elmts) {
+    const size_t N = lb->totNodes;
+    st.tf.resize(N); st.solid.resize(N); st.n.resize(N); st.u.resize(3 * N); st.mass.resize(N); st.visc.resize(N); st.shear.resize(N);
+    std::vector<double> f(19 * N);
+    if (lbGpuFetchFields(st.h, st.tf.data(), st.solid.data(), st.n.data(), st.u.data(), st.mass.data(), st.visc.data(),
+                         st.shear.data(), nullptr, f.data()))
+        die("lbGpuFetchFields");
+    size_t typeDiff = 0;
+    double worst = 0.0;
+    for (size_t i = 0; i < N; ++i) {
+        const unsigned int t = st.tf[i] & LBGPU_TYPE_MASK;
+        if (t != lb->types[i].getType() || ((st.tf[i] & LBGPU_P_BIT) != 0) != lb->types[i].isInsideParticle()) { ++typeDiff; continue; }
+        if (!(t == 0 || t == 3)) continue;
+        const node* nd = lb->nodes[i];
+        worst = fmax(worst, rel_diff(st.n[i], nd->n));
+        worst = fmax(worst, rel_diff(st.mass[i], nd->mass));
+        worst = fmax(worst, rel_diff(st.visc[i], nd->visc));
+        for (int j = 0; j < 19; ++j) worst = fmax(worst, rel_diff(f[19 * i + j], nd->fs[j]));  // post-collision populations
+    }
+    double fWorst = 0.0, fScale = 0.0;
+    for (size_t e = 0; e < elmts.size(); ++e) fScale = fmax(fScale, refF[e].norm());
+    for (size_t e = 0; e < elmts.size(); ++e) fWorst = fmax(fWorst, (refF[e] - elmts[e].FHydro).norm() / (fScale > 0 ? fScale : 1.0));
+    st.worst = fmax(st.worst, worst);
+    cout << "lbgpu verify: step " << st.steps << " type mismatches " << typeDiff << ", max rel field diff " << worst
+         << ", max rel FHydro diff " << fWorst << endl;
+    if (typeDiff != 0 || worst > 1e-9 || fWorst > 1e-9) { cout << "lbgpu verify: FAILED" << endl; exit(2); }
+}
+
+}  // namespace
+
+void LB::latticeBoltzmannGet(GetPot& lbmCfgFile, GetPot& command_line) {
+    LB_ref_latticeBoltzmannGet(this, lbmCfgFile, command_line);
+    GpuState& st = states()[this];
+    // the cadence IO::outputStep will follow (parsed there with the same macro, hybird.cpp:149-176)
+    st.screenExpTime = lbmCfgFile("screenExpTime", 0.0);
+    if (command_line.search("-screenExpTime")) st.screenExpTime = command_line.next(st.screenExpTime);
+    st.fluidExpTime = lbmCfgFile("fluidExpTime", 0.0);
+    if (command_line.search("-fluidExpTime")) st.fluidExpTime = command_line.next(st.fluidExpTime);
+    const char* v = getenv("LBGPU_VERIFY");
+    st.verify = v && v[0] == '1';
+}
+
+void LB::latticeBolzmannInit(cylinderList& cylinders, wallList& walls, particleList& particles, objectList& objects) {
+    LB_ref_latticeBolzmannInit(this, cylinders, walls, particles, objects);
+    GpuState& st = states()[this];
+    const size_t N = totNodes;
+    LbGpuParams prm;
+    memset(&prm, 0, sizeof prm);
+    for (int k = 0; k < 3; ++k) prm.size[k] = (int32_t)lbSize[k];
+    for (int k = 0; k < 6; ++k) prm.boundary[k] = (int32_t)boundary[k];  // capacity 6 although size() is 3 (LB.cpp:175-181)
+    prm.lbF[0] = lbF.x; prm.lbF[1] = lbF.y; prm.lbF[2] = lbF.z;
+    prm.initDynVisc = initDynVisc; prm.plasticVisc = plasticVisc; prm.yieldStress = yieldStress;
+    prm.turbConst = turbConst; prm.slipCoefficient = slipCoefficient;
+    prm.freeSurface = freeSurface; prm.forceField = forceField; prm.nonNewtonian = nonNewtonian; prm.turbulence = turbulenceOn;
+    prm.unitLength = unit.Length; prm.unitTime = unit.Time; prm.unitDensity = unit.Density;
+    prm.nWalls = (int32_t)walls.size();
+    prm.device = -1;
+    prm.slabAxis = 2; prm.nSlabs = 1; prm.slabIndex = 0; prm.nLocalSlabs = 1;
+    std::vector<uint8_t> tf(N);
+    std::vector<uint32_t> solid(N);
+    std::vector<double> f(19 * N, 0.0), n(N, 0.0), u(3 * N, 0.0), mass(N, 0.0), visc(N, 0.0);
+    for (size_t i = 0; i < N; ++i) {
+        const nodeType& ty = types[i];
+        tf[i] = (uint8_t)(ty.getType() | (ty.isInsideParticle() ? LBGPU_P_BIT : 0) | (nodes[i] != 0 ? LBGPU_NODE_BIT : 0));
+        solid[i] = ty.getSolidIndex();
+        if (const node* nd = nodes[i]) {
+            n[i] = nd->n; mass[i] = nd->mass; visc[i] = nd->visc;
+            u[3 * i] = nd->u.x; u[3 * i + 1] = nd->u.y; u[3 * i + 2] = nd->u.z;
+            for (int j = 0; j < 19; ++j) f[19 * i + j] = nd->f[j];
+        }
+    }
+    if (lbGpuInit(&prm, tf.data(), solid.data(), f.data(), n.data(), u.data(), mass.data(), visc.data(), &st.h)) die("lbGpuInit");
+    cout << "lbgpu shim: " << N << " cells uploaded to the GPU" << (st.verify ? " (verify mode: the reference steps alongside)" : "") << endl;
+}
+
+void LB::latticeBoltzmannFreeSurfaceStep() {
+    GpuState& st = states()[this];
+    st.fsRequested = true;
+    if (st.verify) LB_ref_latticeBoltzmannFreeSurfaceStep(this);
+}
+
+void LB::latticeBoltzmannCouplingStep(bool& newNeighborList, elmtList& elmts, particleList& particles) {
+    GpuState& st = states()[this];
+    if (st.verify) { bool flag = newNeighborList; LB_ref_latticeBoltzmannCouplingStep(this, flag, elmts, particles); }
+    if (st.couplePending) {
+        // the previous cycle coupled without stepping the fluid (demTime <= demInitialRepeat, hybird.cpp:60-64)
+        if (lbGpuCouple(st.h, st.rescan, st.parts.data(), (uint32_t)st.parts.size(), st.elmts.data(), (uint32_t)st.elmts.size(),
+                        st.comps.data(), (uint32_t)st.comps.size()))
+            die("lbGpuCouple");
+    }
+    pack(st, elmts, particles);
+    st.rescan = newNeighborList;
+    st.couplePending = true;
+    newNeighborList = false;  // LB.cpp:258
+}
+
+void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList& walls) {
+    GpuState& st = states()[this];
+    std::vector<tVect> refF;
+    if (st.verify) {
+        elmtList refElmts(elmts);  // elmt has const members: copy-construct, never assign
+        wallList refWalls(walls);
+        LB_ref_latticeBolzmannStep(this, refElmts, particles, refWalls);
+        for (size_t e = 0; e < refElmts.size(); ++e) refF.push_back(refElmts[e].FHydro);
+    }
+    if (!st.couplePending) pack(st, elmts, particles);  // computeHydroForces reads the lists it is given (LB.cpp:1851)
+    if (lbGpuStep(st.h, st.fsRequested ? 1 : 0, st.couplePending ? 1 : 0, st.rescan ? 1 : 0, st.parts.data(), (uint32_t)st.parts.size(),
+                  st.elmts.data(), (uint32_t)st.elmts.size(), st.comps.data(), (uint32_t)st.comps.size()))
+        die("lbGpuStep");
+    st.fsRequested = false; st.couplePending = false; st.rescan = false;
+    ++st.steps;
+    const size_t nE = elmts.size(), nW = walls.size();
+    std::vector<double> F(3 * nE + 1), M(3 * nE + 1), V(nE + 1), W(3 * nW + 1);
+    if (lbGpuParticleForces(st.h, F.data(), M.data(), V.data(), W.data())) die("lbGpuParticleForces");
+    for (size_t e = 0; e < nE; ++e) {
+        elmts[e].FHydro = tVect(F[3 * e], F[3 * e + 1], F[3 * e + 2]);
+        elmts[e].MHydro = tVect(M[3 * e], M[3 * e + 1], M[3 * e + 2]);
+        elmts[e].fluidVolume = V[e];
+    }
+    for (size_t w = 0; w < nW; ++w) walls[w].FHydro = tVect(W[3 * w], W[3 * w + 1], W[3 * w + 2]);
+    if (st.verify) verify_against_host(this, st, refF, elmts);
+    else if (export_due(this, st)) refresh_mirrors(this, st);
+}

@@ -114,6 +114,11 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
               uint32_t nParts, const LbGpuElement* elmts, uint32_t nElmts, const uint32_t* components,
               uint32_t nComponents);
 
+/* The coupling step alone (goCycle's branch for demTime <= demInitialRepeat, hybird.cpp:60-64: particle flags
+ * follow the particles while the fluid is not stepped yet). */
+int lbGpuCouple(LbGpuHandle* h, int rescanParticles, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
+                uint32_t nElmts, const uint32_t* components, uint32_t nComponents);
+
 /* Same step repeated `count` times with no particles (pure-fluid / free-surface runs). */
 int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
 

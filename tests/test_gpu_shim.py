@@ -1,0 +1,85 @@
+"""GPU: the drop-in boundary.  hybird_b200/shim/_build/hybird_gpu is the UNMODIFIED reference driver (hybird.cpp,
+DEM.cpp, IO.cpp, ...) linked against the LB shim + liblbgpu.so; hybird_ref is the same objects linked as the
+reference is.  Both binaries are built in the build container (make -C hybird_b200/shim, from /root/reference) and
+travel to the GPU box; nothing here reads /root/reference.
+
+(1) the shipped configuration's physics (cfg1: demChute free surface + Smagorinsky) run through both
+    drivers gives the same console/export.dat lines and the same ParaView fluid files;
+(2) LBGPU_VERIFY=1 makes the shim step the reference's own LB on the host next to the device every cycle, with the
+    reference's DEM in the loop, and compare cell types, fields and particle forces (exit code 2 on a mismatch)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+
+import cases
+
+pytestmark = pytest.mark.gpu
+BUILD = os.path.join(common.ROOT, "hybird_b200", "shim", "_build")
+GPU_BIN, REF_BIN = os.path.join(BUILD, "hybird_gpu"), os.path.join(BUILD, "hybird_ref")
+NUM = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?")
+
+
+def _need_binaries():
+    if not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN)):
+        pytest.skip("shim binaries not built (make -C hybird_b200/shim needs the reference sources)")
+
+
+def _run(binary, cfg, outdir, env=None, threads=None):
+    os.makedirs(outdir, exist_ok=True)
+    e = dict(os.environ, OMP_NUM_THREADS=str(threads or os.cpu_count() or 1))
+    e.update(env or {})
+    r = subprocess.run([binary, "-c", cfg, "-d", outdir, "-n", "run"], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=1200)
+    return r.returncode, r.stdout
+
+
+def _numbers(text):
+    return np.array([float(x) for x in NUM.findall(text)])
+
+
+def test_shipped_config_through_both_drivers(tmp_path):
+    _need_binaries()
+    case = dict(cases.catalogue()["cfg1"])
+    case.update(maximumTimeSteps=40, screenExpTime=1e-3, fluidExpTime=4e-3)
+    cfg = cases.write_case_files(case, str(tmp_path))
+    rc_r, out_r = _run(REF_BIN, cfg, str(tmp_path / "ref"))
+    rc_g, out_g = _run(GPU_BIN, cfg, str(tmp_path / "gpu"))
+    assert rc_r == 0, out_r[-2000:]
+    assert rc_g == 0, out_g[-2000:]
+    assert "cells uploaded to the GPU" in out_g
+    # export.dat: step; time; MaxFSpeed; Volume; Mass per screenExpTime
+    er = open(tmp_path / "ref" / "run" / "export.dat").read()
+    eg = open(tmp_path / "gpu" / "run" / "export.dat").read()
+    assert len(er.splitlines()) == len(eg.splitlines()) >= 8
+    a, b = _numbers(er), _numbers(eg)
+    assert a.shape == b.shape
+    assert np.allclose(a, b, rtol=2e-6, atol=0), np.abs(a - b).max()
+    # ParaView fluid files (ASCII, ~6 significant digits): same file names, same numbers
+    fr = sorted(os.listdir(tmp_path / "ref" / "run" / "fluidData"))
+    fg = sorted(os.listdir(tmp_path / "gpu" / "run" / "fluidData"))
+    assert fr == fg and len(fr) >= 2
+    for name in fr:
+        tr = open(tmp_path / "ref" / "run" / "fluidData" / name).read()
+        tg = open(tmp_path / "gpu" / "run" / "fluidData" / name).read()
+        a, b = _numbers(tr), _numbers(tg)
+        assert a.shape == b.shape, name
+        # printed with 6 digits: a last-digit flip of a rounded value is the most that can differ
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-12), (name, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("name,steps", [("cfg3_mini", 60), ("cluster_dem", 40), ("cfg1_mini", 60)])
+def test_verify_mode_reference_steps_alongside(name, steps, tmp_path):
+    _need_binaries()
+    case = dict(cases.catalogue()[name])
+    case.update(maximumTimeSteps=steps)
+    cfg = cases.write_case_files(case, str(tmp_path))
+    rc, out = _run(GPU_BIN, cfg, str(tmp_path / "gpu"), env={"LBGPU_VERIFY": "1"}, threads=1)
+    assert rc == 0, out[-3000:]
+    lines = [l for l in out.splitlines() if l.startswith("lbgpu verify: step")]
+    assert len(lines) == steps, out[-2000:]
+    assert "FAILED" not in out
