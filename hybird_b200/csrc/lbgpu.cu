@@ -84,6 +84,7 @@ using namespace lb;
 // One device-resident part of the lattice: global planes [zBegin, zEnd) plus a plane below and above.
 struct Slab {
     int index = 0;          // slab number in the global decomposition
+    int slot = 0;           // position among the handle's slabs
     int zBegin = 1, zEnd = 1;
     uint32_t N = 0, XY = 0;
     size_t stride = 0, pad = 0;
@@ -93,6 +94,11 @@ struct Slab {
     DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
     DevBuf<uint8_t> type0, type1, mark;
     DevBuf<uint32_t> solidIndex, bulk;
+    // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
+    // listCounts = {interface cells, tiles, interface cells before clamping to the capacity}
+    DevBuf<uint8_t> tileFlags;
+    DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset;
+    uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
     DevBuf<double> partial, sums, scal, elemOut;
@@ -131,9 +137,9 @@ struct LbGpuHandle {
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
-    int curType = 0;  // type buffer holding the current types
     bool fs = false, shear = false, force = false, macroAlways = false, dynWall = false, slip = false;
-    bool macroValid = true, lastStepFirst = false, lastStepCoupled = false, typesFlipped = false;
+    bool macroValid = true, lastStepFirst = false, lastStepCoupled = false, typesFlipped = false, listsFresh = false;
+    uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
     double uLength = 1, uSpeed = 1, uAngVel = 1, uForce = 1, uTorque = 1, uVolume = 1;
     // CUDA-event pairs around the fused step kernel of the last lbGpuStep/lbGpuRun call (ring of KEV)
@@ -184,8 +190,10 @@ Dev dev_for(LbGpuHandle* h, Slab* s) {
     set_src(d, s, h->cur, h->steps > 0);
     d.fdst = s->fbuf(h->cur ^ 1);
     for (int k = 0; k < Q; ++k) d.fdstK[k] = d.fdst + (size_t)k * s->stride;
-    d.typeOld = s->tbuf(h->curType);
-    d.type = s->tbuf(h->curType);
+    d.type = s->tbuf(0);     // current types (updated in place by the free-surface step)
+    d.typeOld = s->tbuf(0);  // the step kernel of a cycle with a free-surface step looks its links up in tbuf(1) instead
+    d.list = s->cellList.p; d.nList = s->listCounts.p;  // list-driven kernels: the interface cells unless told otherwise
+    d.lazyMass = 0;
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
     d.cellBegin = s->ownBegin; d.cellEnd = s->ownEnd;
@@ -222,7 +230,7 @@ int copy_plane(T* dst, uint32_t dstPlane, const T* src, uint32_t srcPlane, uint3
 }
 
 // plane `sp` of slab a -> ghost plane `dp` of slab b (same process)
-int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32_t what, bool up, bool typeNew) {
+int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32_t what, bool up) {
     cudaStream_t st = h->stream;
     const uint32_t XY = a->XY;
     int rc;
@@ -240,7 +248,7 @@ int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32
         double* src = a->fbuf(h->cur); double* dst = b->fbuf(h->cur);
         for (int k = 0; k < Q; ++k) if ((rc = copy_plane(dst + (size_t)k * b->stride, dp, src + (size_t)k * a->stride, sp, XY, st))) return rc;
     }
-    if (what & G_TYPE) { const int tbi = typeNew ? (h->curType ^ 1) : h->curType; if ((rc = copy_plane(b->tbuf(tbi), dp, a->tbuf(tbi), sp, XY, st))) return rc; }
+    if (what & G_TYPE) if ((rc = copy_plane(b->tbuf(0), dp, a->tbuf(0), sp, XY, st))) return rc;
     if (what & G_SOLID) if ((rc = copy_plane(b->solidIndex.p, dp, a->solidIndex.p, sp, XY, st))) return rc;
     if (what & G_MASS) if ((rc = copy_plane(b->mass.p, dp, a->mass.p, sp, XY, st))) return rc;
     if (what & G_MACRO) {
@@ -259,7 +267,6 @@ int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32
     return 0;
 }
 
-// typeNew: the type buffer being written by a free-surface step (curType^1) instead of the current one
 // ---------------------------------------------------------------------------------------------
 // Slabs of other processes: NCCL send/recv of the face planes (every field plane is contiguous, so the planes are
 // sent straight out of / received straight into the SoA arrays, no packing), one group per exchange.
@@ -267,7 +274,7 @@ int copy_face(LbGpuHandle* h, Slab* a, uint32_t sp, Slab* b, uint32_t dp, uint32
 struct Xfer { void* ptr; size_t bytes; };
 
 // field planes exchanged with the slab above (up) or below: what this slab sends and where it receives
-void face_planes(LbGpuHandle* h, Slab* s, uint32_t what, bool up, bool typeNew, std::vector<Xfer>& snd, std::vector<Xfer>& rcv) {
+void face_planes(LbGpuHandle* h, Slab* s, uint32_t what, bool up, std::vector<Xfer>& snd, std::vector<Xfer>& rcv) {
     const size_t XY = s->XY;
     const size_t sp = up ? (size_t)s->dev.Z - 2 : 1, dp = up ? (size_t)s->dev.Z - 1 : 0;
     auto add2 = [&](char* sendBase, char* recvBase, size_t elem) {
@@ -285,7 +292,7 @@ void face_planes(LbGpuHandle* h, Slab* s, uint32_t what, bool up, bool typeNew, 
         }
     }
     if (what & G_POPS_SRC) { double* f = s->fbuf(h->cur); for (int k = 0; k < Q; ++k) add(f + (size_t)k * s->stride, 8); }
-    if (what & G_TYPE) add(s->tbuf(typeNew ? (h->curType ^ 1) : h->curType), 1);
+    if (what & G_TYPE) add(s->tbuf(0), 1);
     if (what & G_SOLID) add(s->solidIndex.p, 4);
     if (what & G_MASS) add(s->mass.p, 8);
     if (what & G_MACRO) { add(s->n.p, 8); add(s->ux.p, 8); add(s->uy.p, 8); add(s->uz.p, 8); }
@@ -302,14 +309,14 @@ void neighbour_ranks(LbGpuHandle* h, int* down, int* up) {
     *up = c.rank + 1 < c.world ? c.rank + 1 : (ring ? 0 : -1);
 }
 
-int exchange_remote(LbGpuHandle* h, uint32_t what, bool typeNew, cudaStream_t st) {
+int exchange_remote(LbGpuHandle* h, uint32_t what, cudaStream_t st) {
     lbcomm::Api& A = lbcomm::api();
     const lbcomm::Comm& c = lbcomm::comm();
     int down, up;
     neighbour_ranks(h, &down, &up);
     std::vector<Xfer> sUp, rUp, sDn, rDn;
-    if (up >= 0) face_planes(h, h->slabs.back().get(), what, true, typeNew, sUp, rUp);
-    if (down >= 0) face_planes(h, h->slabs.front().get(), what, false, typeNew, sDn, rDn);
+    if (up >= 0) face_planes(h, h->slabs.back().get(), what, true, sUp, rUp);
+    if (down >= 0) face_planes(h, h->slabs.front().get(), what, false, sDn, rDn);
     // posting order send-up, send-down, recv-down, recv-up pairs every send with its receive even when both
     // neighbours are the same rank (two ranks on a periodic axis)
     NC(A.GroupStart());
@@ -331,14 +338,13 @@ int allreduce_sum(LbGpuHandle* h, void* buf, size_t count, int dtype) {
 // popsPushed: the local mirrors of everything the step kernel stores (populations, n, u, visc, hydroForce) were
 // already written by that kernel (ghost push)
 // remote: also move the planes shared with other processes (false when the caller overlaps that transport itself)
-int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushed = false, bool remote = true) {
+int exchange(LbGpuHandle* h, uint32_t what, bool popsPushed = false, bool remote = true) {
     cudaStream_t st = h->stream;
     const uint32_t local = popsPushed ? (what & ~(uint32_t)(G_POPS | G_MACRO | G_VISC | G_HF)) : what;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
         if (!s->nGhost || !local) continue;
         Dev d = dev_for(h, s);
-        if (typeNew) d.type = s->tbuf(h->curType ^ 1);
         k_fill_ghosts<<<(s->nGhost + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d, s->gDst.p, s->gSrc.p, s->gPop.p, 0, s->nGhost, local, s->mark.p);
         ++h->launches;
     }
@@ -353,11 +359,11 @@ int exchange(LbGpuHandle* h, uint32_t what, bool typeNew = false, bool popsPushe
             Slab* b = h->slabs[ku].get();
             int rc;
             // a's top owned plane -> b's lower ghost plane; b's bottom owned plane -> a's upper ghost plane
-            if ((rc = copy_face(h, a, (uint32_t)a->dev.Z - 2, b, 0, what, true, typeNew))) return rc;
-            if ((rc = copy_face(h, b, 1, a, (uint32_t)a->dev.Z - 1, what, false, typeNew))) return rc;
+            if ((rc = copy_face(h, a, (uint32_t)a->dev.Z - 2, b, 0, what, true))) return rc;
+            if ((rc = copy_face(h, b, 1, a, (uint32_t)a->dev.Z - 1, what, false))) return rc;
         }
     }
-    if (multiProc && remote) { if (int rc = exchange_remote(h, what, typeNew, st)) return rc; }
+    if (multiProc && remote) { if (int rc = exchange_remote(h, what, st)) return rc; }
     CU(cudaGetLastError());
     return 0;
 }
@@ -407,45 +413,63 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
     return 0;
 }
 
+// interface-cell list and visited-tile list of every slab from the current types (count - band - scan - write)
+int build_lists(LbGpuHandle* h) {
+    cudaStream_t st = h->stream;
+    for (size_t q = 0; q < h->slabs.size(); ++q) {
+        Slab* s = h->slabs[q].get();
+        const uint32_t nT = s->blocks;
+        k_list_count<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p);
+        k_list_band<<<(nT + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p);
+        k_list_offsets<<<1, 1024, 0, st>>>(s->listBlockCount.p, s->listTileOffset.p, s->tileFlags.p, s->listBlocks, nT, s->listCounts.p, s->cellCap);
+        k_list_write<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p, s->listTileOffset.p, s->cellList.p,
+                                                      s->cellCap, s->tileList.p);
+        h->launches += 4;
+        // the host only needs the tile count to size the step kernel's grid; a stale value is fine (grid-stride loop)
+        CU(cudaMemcpyAsync(h->pinnedCounts + 4 * q, s->listCounts.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    }
+    h->listsFresh = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 int free_surface_step(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     int rc;
+    if ((rc = build_lists(h))) return rc;
+    // candidate ownership (lb_kernels.cuh, candidate_cell) is decided on the types of before this update: tbuf(1)
     auto fsdev = [&](Slab* s) {
         Dev d = dev_for(h, s);
-        d.type = s->tbuf(h->curType ^ 1);
+        d.typeOld = s->tbuf(1);
         return d;
     };
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
         const Dev d = fsdev(s);
-        const uint32_t B = own_blocks(s);
-        k_fs_mass<<<B, BLOCK, 0, st>>>(d);
-        k_fs_mutate<<<B, BLOCK, 0, st>>>(d, s->mark.p);
+        k_fs_mass<<<s->listGrid, BLOCK, 0, st>>>(d);
+        k_fs_mutate<<<s->listGrid, BLOCK, 0, st>>>(d, s->mark.p);
         h->launches += 2;
     }
-    if ((rc = exchange(h, G_MARK | G_TYPE, true))) return rc;
+    if ((rc = exchange(h, G_MARK | G_TYPE))) return rc;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
-        k_fs_smooth<<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s->mark.p, s->partial.p);
+        k_fs_smooth<<<s->listGrid, BLOCK, 0, st>>>(fsdev(s), s->mark.p, s->partial.p);
         ++h->launches;
     }
-    if ((rc = exchange(h, G_TYPE, true))) return rc;
+    if ((rc = exchange(h, G_TYPE))) return rc;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
-        k_fs_isolated<0><<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s->partial.p + s->blocks, s->counters.p);
+        k_fs_isolated<0><<<s->listGrid, BLOCK, 0, st>>>(fsdev(s), s->partial.p + s->listGrid, s->counters.p);
         ++h->launches;
     }
-    if ((rc = exchange(h, G_TYPE, true))) return rc;
+    if ((rc = exchange(h, G_TYPE))) return rc;
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
-        const uint32_t B = own_blocks(s);
         CU(cudaMemsetAsync(s->counters.p, 0, sizeof(unsigned long long), st));
-        k_fs_isolated<1><<<B, BLOCK, 0, st>>>(fsdev(s), s->partial.p + 2 * (size_t)s->blocks, s->counters.p);
-        // three partial arrays with a pitch of s->blocks; the first B entries of each are used
-        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p, B, 1, s->sums.p, 0);
-        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p + s->blocks, B, 1, s->sums.p + 1, 0);
-        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p + 2 * (size_t)s->blocks, B, 1, s->sums.p + 2, 0);
-        h->launches += 4;
+        k_fs_isolated<1><<<s->listGrid, BLOCK, 0, st>>>(fsdev(s), s->partial.p + 2 * (size_t)s->listGrid, s->counters.p);
+        // three partial arrays (one entry per persistent block), summed in fixed order
+        k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p, s->listGrid, 3, s->sums.p, 0);
+        h->launches += 2;
     }
     Slab* s0 = h->slabs[0].get();
     for (size_t k = 1; k < h->slabs.size(); ++k) {
@@ -460,13 +484,39 @@ int free_surface_step(LbGpuHandle* h) {
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
         if (s != s0) CU(cudaMemcpyAsync(s->counters.p, s0->counters.p, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
-        k_redistribute<<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s0->scal.p + 1);
+        k_redistribute<true><<<s->listGrid, BLOCK, 0, st>>>(fsdev(s), s0->scal.p + 1);
         ++h->launches;
     }
     // new interface cells carry n, u, visc taken from their donors: refresh everything a neighbour may read
-    if ((rc = exchange(h, G_TYPE | G_MASS | G_MACRO | G_VISC | G_HF, true))) return rc;
-    h->curType ^= 1;
-    h->typesFlipped = true;
+    if ((rc = exchange(h, G_TYPE | G_MASS | G_MACRO | G_VISC | G_HF))) return rc;
+    h->typesFlipped = true;  // until the step kernel has run: tbuf(1) holds the types of before this update
+    h->listsFresh = false;   // the interface list describes the interface of before this update
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// after the step kernel of a cycle with a free-surface step: tbuf(1) := tbuf(0) wherever types can have changed
+// (band tiles, periodic ghost cells, remote ghost planes), marks cleared there
+int sync_old_types(LbGpuHandle* h) {
+    cudaStream_t st = h->stream;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        k_fs_sync<<<s->listGrid, BLOCK, 0, st>>>(dev_all(h, s), s->tbuf(1), s->mark.p);
+        ++h->launches;
+        if (s->nGhost) {
+            k_fs_sync_ghosts<<<(s->nGhost + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(dev_all(h, s), s->gDst.p, s->nGhost, s->tbuf(1), s->mark.p);
+            ++h->launches;
+        }
+        const size_t XY = s->XY, top = (size_t)(s->dev.Z - 1) * XY;
+        if (s->remoteLo) {
+            CU(cudaMemcpyAsync(s->tbuf(1), s->tbuf(0), XY, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(s->mark.p, 0, XY, st));
+        }
+        if (s->remoteHi) {
+            CU(cudaMemcpyAsync(s->tbuf(1) + top, s->tbuf(0) + top, XY, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(s->mark.p + top, 0, XY, st));
+        }
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -538,10 +588,20 @@ int lb_step(LbGpuHandle* h) {
         if (end <= begin) return;
         Dev d = dev_for(h, s);
         // the streaming being evaluated happened under the type map of before this cycle's free-surface step
-        if (h->typesFlipped) d.typeOld = s->tbuf(h->curType ^ 1);
+        if (h->typesFlipped) { d.typeOld = s->tbuf(1); d.lazyMass = 1; }
         d.pStride = s->blocks; d.pBase = 0;
         d.cellBegin = begin; d.cellEnd = end;
-        k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
+        if (fsOn) {
+            // one tile per block, sized with the tile count of the last list build that has reached the host (any
+            // value is correct: the kernel strides over the list)
+            d.list = s->tileList.p; d.nList = s->listCounts.p + 1;
+            uint32_t g = h->pinnedCounts[4 * s->slot + 1];
+            g = g + g / 16 + 8;
+            if (g > s->blocks) g = s->blocks;
+            k<<<g, BLOCK, 0, st>>>(d);
+        } else {
+            k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
+        }
         ++h->launches;
     };
     std::vector<std::pair<uint32_t, uint32_t>> rest(h->slabs.size());
@@ -556,14 +616,13 @@ int lb_step(LbGpuHandle* h) {
     if (overlap) {
         CU(cudaEventRecord(h->evFaces, st));
         CU(cudaStreamWaitEvent(h->commStream, h->evFaces, 0));
-        if ((rc = exchange_remote(h, what, false, h->commStream))) return rc;
+        if ((rc = exchange_remote(h, what, h->commStream))) return rc;
         CU(cudaEventRecord(h->evHalo, h->commStream));
     }
     for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
     CU(cudaEventRecord(h->kev1[ke], st));
     ++h->kevCount;
-    h->typesFlipped = false;
-    if ((rc = exchange(h, what, false, true, !overlap))) return rc;
+    if ((rc = exchange(h, what, true, !overlap))) return rc;
     if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
     Slab* s0 = h->slabs[0].get();
     if (h->dynWall) {
@@ -579,7 +638,12 @@ int lb_step(LbGpuHandle* h) {
             // LB::redistributeMass(extraMass) at the end of LB::streaming (LB.cpp:1477)
             k_extra_mass_finalize<<<1, 1, 0, st>>>(s0->sums.p + 4, s0->counters.p, s0->scal.p + 2);
             ++h->launches;
-            for (auto& sp : h->slabs) { k_redistribute<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()), s0->scal.p + 2); ++h->launches; }
+            if (!h->typesFlipped && !h->listsFresh) { if ((rc = build_lists(h))) return rc; }
+            for (auto& sp : h->slabs) {
+                if (h->typesFlipped) { Dev d = dev_for(h, sp.get()); d.typeOld = sp->tbuf(1); k_redistribute<true><<<sp->listGrid, BLOCK, 0, st>>>(d, s0->scal.p + 2); }
+                else k_redistribute<false><<<sp->listGrid, BLOCK, 0, st>>>(dev_for(h, sp.get()), s0->scal.p + 2);
+                ++h->launches;
+            }
             if ((rc = exchange(h, G_MASS))) return rc;
         }
     }
@@ -594,6 +658,8 @@ int lb_step(LbGpuHandle* h) {
         // every rank ends up with the forces of all elements (LB::computeHydroForces sums over the whole lattice)
         if ((rc = allreduce_sum(h, s0->elemOut.p, (size_t)7 * h->nElmts, lbcomm::ncclFloat64))) return rc;
     }
+    if (h->typesFlipped) { if ((rc = sync_old_types(h))) return rc; }
+    h->typesFlipped = false;
     CU(cudaGetLastError());
     h->cur ^= 1;
     h->macroValid = macro;
@@ -605,6 +671,8 @@ int lb_step(LbGpuHandle* h) {
 
 int check_status(LbGpuHandle* h) {
     for (auto& sp : h->slabs) {
+        if (h->fs && h->pinnedCounts[4 * sp->slot + 2] > sp->cellCap)
+            return fail(LBGPU_EUNSUPPORTED, "free surface: %u interface cells exceed the list capacity %u", h->pinnedCounts[4 * sp->slot + 2], sp->cellCap);
         CU(cudaMemcpyAsync(h->pinnedStatus, sp->status.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         if (*h->pinnedStatus) {
@@ -643,12 +711,24 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
     CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
     CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
-    const size_t NT = ((size_t)N + BLOCK - 1) / BLOCK * BLOCK + BLOCK;  // the last block reads whole
+    const size_t NT = ((size_t)N + LIST_CELLS - 1) / LIST_CELLS * LIST_CELLS + BLOCK;  // the last block of a pass reads whole
     CU(s->type0.alloc(NT)); CU(s->solidIndex.alloc(N));
     CU(cudaMemsetAsync(s->type0.p, T_STAT_WALL, NT, st));
-    if (h->fs) { CU(s->type1.alloc(NT)); CU(s->mark.alloc(N)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, N, st)); }
+    if (h->fs) {
+        CU(s->type1.alloc(NT)); CU(s->mark.alloc(NT)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, NT, st));
+        s->listBlocks = (s->blocks + LIST_TILES - 1) / LIST_TILES;
+        s->cellCap = N / 2 + 1024;
+        CU(s->tileFlags.alloc((size_t)s->listBlocks * LIST_TILES + 16)); CU(s->tileList.alloc(s->blocks)); CU(s->cellList.alloc(s->cellCap));
+        CU(s->listCounts.alloc(4)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc(s->listBlocks));
+        CU(cudaMemsetAsync(s->listCounts.p, 0, 4 * sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(s->tileFlags.p, 0, s->tileFlags.n, st));
+        s->listGrid = (uint32_t)h->numSMs * 16u;
+    }
     const int nSums = 1 + 3 * prm->nWalls;
-    const size_t nPartial = (size_t)s->blocks * (size_t)(3 > nSums ? 3 : nSums);
+    // per-block partial sums: one slot per block of the widest launch that writes them (the list-driven free-surface
+    // kernels run h->numSMs*16 blocks whatever the lattice size)
+    const size_t widest = (size_t)s->blocks > (size_t)h->numSMs * 16 ? (size_t)s->blocks : (size_t)h->numSMs * 16;
+    const size_t nPartial = widest * (size_t)(3 > nSums ? 3 : nSums);
     CU(s->partial.alloc(nPartial));
     CU(s->sums.alloc(8 + 3 * 64)); CU(s->scal.alloc(8));
     CU(s->counters.alloc(8)); CU(s->status.alloc(4));
@@ -869,10 +949,12 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
         h->uForce = D * L * L * L * L / Tm / Tm; h->uTorque = D * L * L * L * L * L / Tm / Tm;
         CU(cudaMallocHost((void**)&h->pinnedStatus, 64));
+        CU(cudaMallocHost((void**)&h->pinnedCounts, sizeof(uint32_t) * 4 * (size_t)nLocal));
+        memset(h->pinnedCounts, 0, sizeof(uint32_t) * 4 * (size_t)nLocal);
         for (int k = 0; k < nLocal; ++k) {
             h->slabs.emplace_back(new Slab());
             Slab* s = h->slabs.back().get();
-            s->index = first + k;
+            s->index = first + k; s->slot = k;
             int32_t zb, ze;
             lbGpuSlabRange(prm->size[2], G, first + k, &zb, &ze);
             s->zBegin = zb; s->zEnd = ze;
@@ -883,7 +965,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         cudaStream_t st = h->stream;
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
-            if (h->fs) CU(cudaMemcpyAsync(s->type1.p, s->type0.p, s->N, cudaMemcpyDeviceToDevice, st));
+            if (h->fs) CU(cudaMemcpyAsync(s->type1.p, s->type0.p, s->type0.n, cudaMemcpyDeviceToDevice, st));
             if (!h->fs) {
                 // cell activity never changes without a free surface: the bulk bitmap is built once
                 CU(s->bulk.alloc((size_t)s->blocks * (BLOCK / 32) + 1));
@@ -896,6 +978,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
             ++h->launches;
         }
+        if (h->fs) { if (int r = build_lists(h)) return r; }  // valid until the first free-surface step rebuilds them
         Slab* s0 = h->slabs[0].get();
         for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_counters<<<1, 32, 0, st>>>(s0->counters.p + 1, h->slabs[k]->counters.p + 1, 3); ++h->launches; }
         if (int r = allreduce_sum(h, s0->counters.p + 1, 3, lbcomm::ncclUint64)) return r;
@@ -1211,6 +1294,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     for (cudaEvent_t e : h->kev1) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
     if (h->pinnedStatus) cudaFreeHost(h->pinnedStatus);
+    if (h->pinnedCounts) cudaFreeHost(h->pinnedCounts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return LBGPU_OK;
