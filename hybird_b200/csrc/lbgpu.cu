@@ -94,10 +94,13 @@ struct Slab {
     DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
     DevBuf<uint8_t> type0, type1, mark;
     DevBuf<uint32_t> solidIndex, bulk;
+    DevBuf<uint32_t> staticList, staticCount;  // PART 2 of the split step kernel: owned non-bulk cells that can be active
+    uint32_t nStatic = 0;
     // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
     // listCounts = {interface cells, tiles, interface cells before clamping to the capacity}
     DevBuf<uint8_t> tileFlags;
-    DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset;
+    DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset, candList, candOwned, candBlockCount;
+    uint32_t candCap = 0;
     uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
@@ -153,26 +156,35 @@ namespace {
 
 typedef void (*StepKernel)(const Dev);
 
-// FS / DYNWALL are compile-time in k_step; only the combinations that can occur are instantiated.
+// FS / DYNWALL / PART are compile-time in k_step; only the combinations that can occur are instantiated.
+// part 0: the whole step in one launch (lean variants); parts 1 + 2: bulk cells, then the rest (lb_kernels.cuh).
 template <bool FORCE, bool SHEAR, bool MACRO, bool COUPLE>
-StepKernel pick_step(bool fsOn, bool dyn) {
+StepKernel pick_step(bool fsOn, bool dyn, int part) {
     if constexpr (!MACRO) {
-        return k_step<FORCE, SHEAR, false, COUPLE, false, false>;
+        if (part == 1) return k_step<FORCE, SHEAR, false, COUPLE, false, false, 1>;
+        if (part == 2) return k_step<FORCE, SHEAR, false, COUPLE, false, false, 2>;
+        return k_step<FORCE, SHEAR, false, COUPLE, false, false, 0>;
     } else {
-        if (fsOn) return dyn ? k_step<FORCE, SHEAR, true, COUPLE, true, true> : k_step<FORCE, SHEAR, true, COUPLE, true, false>;
-        return dyn ? k_step<FORCE, SHEAR, true, COUPLE, false, true> : k_step<FORCE, SHEAR, true, COUPLE, false, false>;
+        // moving-wall sums only arise next to walls, i.e. never on cells with the static bulk bit
+        if (part == 1) return fsOn ? k_step<FORCE, SHEAR, true, COUPLE, true, false, 1> : k_step<FORCE, SHEAR, true, COUPLE, false, false, 1>;
+        if (part == 3) return k_step<FORCE, SHEAR, true, COUPLE, true, false, 3>;
+        if (fsOn) return dyn ? k_step<FORCE, SHEAR, true, COUPLE, true, true, 2> : k_step<FORCE, SHEAR, true, COUPLE, true, false, 2>;
+        return dyn ? k_step<FORCE, SHEAR, true, COUPLE, false, true, 2> : k_step<FORCE, SHEAR, true, COUPLE, false, false, 2>;
     }
 }
 
-StepKernel select_step(bool force, bool shear, bool macro, bool couple, bool fsOn, bool dyn) {
+// the variants with a heavy generic path are split into a bulk launch and a launch for the other cells
+bool step_is_split(bool shear, bool macro, bool couple, bool fsOn, bool dyn) { return macro || shear || couple || fsOn || dyn; }
+
+StepKernel select_step(bool force, bool shear, bool macro, bool couple, bool fsOn, bool dyn, int part) {
     if (!macro) {
-        if (couple) return shear ? pick_step<true, true, false, true>(false, false) : pick_step<true, false, false, true>(false, false);
-        if (force) return shear ? pick_step<true, true, false, false>(false, false) : pick_step<true, false, false, false>(false, false);
-        return shear ? pick_step<false, true, false, false>(false, false) : pick_step<false, false, false, false>(false, false);
+        if (couple) return shear ? pick_step<true, true, false, true>(false, false, part) : pick_step<true, false, false, true>(false, false, part);
+        if (force) return shear ? pick_step<true, true, false, false>(false, false, part) : pick_step<true, false, false, false>(false, false, part);
+        return shear ? pick_step<false, true, false, false>(false, false, part) : pick_step<false, false, false, false>(false, false, part);
     }
     // the full variants always carry the force path (exact when the force is zero)
-    if (couple) return shear ? pick_step<true, true, true, true>(fsOn, dyn) : pick_step<true, false, true, true>(fsOn, dyn);
-    return shear ? pick_step<true, true, true, false>(fsOn, dyn) : pick_step<true, false, true, false>(fsOn, dyn);
+    if (couple) return shear ? pick_step<true, true, true, true>(fsOn, dyn, part) : pick_step<true, false, true, true>(fsOn, dyn, part);
+    return shear ? pick_step<true, true, true, false>(fsOn, dyn, part) : pick_step<true, false, true, false>(fsOn, dyn, part);
 }
 
 // source populations of a launch: buffer `buf`, pulled through the links (pull) or taken in place
@@ -193,6 +205,7 @@ Dev dev_for(LbGpuHandle* h, Slab* s) {
     d.type = s->tbuf(0);     // current types (updated in place by the free-surface step)
     d.typeOld = s->tbuf(0);  // the step kernel of a cycle with a free-surface step looks its links up in tbuf(1) instead
     d.list = s->cellList.p; d.nList = s->listCounts.p;  // list-driven kernels: the interface cells unless told otherwise
+    d.cand = s->candList.p; d.nCand = s->listCounts.p + 3;
     d.lazyMass = 0;
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
@@ -413,20 +426,30 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
     return 0;
 }
 
-// interface-cell list and visited-tile list of every slab from the current types (count - band - scan - write)
+// interface-cell list and visited-tile list of every slab from the current types: count - scan - write for the cells
+// (k_list_*), then for the tiles (k_tile_*)
 int build_lists(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
-        const uint32_t nT = s->blocks;
+        const uint32_t nT = s->blocks, tb = (nT + BLOCK - 1) / BLOCK;
         k_list_count<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p);
-        k_list_band<<<(nT + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p);
-        k_list_offsets<<<1, 1024, 0, st>>>(s->listBlockCount.p, s->listTileOffset.p, s->tileFlags.p, s->listBlocks, nT, s->listCounts.p, s->cellCap);
-        k_list_write<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p, s->listTileOffset.p, s->cellList.p,
-                                                      s->cellCap, s->tileList.p);
-        h->launches += 4;
+        k_list_offsets<<<1, 1024, 0, st>>>(s->listBlockCount.p, s->listBlocks, s->listCounts.p, 0, s->cellCap);
+        k_list_write<<<s->listBlocks, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p, s->listBlockCount.p, s->cellList.p, s->cellCap);
+        {   // candidates of the update: owners decided on the (identical) pre-update copy of the types
+            Dev d = dev_for(h, s);
+            d.typeOld = s->tbuf(1);
+            k_cand_count<<<s->listGrid, BLOCK, 0, st>>>(d, s->candOwned.p, s->candBlockCount.p);
+            k_cand_offsets<<<1, 1024, 0, st>>>(d, s->candBlockCount.p, s->listCounts.p, s->candCap);
+            k_cand_write<<<s->listGrid, BLOCK, 0, st>>>(d, s->candOwned.p, s->candBlockCount.p, s->candList.p, s->candCap, s->tileFlags.p);
+            h->launches += 3;
+        }
+        k_tile_count<<<tb, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p);
+        k_list_offsets<<<1, 1024, 0, st>>>(s->listTileOffset.p, tb, s->listCounts.p, 1, nT);
+        k_tile_write<<<tb, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, s->tileList.p);
+        h->launches += 6;
         // the host only needs the tile count to size the step kernel's grid; a stale value is fine (grid-stride loop)
-        CU(cudaMemcpyAsync(h->pinnedCounts + 4 * q, s->listCounts.p, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h->pinnedCounts + 8 * q, s->listCounts.p, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
     h->listsFresh = true;
     CU(cudaGetLastError());
@@ -573,7 +596,11 @@ int lb_step(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     int rc;
     const int nSums = 1 + 3 * h->prm.nWalls;
-    StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall);
+    const bool split = step_is_split(h->shear, macro, couple, fsOn, h->dynWall);
+    StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, split ? 1 : 0);
+    StepKernel k2 = split ? select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, 2) : nullptr;
+    StepKernel k3 = (split && fsOn) ? select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, 3) : nullptr;
+    if (fsOn && !h->typesFlipped && !h->listsFresh) { if ((rc = build_lists(h))) return rc; }  // a cycle without its own update
     const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
@@ -595,7 +622,7 @@ int lb_step(LbGpuHandle* h) {
             // one tile per block, sized with the tile count of the last list build that has reached the host (any
             // value is correct: the kernel strides over the list)
             d.list = s->tileList.p; d.nList = s->listCounts.p + 1;
-            uint32_t g = h->pinnedCounts[4 * s->slot + 1];
+            uint32_t g = h->pinnedCounts[8 * s->slot + 1];
             g = g + g / 16 + 8;
             if (g > s->blocks) g = s->blocks;
             k<<<g, BLOCK, 0, st>>>(d);
@@ -603,6 +630,16 @@ int lb_step(LbGpuHandle* h) {
             k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
         }
         ++h->launches;
+        if (k2 && s->nStatic) {  // the cells next to walls, shells and periodic faces
+            d.list = s->staticList.p; d.nList = s->staticCount.p + 1;
+            k2<<<(s->nStatic + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
+            ++h->launches;
+        }
+        if (k3) {  // interface cells old and new
+            d.list = s->cellList.p; d.nList = s->listCounts.p;
+            k3<<<s->listGrid, BLOCK, 0, st>>>(d);
+            ++h->launches;
+        }
     };
     std::vector<std::pair<uint32_t, uint32_t>> rest(h->slabs.size());
     for (size_t q = 0; q < h->slabs.size(); ++q) {
@@ -671,8 +708,10 @@ int lb_step(LbGpuHandle* h) {
 
 int check_status(LbGpuHandle* h) {
     for (auto& sp : h->slabs) {
-        if (h->fs && h->pinnedCounts[4 * sp->slot + 2] > sp->cellCap)
-            return fail(LBGPU_EUNSUPPORTED, "free surface: %u interface cells exceed the list capacity %u", h->pinnedCounts[4 * sp->slot + 2], sp->cellCap);
+        if (h->fs && h->pinnedCounts[8 * sp->slot + 2] > sp->cellCap)
+            return fail(LBGPU_EUNSUPPORTED, "free surface: %u interface cells exceed the list capacity %u", h->pinnedCounts[8 * sp->slot + 2], sp->cellCap);
+        if (h->fs && h->pinnedCounts[8 * sp->slot + 4] > sp->candCap)
+            return fail(LBGPU_EUNSUPPORTED, "free surface: %u candidate cells exceed the list capacity %u", h->pinnedCounts[8 * sp->slot + 4], sp->candCap);
         CU(cudaMemcpyAsync(h->pinnedStatus, sp->status.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         if (*h->pinnedStatus) {
@@ -717,10 +756,14 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     if (h->fs) {
         CU(s->type1.alloc(NT)); CU(s->mark.alloc(NT)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, NT, st));
         s->listBlocks = (s->blocks + LIST_TILES - 1) / LIST_TILES;
-        s->cellCap = N / 2 + 1024;
+        // capacities: the interface is a sheet; a lattice where more than 1 cell in 8 is an interface cell is refused
+        s->cellCap = N / 8 + 1024;
+        s->candCap = 4 * s->cellCap;
+        CU(s->candList.alloc(s->candCap)); CU(s->candOwned.alloc((size_t)Q * s->cellCap));
+        CU(s->candBlockCount.alloc(((size_t)Q * s->cellCap + BLOCK - 1) / BLOCK + 1));
         CU(s->tileFlags.alloc((size_t)s->listBlocks * LIST_TILES + 16)); CU(s->tileList.alloc(s->blocks)); CU(s->cellList.alloc(s->cellCap));
-        CU(s->listCounts.alloc(4)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc(s->listBlocks));
-        CU(cudaMemsetAsync(s->listCounts.p, 0, 4 * sizeof(uint32_t), st));
+        CU(s->listCounts.alloc(8)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc((s->blocks + BLOCK - 1) / BLOCK + 1));
+        CU(cudaMemsetAsync(s->listCounts.p, 0, 8 * sizeof(uint32_t), st));
         CU(cudaMemsetAsync(s->tileFlags.p, 0, s->tileFlags.n, st));
         s->listGrid = (uint32_t)h->numSMs * 16u;
     }
@@ -949,8 +992,8 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
         h->uForce = D * L * L * L * L / Tm / Tm; h->uTorque = D * L * L * L * L * L / Tm / Tm;
         CU(cudaMallocHost((void**)&h->pinnedStatus, 64));
-        CU(cudaMallocHost((void**)&h->pinnedCounts, sizeof(uint32_t) * 4 * (size_t)nLocal));
-        memset(h->pinnedCounts, 0, sizeof(uint32_t) * 4 * (size_t)nLocal);
+        CU(cudaMallocHost((void**)&h->pinnedCounts, sizeof(uint32_t) * 8 * (size_t)nLocal));
+        memset(h->pinnedCounts, 0, sizeof(uint32_t) * 8 * (size_t)nLocal);
         for (int k = 0; k < nLocal; ++k) {
             h->slabs.emplace_back(new Slab());
             Slab* s = h->slabs.back().get();
@@ -966,13 +1009,29 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             if (h->fs) CU(cudaMemcpyAsync(s->type1.p, s->type0.p, s->type0.n, cudaMemcpyDeviceToDevice, st));
-            if (!h->fs) {
-                // cell activity never changes without a free surface: the bulk bitmap is built once
+            {
+                // built once: without a free surface cell activity never changes; with one the bitmap holds the static part
                 CU(s->bulk.alloc((size_t)s->blocks * (BLOCK / 32) + 1));
                 CU(cudaMemsetAsync(s->bulk.p, 0, sizeof(uint32_t) * s->bulk.n, st));
-                k_build_bulk<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
+                if (h->fs) k_build_bulk<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
+                else k_build_bulk<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
                 ++h->launches;
                 s->dev.bulk = s->bulk.p;
+                // the static list of the split step kernel (count - scan - write, once)
+                DevBuf<uint32_t> bc;
+                CU(bc.alloc(s->blocks)); CU(s->staticCount.alloc(4));
+                CU(cudaMemsetAsync(s->staticCount.p, 0, 4 * sizeof(uint32_t), st));
+                if (h->fs) k_static_count<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
+                else k_static_count<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
+                k_list_offsets<<<1, 1024, 0, st>>>(bc.p, s->blocks, s->staticCount.p, 1, s->N);
+                CU(cudaMemcpyAsync(h->pinnedStatus + 8, s->staticCount.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                s->nStatic = h->pinnedStatus[8];
+                CU(s->staticList.alloc(s->nStatic + 1));
+                if (h->fs) k_static_write<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
+                else k_static_write<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
+                CU(cudaStreamSynchronize(st));
+                h->launches += 3;
             }
             // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
