@@ -1088,6 +1088,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     for (uint32_t k = 0; k < count; ++k) {
         int rc;
         if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
+        if (h->nParts > 0) { if ((rc = coupling_step(h, false))) return rc; }  // goCycle's order, particles of the last upload
         if ((rc = lb_step(h))) return rc;
     }
     CU(cudaEventRecord(h->evB, h->stream));

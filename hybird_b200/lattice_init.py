@@ -225,17 +225,23 @@ def build_state(case: dict, parts=None, window=None, reduce_max=None) -> Lattice
     pflag = np.zeros(N, dtype=bool)
     solid = np.zeros(N, dtype=np.uint32)
     if parts is not None and len(parts):
-        active = (t == FLUID) | (t == INTERFACE)
+        # cells of each sphere's bounding box only (the reference tests every cell against every particle); the
+        # exact test is tVect::insideSphere (vector.cpp:153-158); ascending particle order keeps "last wins"
         for k in range(len(parts)):
             c0 = parts[k]["x0"] / L
             r = parts[k]["r"] / L
-            # bounding box first, exact test (tVect::insideSphere, vector.cpp:153-158) inside it
-            box = (np.abs(x - c0[0]) <= r + 1) & (np.abs(y - c0[1]) <= r + 1) & (np.abs(z - c0[2]) <= r + 1) & active
-            ids = np.nonzero(box)[0]
-            dx, dy, dz = x[ids] - c0[0], y[ids] - c0[1], z[ids] - c0[2]
-            ins = (dx * dx + dy * dy + dz * dz) < r * r
-            pflag[ids[ins]] = True
-            solid[ids[ins]] = parts[k]["particleIndex"]
+            bx = np.arange(max(0, math.floor(c0[0] - r)), min(X - 1, math.ceil(c0[0] + r)) + 1, dtype=np.int64)
+            by = np.arange(max(0, math.floor(c0[1] - r)), min(Y - 1, math.ceil(c0[1] + r)) + 1, dtype=np.int64)
+            bz = np.arange(max(0, math.floor(c0[2] - r)), min(Z - 1, math.ceil(c0[2] + r)) + 1, dtype=np.int64)
+            bz = bz[nb.local_of[bz] >= 0]
+            if not (bx.size and by.size and bz.size):
+                continue
+            gz, gy, gx = np.meshgrid(bz, by, bx, indexing="ij")
+            dx, dy, dz = gx - c0[0], gy - c0[1], gz - c0[2]
+            ids = (gx + X * (gy + Y * nb.local_of[gz]))[(dx * dx + dy * dy + dz * dz) < r * r]
+            ids = ids[(t[ids] == FLUID) | (t[ids] == INTERFACE)]
+            pflag[ids] = True
+            solid[ids] = parts[k]["particleIndex"]
 
     # initializeWallBoundaries (LB.cpp:497-533): DEM walls in index order; later walls override
     walls = make_walls(prm, case.get("wall_vel", ()))

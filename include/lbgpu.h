@@ -119,7 +119,9 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
 int lbGpuCouple(LbGpuHandle* h, int rescanParticles, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
                 uint32_t nElmts, const uint32_t* components, uint32_t nComponents);
 
-/* Same step repeated `count` times with no particles (pure-fluid / free-surface runs). */
+/* `count` cycles back to back without a host round trip. The particle state of the last lbGpuStep/lbGpuCouple upload
+ * (none: pure-fluid / free-surface runs) stays resident and fixed: the coupling step (particle flags, without rescan)
+ * and the hydrodynamic force reduction run every cycle as in goCycle (hybird.cpp:49-57). */
 int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
 
 /* Results of the last step in physical units; any pointer may be NULL. Synchronises. */

@@ -13,157 +13,15 @@ so that all three see identical inputs.  The five BASELINE.json configs are `cfg
 """
 from __future__ import annotations
 
-import copy
-import math
 import os
 import subprocess
+import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
 REF_HARNESS = os.path.join(HERE, "_ref", "ref_harness")
 
-_BASE = dict(
-    demSolve=1, lbSolve=1, freeSurfaceSolve=0, forceFieldSolve=1, nonNewtonianSolve=0, turbulenceSolve=0,
-    problemName="NONE", demInitialRepeat=0, lbmInitialRepeat=0, maximumTimeSteps=0, maxTime=1e9,
-    screenExpTime=0, fluidExpTime=0, partExpTime=0, recycleExpTime=0, objectExpTime=0, saveCount=0,
-    unitLength=1.0, unitTime=1.0, unitDensity=1.0,
-    lbSizeX=16, lbSizeY=16, lbSizeZ=16, initVisc=1.0 / 6.0,
-    initVelocityX=0.0, initVelocityY=0.0, initVelocityZ=0.0, plasticVisc=1.0 / 6.0, yieldStress=0.0,
-    lbFX=0.0, lbFY=0.0, lbFZ=0.0,
-    boundary0=7, boundary1=7, boundary2=7, boundary3=7, boundary4=7, boundary5=7,
-    slipCoefficient=0.0, turbConst=0.0,
-    density=2.5, contactModel="LINEAR", youngMod=1.0, poisson=0.3, linearStiff=1.0, restitution=0.9,
-    viscTang=0.5, frictionCoefPart=0.3, frictionCoefWall=0.3,
-    translateX=0.0, translateY=0.0, translateZ=0.0, scale=1.0, numVisc=0.0, multiStep=1, criticalRatio=0.1,
-)
-
-# harness-only keys (not written to the .cfg)
-_HARNESS_KEYS = ("name", "elements", "fluid_box", "gas_box", "fluid_sphere", "gas_sphere", "wall_vel", "motion",
-                 "rescan_every", "note")
-
-
-def make_case(name, **kw):
-    c = copy.deepcopy(_BASE)
-    c.update(name=name, elements=[], motion="none", rescan_every=0)
-    c.update(kw)
-    return c
-
-
-def _sphere_bed(n, lo, hi, rmin, rmax, seed):
-    """Random sequential addition of non-overlapping spheres (own 64-bit LCG: no numpy dependency,
-    identical on every box)."""
-    state = seed & 0xFFFFFFFFFFFFFFFF
-    def rnd():
-        nonlocal state
-        state = (state * 6364136223846793005 + 1442695040888963407) & 0xFFFFFFFFFFFFFFFF
-        return (state >> 11) / float(1 << 53)
-    out = []
-    cell = 2.0 * rmax
-    grid = {}
-    tries = 0
-    while len(out) < n and tries < 200 * n:
-        tries += 1
-        r = rmin + (rmax - rmin) * rnd()
-        p = [lo[k] + r + (hi[k] - lo[k] - 2 * r) * rnd() for k in range(3)]
-        key = tuple(int(p[k] // cell) for k in range(3))
-        ok = True
-        for dx in (-1, 0, 1):
-            for dy in (-1, 0, 1):
-                for dz in (-1, 0, 1):
-                    for (q, rq) in grid.get((key[0] + dx, key[1] + dy, key[2] + dz), ()):
-                        if (p[0] - q[0]) ** 2 + (p[1] - q[1]) ** 2 + (p[2] - q[2]) ** 2 < (r + rq) ** 2:
-                            ok = False
-        if ok:
-            grid.setdefault(key, []).append((p, r))
-            out.append(dict(size=1, radius=r, x0=p, x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.0]))
-    return out
-
-
-def catalogue():
-    C = {}
-    # --- cfg 2: pure-fluid channel, periodic x/y, no-slip z, body force along x (SURVEY 8d) -----
-    C["cfg2"] = make_case("cfg2", lbSizeX=256, lbSizeY=256, lbSizeZ=256, boundary0=4, boundary1=4, boundary2=4,
-                          boundary3=4, lbFX=1e-6)
-    C["cfg2_mini"] = make_case("cfg2_mini", lbSizeX=24, lbSizeY=20, lbSizeZ=16, boundary0=4, boundary1=4,
-                               boundary2=4, boundary3=4, lbFX=1e-6)
-    # a harder pure-fluid case: oblique force, initial velocity, all three periodic pairs off/on mixes
-    C["channel_oblique"] = make_case("channel_oblique", lbSizeX=18, lbSizeY=14, lbSizeZ=12, boundary0=4, boundary1=4,
-                                     lbFX=3e-5, lbFY=-2e-5, lbFZ=-1e-5, initVelocityX=0.01, initVelocityY=-0.02,
-                                     initVelocityZ=0.005, initVisc=0.05)
-    C["box_noforce"] = make_case("box_noforce", lbSizeX=12, lbSizeY=12, lbSizeZ=12, forceFieldSolve=0, lbFX=1e-3,
-                                 initVelocityX=0.02)
-    C["periodic_all"] = make_case("periodic_all", lbSizeX=12, lbSizeY=10, lbSizeZ=14, boundary0=4, boundary1=4,
-                                  boundary2=4, boundary3=4, boundary4=4, boundary5=4, lbFZ=-2e-5, initVelocityY=0.03)
-    # --- viscosity models ------------------------------------------------------------------------
-    C["smago_channel"] = make_case("smago_channel", lbSizeX=16, lbSizeY=12, lbSizeZ=14, boundary0=4, boundary1=4,
-                                   turbulenceSolve=1, turbConst=0.01, lbFX=5e-5, initVisc=0.01)
-    C["bingham_channel"] = make_case("bingham_channel", lbSizeX=16, lbSizeY=12, lbSizeZ=14, boundary0=4, boundary1=4,
-                                     nonNewtonianSolve=1, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,
-                                     lbFX=5e-5)
-    C["bingham_smago"] = make_case("bingham_smago", lbSizeX=14, lbSizeY=12, lbSizeZ=12, boundary2=4, boundary3=4,
-                                   nonNewtonianSolve=1, turbulenceSolve=1, turbConst=0.02, plasticVisc=0.02,
-                                   yieldStress=2e-5, initVisc=0.02, lbFY=4e-5, lbFZ=-1e-5)
-    # --- walls -----------------------------------------------------------------------------------
-    C["couette_dyn"] = make_case("couette_dyn", lbSizeX=14, lbSizeY=12, lbSizeZ=12, boundary0=4, boundary1=4,
-                                 boundary2=4, boundary3=4, boundary4=7, boundary5=8, wall_vel=[(1, 0.03, 0.01, 0.0)],
-                                 lbFX=1e-6)
-    C["slip_box"] = make_case("slip_box", lbSizeX=14, lbSizeY=12, lbSizeZ=12, boundary0=5, boundary1=5, boundary2=7,
-                              boundary3=5, boundary4=5, boundary5=7, slipCoefficient=0.3, lbFX=2e-5, lbFY=1e-5,
-                              lbFZ=-3e-5, initVelocityX=0.01)
-    C["slip_dyn"] = make_case("slip_dyn", lbSizeX=14, lbSizeY=12, lbSizeZ=12, boundary0=4, boundary1=4, boundary2=5,
-                              boundary3=6, boundary4=6, boundary5=8, slipCoefficient=0.4,
-                              wall_vel=[(1, 0.02, 0.0, 0.01), (2, 0.01, 0.02, 0.0), (3, -0.02, 0.01, 0.0)],
-                              lbFX=2e-5, lbFZ=-1e-5)
-    # --- cfg 3: single sphere, DEM-coupled (SURVEY 8d) -------------------------------------------
-    C["cfg3"] = make_case("cfg3", lbSizeX=128, lbSizeY=128, lbSizeZ=256, lbFZ=-1e-5, initVisc=0.1,
-                          elements=[dict(size=1, radius=8.0, x0=[64.0, 64.0, 192.0], x1=[0, 0, 0], w=[0, 0, 0])],
-                          motion="dem")
-    C["cfg3_mini"] = make_case("cfg3_mini", lbSizeX=24, lbSizeY=24, lbSizeZ=40, lbFZ=-1e-5, initVisc=0.1,
-                               elements=[dict(size=1, radius=4.0, x0=[12.0, 12.0, 28.0], x1=[0, 0, 0], w=[0, 0, 0])],
-                               motion="dem")
-    C["sphere_kin"] = make_case("sphere_kin", lbSizeX=20, lbSizeY=18, lbSizeZ=24, lbFZ=-1e-5, initVisc=0.1,
-                                elements=[dict(size=1, radius=3.6, x0=[9.3, 8.7, 15.2], x1=[0.021, -0.013, -0.034],
-                                               w=[0.01, 0.02, -0.015])],
-                                motion="kin", rescan_every=7)
-    C["two_spheres_kin"] = make_case(
-        "two_spheres_kin", lbSizeX=26, lbSizeY=18, lbSizeZ=20, boundary0=4, boundary1=4, lbFZ=-2e-5, initVisc=0.08,
-        elements=[dict(size=1, radius=3.2, x0=[8.4, 8.9, 10.2], x1=[0.05, 0.0, 0.01], w=[0.0, 0.03, 0.0]),
-                  dict(size=1, radius=2.7, x0=[14.6, 9.4, 10.9], x1=[-0.04, 0.01, -0.01], w=[0.02, 0.0, 0.01])],
-        motion="kin", rescan_every=5)
-    C["cluster_dem"] = make_case(
-        "cluster_dem", lbSizeX=24, lbSizeY=22, lbSizeZ=26, lbFZ=-3e-5, initVisc=0.1,
-        elements=[dict(size=2, radius=2.6, x0=[11.0, 10.5, 17.0], x1=[0.0, 0.0, 0.0], w=[0.01, 0.02, 0.0]),
-                  dict(size=3, radius=2.2, x0=[12.5, 11.0, 8.5], x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.02])],
-        motion="dem")
-    # --- cfg 4: free-surface dam break, Bingham (SURVEY 8d) --------------------------------------
-    C["cfg4"] = make_case("cfg4", lbSizeX=512, lbSizeY=128, lbSizeZ=256, freeSurfaceSolve=1, nonNewtonianSolve=1,
-                          lbFZ=-1e-4, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,
-                          fluid_box=(1, 128, 1, 126, 1, 192))
-    C["cfg4_mini"] = make_case("cfg4_mini", lbSizeX=40, lbSizeY=12, lbSizeZ=24, freeSurfaceSolve=1, nonNewtonianSolve=1,
-                               lbFZ=-1e-4, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,
-                               fluid_box=(1, 12, 1, 10, 1, 18))
-    C["dam_newtonian"] = make_case("dam_newtonian", lbSizeX=30, lbSizeY=10, lbSizeZ=20, freeSurfaceSolve=1,
-                                   lbFZ=-2e-4, initVisc=0.02, fluid_box=(1, 10, 1, 8, 1, 14))
-    C["droplet"] = make_case("droplet", lbSizeX=20, lbSizeY=20, lbSizeZ=24, freeSurfaceSolve=1, lbFZ=-3e-4,
-                             initVisc=0.03, fluid_sphere=(9.5, 9.5, 14.0, 5.2))
-    C["bubble_periodic"] = make_case("bubble_periodic", lbSizeX=18, lbSizeY=16, lbSizeZ=20, boundary0=4, boundary1=4,
-                                     boundary2=4, boundary3=4, freeSurfaceSolve=1, lbFZ=-2e-4, initVisc=0.03,
-                                     gas_sphere=(8.0, 8.0, 8.0, 4.3), gas_box=(0, 17, 0, 15, 15, 19))
-    # --- cfg 1: the shipped lbmConfigDevisFluid.cfg values (stand-in empty particle/object files) -
-    devis = dict(problemName="demChute", freeSurfaceSolve=1, turbulenceSolve=1, unitLength=1.0e-3, unitTime=2.0e-4,
-                 unitDensity=0.846e3, initVisc=0.017258, plasticVisc=50.0, yieldStress=500.0, boundary0=4, boundary1=4,
-                 turbConst=0.01, chuteInclination=15.0, density=2230.0, contactModel="HERTZIAN", youngMod=2.0e7,
-                 linearStiff=0.0, restitution=0.99, viscTang=0.2, frictionCoefPart=0.5, frictionCoefWall=0.2,
-                 multiStep=0, criticalRatio=0.005)
-    C["cfg1"] = make_case("cfg1", lbSizeX=0.1, lbSizeY=0.15, lbSizeZ=0.03, **devis)
-    C["cfg1_mini"] = make_case("cfg1_mini", lbSizeX=0.02, lbSizeY=0.024, lbSizeZ=0.03, **devis)
-    # --- cfg 5: debris flow, free surface + many spheres -----------------------------------------
-    C["cfg5_mini"] = make_case(
-        "cfg5_mini", lbSizeX=48, lbSizeY=20, lbSizeZ=24, boundary2=4, boundary3=4, freeSurfaceSolve=1, lbFZ=-1e-4,
-        lbFX=3e-5, initVisc=0.05, fluid_box=(0, 47, 0, 19, 0, 15),
-        elements=_sphere_bed(14, (1.5, 1.5, 1.5), (46.5, 18.5, 13.5), 2.2, 3.0, 12345), motion="kin", rescan_every=6)
-    for e in C["cfg5_mini"]["elements"]:
-        e["x1"] = [0.02, 0.0, -0.01]
-    return C
+from hybird_b200.workloads import _BASE, _HARNESS_KEYS, make_case, _sphere_bed, catalogue, materialise  # noqa: E402,F401
 
 
 def write_case_files(case, workdir):

@@ -1,0 +1,179 @@
+"""GPU: BASELINE.json's configurations at FULL size, checked through size-independent properties
+(the CPU oracle cannot run 16-67 M cells in test time):
+
+  cfg2  256^3 periodic channel    the flow is invariant along the periodic x and y axes and every cell executes the
+                                  same instruction sequence, so every (x, y) column must be BIT-IDENTICAL to the column
+                                  of a 6x6x256 lattice stepped by the CPU oracle; mass is conserved.
+  cfg3  128x128x256 + sphere      lattice and sphere are symmetric under x <-> y: f_j(x,y,z) = f_pi(j)(y,x,z), Fx = Fy
+                                  (to rounding: the sums run in a different order), and the drag opposes the fall.
+  cfg4  512x128x256 dam break     total mass conserved; fluid and gas cells never touch (the closure the reference's
+                                  updateInterface maintains, LB.cpp:1592-1794); 2 slabs == 1 slab.
+  cfg5  20 000 spheres            (a 256x256x258 section with 5 000 of the spheres keeps the host set-up short)
+                                  fluid volume handed to DEM == mass of the flagged cells; 4 slabs == 1 slab.
+"""
+import numpy as np
+import pytest
+
+import common
+from hybird_b200 import lattice_init as li
+from hybird_b200 import workloads
+
+pytestmark = pytest.mark.gpu
+
+CX, CY, CZ = li.CX, li.CY, li.CZ
+
+
+def _engine(case, n_slabs=1, parts=None):
+    from hybird_b200 import LB
+    st = li.build_state(case, parts)
+    prm = dict(st.params)
+    if n_slabs > 1:
+        prm["nSlabs"] = n_slabs
+        prm["nLocalSlabs"] = n_slabs
+    lb = LB(prm)
+    lb.latticeBolzmannInit(st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)
+    return lb, st
+
+
+def _active(tf):
+    return np.isin(tf & 0x0F, (0, 3))
+
+
+def test_cfg2_full_every_column_equals_the_oracle_column(oracle_lib):
+    cat = workloads.catalogue()
+    steps = 40
+    lb, st = _engine(cat["cfg2"])
+    X, Y, Z = st.params["size"]
+    m0 = float(lb.fetch(("f",))["f"][_active(st.type_flags)].sum())
+    lb.run(steps)
+    lb.synchronize()
+    d = lb.fetch(("type_flags", "f", "visc"))
+    lb.close()
+    assert np.array_equal(d["type_flags"] & 0x0F, st.type_flags & 0x0F)
+    f = d["f"].reshape(Z, Y, X, 19)
+    # the same channel, 4x4 interior cells wide, on the CPU oracle
+    small = dict(cat["cfg2"]); small["lbSizeX"] = 6; small["lbSizeY"] = 6
+    so = li.build_state(small)
+    o = common.make_oracle(so)
+    for _ in range(steps):
+        o.latticeBolzmannStep()
+    col = np.array(o.fs).reshape(Z, 6, 6, 19)[:, 2, 2, :]  # (Z, 19)
+    o.close()
+    inner = f[1:Z - 1, 1:Y - 1, 1:X - 1, :]
+    want = np.broadcast_to(col[1:Z - 1, None, None, :], inner.shape)
+    assert np.array_equal(inner, want), "a column of the 256^3 channel differs from the oracle's column"
+    # mass: BGK + Guo forcing + bounce-back conserve the sum of the populations
+    m1 = float(inner.sum())
+    assert abs(m1 - m0) <= 1e-11 * abs(m0), (m0, m1)
+
+
+def test_cfg3_full_xy_symmetry_and_drag():
+    case = dict(workloads.catalogue()["cfg3"])
+    # a sphere falling at constant speed, centred on the lattice's x <-> y mirror plane
+    case["elements"] = [dict(size=1, radius=8.0, x0=[63.5, 63.5, 192.0], x1=[0.0, 0.0, -0.02], w=[0.0, 0.0, 0.0])]
+    parts, elmts, comps = li.expand_elements(case["elements"])
+    lb, st = _engine(case, parts=parts)
+    X, Y, Z = st.params["size"]
+    F = None
+    for s in range(30):
+        lb.latticeBoltzmannCouplingStep(s == 0, elmts, parts, comps)
+        F, M, V, W = lb.latticeBolzmannStep(elmts, parts)
+    d = lb.fetch(("type_flags", "f", "n"))
+    lb.close()
+    # direction permutation of the mirror x <-> y
+    perm = np.array([int(np.nonzero((CX == CY[j]) & (CY == CX[j]) & (CZ == CZ[j]))[0][0]) for j in range(19)])
+    f = d["f"].reshape(Z, Y, X, 19)
+    tf = d["type_flags"].reshape(Z, Y, X)
+    assert np.array_equal(tf, tf.transpose(0, 2, 1))
+    act = _active(tf)
+    mirrored = f.transpose(0, 2, 1, 3)[..., perm]
+    assert common.max_rel(f[act], mirrored[act]) <= 1e-10
+    n = d["n"].reshape(Z, Y, X)
+    assert common.max_rel(n[act], n.transpose(0, 2, 1)[act]) <= 1e-12
+    # force: x and y components equal, the z component opposes the motion (FHydro = sum of mass/n (u - u_p))
+    assert abs(F[0, 0] - F[0, 1]) <= 1e-9 * abs(F[0, 2])
+    assert F[0, 2] > 0.0
+    assert abs(M[0, 2]) <= 1e-9 * abs(F[0, 2]) * 8.0
+    assert abs(V[0] - np.count_nonzero(tf & 0x10)) <= 1e-6 * V[0]  # density ~ 1: fluid volume ~ flagged cells
+
+
+def _fluid_touches_gas(tf3, boundary):
+    """True if a fluid cell has a gas link (non-periodic axes only: enough for cfg4/cfg5's walls; periodic y wraps)."""
+    t = tf3 & 0x0F
+    fluid, gas = t == 0, t == 2
+    Z, Y, X = t.shape
+    bad = False
+    for j in range(1, 19):
+        g = gas
+        if CY[j] and boundary[2] == 4:  # periodic y: interior planes wrap
+            g = gas.copy(); g[:, 0, :] = gas[:, Y - 2, :]; g[:, Y - 1, :] = gas[:, 1, :]
+        sl = lambda c, n: (slice(1 + c, n - 1 + c))
+        shifted = g[sl(CZ[j], Z), sl(CY[j], Y), sl(CX[j], X)]
+        bad |= bool((fluid[1:Z - 1, 1:Y - 1, 1:X - 1] & shifted).any())
+    return bad
+
+
+def test_cfg4_full_mass_closure_and_slabs():
+    case = workloads.catalogue()["cfg4"]
+    steps = 60
+    out = []
+    for n_slabs in (1, 2):
+        lb, st = _engine(case, n_slabs)
+        X, Y, Z = st.params["size"]
+        lb.run(steps)
+        lb.synchronize()
+        out.append(lb.fetch(("type_flags", "mass", "n", "u")))
+        lb.close()
+    one, two = out
+    tf = one["type_flags"]
+    act = _active(tf)
+    m0 = float(st.mass[_active(st.type_flags)].sum())
+    m1 = float(one["mass"][act].sum())
+    assert abs(m1 - m0) <= 1e-9 * m0, (m0, m1)
+    assert np.count_nonzero(tf != st.type_flags) > 1000, "the dam did not move"
+    assert not _fluid_touches_gas(tf.reshape(Z, Y, X), st.params["boundary"])
+    assert np.array_equal(two["type_flags"], tf)
+    for k in ("mass", "n", "u"):
+        assert common.max_rel(two[k][act], one[k][act]) <= 1e-9, k
+
+
+def test_cfg5_section_volume_closure_and_slabs():
+    case = workloads.materialise(dict(workloads.catalogue()["cfg5"]))
+    case["lbSizeZ"] = 258
+    case["fluid_box"] = (0, 160, 0, 255, 0, 257)
+    case["elements"] = [e for e in case["elements"] if e["x0"][2] + e["radius"] < 256.5]
+    assert len(case["elements"]) > 4000
+    parts, elmts, comps = li.expand_elements(case["elements"])
+    x0 = parts["x0"].copy()
+    steps = 12
+    res = []
+    for n_slabs in (1, 4):
+        p = parts.copy()
+        xe = x0.copy()
+        lb, st = _engine(case, n_slabs, parts=p)
+        X, Y, Z = st.params["size"]
+        for s in range(steps):
+            li.advance_kinematic(p, elmts, xe, 1.0)
+            lb.latticeBoltzmannFreeSurfaceStep()
+            lb.latticeBoltzmannCouplingStep(s % 5 == 0, elmts, p, comps)
+            F, M, V, W = lb.latticeBolzmannStep(elmts, p)
+        d = lb.fetch(("type_flags", "solidIndex", "mass", "n"))
+        res.append((d, F, M, V))
+        lb.close()
+    (d1, F1, M1, V1), (d4, F4, M4, V4) = res
+    tf = d1["type_flags"]
+    assert np.array_equal(d4["type_flags"], tf)
+    act = _active(tf)
+    pf = act & ((tf & 0x10) != 0)
+    assert np.array_equal(d4["solidIndex"][pf], d1["solidIndex"][pf])
+    assert common.max_rel(d4["mass"][act], d1["mass"][act]) <= 1e-9
+    fscale = np.abs(F1).max()
+    assert np.abs(F4 - F1).max() <= 1e-9 * fscale
+    assert np.abs(M4 - M1).max() <= 1e-9 * fscale * 4.0
+    assert np.abs(V4 - V1).max() <= 1e-9 * np.abs(V1).max()
+    # the fluid volume handed to DEM is the mass of the cells flagged for that element (LB.cpp:1897-1902)
+    vol = np.bincount(d1["solidIndex"][pf], weights=d1["mass"][pf], minlength=len(elmts))
+    assert np.abs(vol - V1).max() <= 1e-9 * max(np.abs(V1).max(), 1.0)
+    assert not _fluid_touches_gas(tf.reshape(Z, Y, X), st.params["boundary"])
+    # moving spheres exert forces: not a trivial state
+    assert np.count_nonzero(np.abs(F1).sum(axis=1) > 0) > 0.9 * len(elmts)
