@@ -94,6 +94,7 @@ struct Slab {
     DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
     DevBuf<uint8_t> type0, type1, mark;
     DevBuf<uint32_t> solidIndex, bulk;
+    DevBuf<uint32_t> curveRow;  // curved walls: row of the handle's curveDelta per cell
     DevBuf<uint32_t> staticList, staticCount;  // PART 2 of the split step kernel: owned non-bulk cells that can be active
     uint32_t nStatic = 0;
     // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
@@ -144,6 +145,10 @@ struct LbGpuHandle {
     bool macroValid = true, lastStepFirst = false, lastStepCoupled = false, typesFlipped = false, listsFresh = false;
     uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
+    // curved walls (type 9) and LB::enforceMassConservation (problemName DRUM)
+    bool hasCurved = false, curvesSet = false, enforceMass = false;
+    double totalMass = 0.0;
+    DevBuf<double> curveDelta;
     double uLength = 1, uSpeed = 1, uAngVel = 1, uForce = 1, uTorque = 1, uVolume = 1;
     // CUDA-event pairs around the fused step kernel of the last lbGpuStep/lbGpuRun call (ring of KEV)
     static constexpr uint32_t KEV = 512;
@@ -207,6 +212,7 @@ Dev dev_for(LbGpuHandle* h, Slab* s) {
     d.list = s->cellList.p; d.nList = s->listCounts.p;  // list-driven kernels: the interface cells unless told otherwise
     d.cand = s->candList.p; d.nCand = s->listCounts.p + 3;
     d.lazyMass = 0;
+    d.curveRow = s->curveRow.p; d.curveDelta = h->curveDelta.p; d.shearState = h->shear ? 1 : 0;
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
     d.cellBegin = s->ownBegin; d.cellEnd = s->ownEnd;
@@ -510,6 +516,23 @@ int free_surface_step(LbGpuHandle* h) {
         k_redistribute<true><<<s->listGrid, BLOCK, 0, st>>>(fsdev(s), s0->scal.p + 1);
         ++h->launches;
     }
+    if (h->enforceMass) {
+        // LB::enforceMassConservation (LB.cpp:1806-1822; DRUM): total mass, then redistributeMass(-0.01*deficit)
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            k_mass_total<<<own_blocks(s), BLOCK, 0, st>>>(fsdev(s), s->partial.p);
+            k_reduce_partials<<<1, 1024, 0, st>>>(s->partial.p, own_blocks(s), 1, s->sums.p + 3, 0);
+            h->launches += 2;
+            if (s != s0) { k_add_arrays<<<1, 32, 0, st>>>(s0->sums.p + 3, s->sums.p + 3, 1); ++h->launches; }
+        }
+        if ((rc = allreduce_sum(h, s0->sums.p + 3, 1, lbcomm::ncclFloat64))) return rc;
+        k_mass_deficit_finalize<<<1, 1, 0, st>>>(s0->sums.p + 3, h->totalMass, s0->counters.p, s0->scal.p + 3);
+        ++h->launches;
+        for (auto& sp : h->slabs) {
+            k_redistribute<true><<<sp->listGrid, BLOCK, 0, st>>>(fsdev(sp.get()), s0->scal.p + 3);
+            ++h->launches;
+        }
+    }
     // new interface cells carry n, u, visc taken from their donors: refresh everything a neighbour may read
     if ((rc = exchange(h, G_TYPE | G_MASS | G_MACRO | G_VISC | G_HF))) return rc;
     h->typesFlipped = true;  // until the step kernel has run: tbuf(1) holds the types of before this update
@@ -595,6 +618,8 @@ int lb_step(LbGpuHandle* h) {
     const bool fsOn = h->fs;
     cudaStream_t st = h->stream;
     int rc;
+    if (h->hasCurved && !h->curvesSet)
+        return fail(LBGPU_EINVAL, "the lattice has curved-wall cells (type 9): call lbGpuSetCurves before the first step");
     const int nSums = 1 + 3 * h->prm.nWalls;
     const bool split = step_is_split(h->shear, macro, couple, fsOn, h->dynWall);
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, split ? 1 : 0);
@@ -605,7 +630,7 @@ int lb_step(LbGpuHandle* h) {
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
     CU(cudaEventRecord(h->kev0[ke], st));
-    const uint32_t what = G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u);
+    const uint32_t what = G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u) | (h->hasCurved ? (G_MACRO | G_VISC) : 0u);
     // Slabs of other processes: the two face planes are updated first and travel (NCCL, comm stream) while the
     // interior is updated.  Moving walls keep the plain order (their per-block partial sums are indexed by block).
     int down = -1, up = -1;
@@ -662,6 +687,18 @@ int lb_step(LbGpuHandle* h) {
     if ((rc = exchange(h, what, true, !overlap))) return rc;
     if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
     Slab* s0 = h->slabs[0].get();
+    if (h->hasCurved && fsOn) {
+        // extraMass of the curved links, after every cell's n, u of this step are in place (ghosts included)
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            if (!s->nStatic) continue;
+            Dev d = dev_for(h, s);
+            d.pStride = s->blocks; d.pBase = 0;
+            d.list = s->staticList.p; d.nList = s->staticCount.p + 1;
+            k_curved_extra_mass<<<(s->nStatic + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
+            ++h->launches;
+        }
+    }
     if (h->dynWall) {
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
@@ -950,10 +987,10 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     const unsigned long long XY = (unsigned long long)prm->size[0] * prm->size[1];
     const unsigned long long Nh = XY * (unsigned long long)(zHi - zLo + 2);  // cells in the host arrays
     if (Nh >= (1ull << 31)) return fail(LBGPU_EINVAL, "lbGpuInit: %llu cells exceed the 2^31 index range", Nh);
-    bool anyDyn = false, anyGas = false, anyIface = false, anySlip = false;
+    bool anyDyn = false, anyGas = false, anyIface = false, anySlip = false, anyCurved = false;
     for (unsigned long long i = 0; i < Nh; ++i) {
         const int t = type_flags[i] & LBGPU_TYPE_MASK;
-        if (t == T_CURVED) return fail(LBGPU_EUNSUPPORTED, "lbGpuInit: curved walls (type 9, LB.cpp:1278-1319) are not implemented");
+        anyCurved |= (t == T_CURVED);
         if (t == 1 || t > 9) return fail(LBGPU_EINVAL, "lbGpuInit: cell %llu has undefined type %d", i, t);
         anyDyn |= (t == T_DYN_WALL || t == T_SLIP_DYN);
         anySlip |= (t == T_SLIP_STAT || t == T_SLIP_DYN);
@@ -984,9 +1021,11 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->fs = prm->freeSurface != 0;
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);
-        h->dynWall = anyDyn;
+        // curved links use the moving-wall machinery: stored n, u and the extraMass sum (LB.cpp:1278-1319)
+        h->hasCurved = anyCurved;
+        h->dynWall = anyDyn || anyCurved;
         h->slip = anySlip;
-        h->macroAlways = h->fs || anyDyn || anyGas || anyIface;
+        h->macroAlways = h->fs || anyDyn || anyCurved || anyGas || anyIface;
         // measureUnits::setComposite (node.cpp:476-488)
         const double L = prm->unitLength, Tm = prm->unitTime, D = prm->unitDensity;
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
@@ -1049,6 +1088,38 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     rc = body();
     if (rc) { lbGpuFinalize(h); return rc; }
     *out = h;
+    return LBGPU_OK;
+}
+
+int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, const double* delta) {
+    if (!h) return fail(LBGPU_EINVAL, "lbGpuSetCurves: null handle");
+    if (nCurves && (!cells || !delta)) return fail(LBGPU_EINVAL, "lbGpuSetCurves: null array");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(h->curveDelta.alloc((size_t)nCurves * Q + 1));
+    if (nCurves) CU(cudaMemcpy(h->curveDelta.p, delta, sizeof(double) * Q * (size_t)nCurves, cudaMemcpyHostToDevice));
+    // host arrays start at the plane below the handle's first slab
+    const long long hostZ0 = (long long)h->slabs.front()->zBegin - 1;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        std::vector<uint32_t> row(s->N, 0xffffffffu);
+        const long long shift = ((long long)s->zBegin - 1 - hostZ0) * (long long)s->XY;
+        for (uint32_t k = 0; k < nCurves; ++k) {
+            const long long loc = (long long)cells[k] - shift;
+            if (loc >= 0 && loc < (long long)s->N) row[(size_t)loc] = k;
+        }
+        CU(s->curveRow.alloc(s->N));
+        CU(cudaMemcpy(s->curveRow.p, row.data(), sizeof(uint32_t) * s->N, cudaMemcpyHostToDevice));
+    }
+    h->curvesSet = true;
+    return LBGPU_OK;
+}
+
+int lbGpuSetMassTarget(LbGpuHandle* h, double totalMass) {
+    if (!h) return fail(LBGPU_EINVAL, "lbGpuSetMassTarget: null handle");
+    if (!h->fs) return fail(LBGPU_EINVAL, "lbGpuSetMassTarget: the lattice has no free surface");
+    h->enforceMass = true;
+    h->totalMass = totalMass;
     return LBGPU_OK;
 }
 

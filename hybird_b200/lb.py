@@ -64,6 +64,19 @@ class LB:
                                      abi.ptr(m_), abi.ptr(v_), C.byref(self.h)))
         return self
 
+    # -- LB::curves (LB.h:63-64) as LB::initializeCurved left them; LB::totalMass for problemName DRUM -------
+    def setCurves(self, cells, delta):
+        cells = np.ascontiguousarray(cells, dtype=np.uint32)
+        delta = np.ascontiguousarray(delta, dtype=np.float64)
+        if delta.size != abi.Q * cells.size:
+            raise ValueError("setCurves: delta must hold 19 values per curved cell")
+        abi.check(self.lib.lbGpuSetCurves(self.h, cells.size, abi.ptr(cells), abi.ptr(delta)))
+        return self
+
+    def setMassTarget(self, totalMass):
+        abi.check(self.lib.lbGpuSetMassTarget(self.h, float(totalMass)))
+        return self
+
     # -- LB::latticeBoltzmannFreeSurfaceStep (LB.h:161) ------------------------------------------
     def latticeBoltzmannFreeSurfaceStep(self):
         self._fs_requested = True

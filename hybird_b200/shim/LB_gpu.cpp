@@ -219,6 +219,19 @@ void LB::latticeBolzmannInit(cylinderList& cylinders, wallList& walls, particleL
         }
     }
     if (lbGpuInit(&prm, tf.data(), solid.data(), f.data(), n.data(), u.data(), mass.data(), visc.data(), &st.h)) die("lbGpuInit");
+    // curved walls (LB::curves, LB.cpp:363-367, 581-603) and the DRUM mass target (LB.cpp:205-209, 239-244)
+    {
+        std::vector<uint32_t> cells;
+        std::vector<double> delta;
+        for (size_t i = 0; i < N; ++i) {
+            if (curves[i] == 0) continue;
+            cells.push_back((uint32_t)i);
+            delta.push_back(0.0);  // delta[0] is neither initialised nor read by the reference
+            for (int j = 1; j < 19; ++j) delta.push_back(curves[i]->delta[j]);
+        }
+        if (!cells.empty() && lbGpuSetCurves(st.h, (uint32_t)cells.size(), cells.data(), delta.data())) die("lbGpuSetCurves");
+        if (problemName == DRUM && freeSurface && lbGpuSetMassTarget(st.h, totalMass)) die("lbGpuSetMassTarget");
+    }
     cout << "lbgpu shim: " << N << " cells uploaded to the GPU" << (st.verify ? " (verify mode: the reference steps alongside)" : "") << endl;
 }
 

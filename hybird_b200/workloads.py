@@ -153,6 +153,17 @@ def catalogue():
         elements=_sphere_bed(14, (1.5, 1.5, 1.5), (46.5, 18.5, 13.5), 2.2, 3.0, 12345), motion="kin", rescan_every=6)
     for e in C["cfg5_mini"]["elements"]:
         e["x1"] = [0.02, 0.0, -0.01]
+    # --- curved walls (Mei-Luo-Shyy) and LB::enforceMassConservation: the reference's rotating DRUM geometry
+    # (DEM.cpp:876-890, LB.cpp:734-748) scaled to a 38x10x50 lattice; unitDensity is chosen so that the mass target
+    # fluidMass/unit.Mass (LB.cpp:205-208) is close to the mass the fluid region actually holds
+    C["drum_mini"] = make_case(
+        "drum_mini", problemName="DRUM", unitLength=0.05, unitTime=8e-4, unitDensity=2049.0, lbSizeX=1.9, lbSizeY=0.5,
+        lbSizeZ=2.5, boundary2=4, boundary3=4, freeSurfaceSolve=1, lbFZ=-9.81, initVisc=320.0, plasticVisc=320.0,
+        drumSpeed=1.5, fluidMass=400.0)
+    C["drum_bingham"] = make_case(
+        "drum_bingham", problemName="DRUM", unitLength=0.0625, unitTime=1e-3, unitDensity=1308.0, lbSizeX=1.9,
+        lbSizeY=0.5, lbSizeZ=2.5, boundary2=7, boundary3=8, freeSurfaceSolve=1, nonNewtonianSolve=1, lbFZ=-9.81,
+        initVisc=200.0, plasticVisc=200.0, yieldStress=20.0, drumSpeed=-1.2, fluidMass=500.0)
     # cfg 5 at full size: 1024x256x256 with the long (flow) axis stored slowest, i.e. as the lattice's z (the engine
     # cuts slabs along z); depth is x (fluid for x <= 160, gravity along -x), y periodic, 20 000 spheres r in [3,4]
     # by random sequential addition (seed 12345) inside the fluid.  The bed is generated on demand (materialise).

@@ -38,7 +38,7 @@ enum {
     LBGPU_EINVAL = -1,      /* bad argument */
     LBGPU_ENODEVICE = -2,   /* no CUDA device / driver */
     LBGPU_ECUDA = -3,       /* CUDA runtime error */
-    LBGPU_EUNSUPPORTED = -4,/* feature of the reference not implemented (curved walls, type 9) */
+    LBGPU_EUNSUPPORTED = -4,/* configuration outside what the engine handles (slab axis, list capacities) */
     LBGPU_ETYPE = -5,       /* "TYPE ERROR" of LB::streaming (LB.cpp:1458-1461): link to an illegal cell type */
     LBGPU_ECOMM = -6        /* multi-GPU halo transport error */
 };
@@ -106,6 +106,17 @@ int lbGpuCommFinalize(void);
  */
 int lbGpuInit(const LbGpuParams* params, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
               const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out);
+
+/* Curved walls (type 9; problem geometries with a cylinder: DRUM / AVALANCHE / NET).  LB::curves (LB.h:63-64) as
+ * LB::initializeCurved (LB.cpp:589-603) left it: cells[k] is the cell index of the k-th `curve` object in the host
+ * arrays' order, delta[19*k + j] its curve::delta[j] (node.h:133-148; m1, m2 and chi follow from delta, node.cpp:458-472).
+ * Must be called after lbGpuInit and before the first step of a lattice that holds type-9 cells; a slab handle passes
+ * the cells of its own planes (indices relative to its host arrays), the others are ignored. */
+int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, const double* delta /* 19*nCurves */);
+
+/* problemName == DRUM: LB::enforceMassConservation (LB.cpp:1806-1822) runs after every free-surface update with
+ * LB::totalMass = totalMass (lattice units, LB.cpp:204-218). */
+int lbGpuSetMassTarget(LbGpuHandle* h, double totalMass);
 
 /* One goCycle worth of LB work, in the reference's order: free-surface step (if doFreeSurface),
  * coupling step (if doCoupling; rescanParticles = dem.newNeighborList), LB step.

@@ -50,6 +50,10 @@ def run_case(case, steps, workdir="/tmp/hb_cases", dumps=None, verbose=True, typ
     hdr = lbo.read_log(out + "_log.txt")
     st0 = lbo.read_state(out + "_state%06d.bin" % 0)
     o = lbo.Oracle(hdr, st0["type_flags"], st0["solidIndex"], st0["n"], st0["u"], st0["mass"], st0["visc"], f=st0["f"])
+    if len(st0.get("curve_cells", ())):
+        o.set_curves(st0["curve_cells"], st0["curve_delta"])
+    if hdr.get("enforceMass"):
+        o.set_mass_target(hdr["totalMass"])
     trace = lbo.read_particle_trace(out + "_parts.bin")
     forces = lbo.read_forces(out + "_forces.bin", hdr["nElmts"], hdr["nWalls"])
     N = int(np.prod(hdr["size"]))

@@ -10,8 +10,9 @@
  * OMP_NUM_THREADS=1.  Floating-point expressions are written with the reference's association
  * (x86-64 SSE2, no FMA contraction: build with -ffp-contract=off).
  *
- * Not restated (reported as unsupported by lbo_create): curved walls (type 9, DRUM/AVALANCHE/NET
- * geometries only, LB.cpp:1278-1319) and LB::enforceMassConservation (DRUM only, LB.cpp:1806).
+ * Curved walls (type 9, DRUM/AVALANCHE/NET geometries, LB.cpp:1278-1319) need their link fractions
+ * (lbo_set_curves); LB::enforceMassConservation (DRUM only, LB.cpp:1806-1822) runs once a mass
+ * target is set (lbo_set_mass_target).
  */
 #include "lb_oracle.h"
 
@@ -58,6 +59,11 @@ struct LboState {
     uint32_t* solidIndex;
     double *f, *fs, *n, *u, *hydroForce, *mass, *newMass, *visc, *shearRate;
     uint8_t* mark;
+    uint32_t* curveRow;  /* per cell: row of curveDelta, UINT32_MAX for cells without a `curve` object (LB.cpp:363-367) */
+    double* curveDelta;  /* [nCurves][19]: curve::delta (node.h:133-148) */
+    uint32_t nCurves;
+    int enforceMass;     /* problemName == DRUM (LB.cpp:239-244) */
+    double totalMass;    /* LB::totalMass (LB.cpp:204-218) */
     uint32_t *listA, *listB, *listC, *listD; /* scratch index lists, capacity N each */
 };
 
@@ -161,11 +167,6 @@ LboState* lbo_create(const LboParams* p, const uint8_t* type_flags, const uint32
     memcpy(s->type, type_flags, N);
     memcpy(s->solidIndex, solidIndex, sizeof(uint32_t) * N);
     for (uint32_t i = 0; i < N; ++i) {
-        if (T(s, i) == LBO_CURVED) {
-            fprintf(stderr, "lb_oracle: curved walls (type 9) are not restated\n");
-            lbo_destroy(s);
-            return NULL;
-        }
         if (!(s->type[i] & LBO_NODE_BIT)) continue;
         s->n[i] = n[i];
         s->mass[i] = mass[i];
@@ -187,7 +188,24 @@ void lbo_destroy(LboState* s) {
     free(s->type); free(s->solidIndex); free(s->f); free(s->fs); free(s->n); free(s->u); free(s->hydroForce);
     free(s->mass); free(s->newMass); free(s->visc); free(s->shearRate); free(s->mark);
     free(s->listA); free(s->listB); free(s->listC); free(s->listD);
+    free(s->curveRow); free(s->curveDelta);
     free(s);
+}
+
+/* LB::curves as LB::initializeCurved left it (LB.cpp:589-603): delta[j] per curved-wall cell */
+void lbo_set_curves(LboState* s, uint32_t nCurves, const uint32_t* cells, const double* delta) {
+    free(s->curveRow); free(s->curveDelta);
+    s->curveRow = (uint32_t*)malloc(sizeof(uint32_t) * s->N);
+    for (uint32_t i = 0; i < s->N; ++i) s->curveRow[i] = UINT32_MAX;
+    s->curveDelta = (double*)malloc(sizeof(double) * Q * (nCurves ? nCurves : 1));
+    memcpy(s->curveDelta, delta, sizeof(double) * Q * nCurves);
+    for (uint32_t k = 0; k < nCurves; ++k) s->curveRow[cells[k]] = k;
+    s->nCurves = nCurves;
+}
+
+void lbo_set_mass_target(LboState* s, double totalMass) {
+    s->enforceMass = 1;
+    s->totalMass = totalMass;
 }
 
 uint32_t lbo_nodes(const LboState* s) { return s->N; }
@@ -363,9 +381,20 @@ static void updateInterface(LboState* s) {
     redistributeMass(s, massSurplus, iface, nIf);
 }
 
+/* LB::enforceMassConservation (LB.cpp:1806-1822) */
+static void enforceMassConservation(LboState* s) {
+    double thisMass = 0.0;
+    for (uint32_t i = 0; i < s->N; ++i)
+        if (isActiveT(T(s, i)) && !(s->type[i] & LBO_P_BIT)) thisMass += s->mass[i];
+    const double massDeficit = (thisMass - s->totalMass);
+    const uint32_t nIf = listInterface(s, s->listA);
+    redistributeMass(s, -0.01 * massDeficit, s->listA, nIf);
+}
+
 void lbo_free_surface_step(LboState* s) {
     updateMass(s);
     updateInterface(s);
+    if (s->enforceMass) enforceMassConservation(s);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -574,6 +603,32 @@ static void streaming(LboState* s, double* wallFHydro, uint32_t nWalls) {
                 const double usq = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
                 const double vuj = u[0] * VX[j] + u[1] * VY[j] + u[2] * VZ[j];
                 f[OPP[j]] = -fs[j] + W[j] * s->initDensity * (2.0 + C2x2 * (vuj * vuj) - C3x2 * usq);
+            } else if (tl == LBO_CURVED) {
+                /* Mei-Luo-Shyy (LB.cpp:1278-1319), curve::getChi / computeCoefficients (node.cpp:458-472) */
+                if (!s->curveRow || s->curveRow[link] == UINT32_MAX) {
+                    fprintf(stderr, "lb_oracle: curved wall cell %u without curve data\n", link);
+                    exit(3);
+                }
+                const double C1 = 3.0 * LBM_DT * LBM_DT, C2 = 4.5 * LBM_DT * LBM_DT * LBM_DT * LBM_DT, C3 = 1.5 * LBM_DT * LBM_DT;
+                const double* vel = &s->u[3 * link];
+                const double BBi = BBCoeff * s->n[it] * W[j] * (vel[0] * VX[j] + vel[1] * VY[j] + vel[2] * VZ[j]);
+                const double delta = s->curveDelta[(size_t)Q * s->curveRow[link] + OPP[j]];
+                const double tau = 0.5 + 3.0 * s->visc[it];
+                const double chi = (delta >= 0.5) ? (2.0 * delta - 1.0) / tau : (2.0 * delta - 1.0) / (tau - 2.0);
+                double ubf[3] = { 0.0, 0.0, 0.0 };
+                if (delta >= 0.5) {
+                    const double m1 = (delta - 1) / delta, m2 = 1 / delta;
+                    for (int k = 0; k < 3; ++k) ubf[k] = m1 * u[k] + m2 * vel[k];
+                } else {
+                    const uint32_t linkBack = nbr(s, it, OPP[j]);
+                    const double* src = (T(s, linkBack) == LBO_FLUID && (s->type[linkBack] & LBO_NODE_BIT)) ? &s->u[3 * linkBack] : vel;
+                    for (int k = 0; k < 3; ++k) ubf[k] = src[k];
+                }
+                const double usq = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+                const double vu = u[0] * VX[j] + u[1] * VY[j] + u[2] * VZ[j];
+                const double fStar = s->n[it] * W[j] * (1 + C1 * (VX[j] * ubf[0] + VY[j] * ubf[1] + VZ[j] * ubf[2]) + C2 * vu * vu + C3 * usq);
+                f[OPP[j]] = (1.0 - chi) * fs[j] + chi * fStar - BBi;
+                extraMass += s->mass[it] * (chi * fs[j] - chi * fStar + BBi);
             } else if (tl == LBO_DYN_WALL) {
                 const double* vel = &s->u[3 * link];
                 const double BBi = BBCoeff * s->n[it] * W[j] * (vel[0] * VX[j] + vel[1] * VY[j] + vel[2] * VZ[j]);

@@ -52,6 +52,10 @@ typedef struct LboState LboState;
 LboState* lbo_create(const LboParams* p, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
                      const double* n, const double* u, const double* mass, const double* visc);
 void lbo_destroy(LboState* s);
+/* curved-wall cells (type 9): delta[19] of each (curve::delta, node.h:133-148), as LB::initializeCurved computed them */
+void lbo_set_curves(LboState* s, uint32_t nCurves, const uint32_t* cells, const double* delta);
+/* problemName == DRUM: LB::enforceMassConservation (LB.cpp:1806-1822) after every free-surface update */
+void lbo_set_mass_target(LboState* s, double totalMass);
 
 /* LB::latticeBoltzmannFreeSurfaceStep (LB.cpp:235-245) */
 void lbo_free_surface_step(LboState* s);

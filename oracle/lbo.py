@@ -63,6 +63,8 @@ def lib():
         L.lbo_count_type.restype = C.c_uint32
         L.lbo_count_type.argtypes = [vp, C.c_int]
         L.lbo_set_threads.argtypes = [C.c_int]
+        L.lbo_set_curves.argtypes = [vp, C.c_uint32, vp, vp]
+        L.lbo_set_mass_target.argtypes = [vp, C.c_double]
         _lib = L
     return _lib
 
@@ -101,6 +103,15 @@ class Oracle:
             raise RuntimeError("lbo_create failed")
         self._keep = None
         self.nWalls = int(params.get("nWalls", 0))
+
+    def set_curves(self, cells, delta):
+        cells = np.ascontiguousarray(cells, dtype=np.uint32)
+        delta = np.ascontiguousarray(delta, dtype=np.float64)
+        assert delta.size == Q * cells.size
+        self.L.lbo_set_curves(self.h, cells.size, _ptr(cells), _ptr(delta))
+
+    def set_mass_target(self, total_mass):
+        self.L.lbo_set_mass_target(self.h, float(total_mass))
 
     def close(self):
         if self.h:
@@ -182,6 +193,12 @@ def read_state(path):
     out["shearRate"] = take("<f8", N)
     if withNb:
         out["neighbors"] = take("<u4", 19 * N, (N, 19))
+    if raw[off:off + 7] == b"CURVES1":  # curved-wall cells and the mass target (trailer)
+        off += 8
+        nc = int(take("<u4", 1)[0])
+        out["curve_cells"] = take("<u4", nc)
+        out["curve_delta"] = take("<f8", 19 * nc, (nc, 19))
+        out["totalMass"] = float(take("<f8", 1)[0])
     # combined byte as the oracle / CUDA engine use it: t | p<<4 | node<<5
     out["type_flags"] = (out["type"] | ((out["flags"] & 1) << 4) | ((out["flags"] & 2) << 4)).astype(np.uint8)
     return out
@@ -213,6 +230,9 @@ def read_log(path):
     j = toks.index("flags")
     hdr["freeSurface"], hdr["forceField"], hdr["nonNewtonian"], hdr["turbulence"] = \
         int(toks[j + 2]), int(toks[j + 4]), int(toks[j + 6]), int(toks[j + 8])
+    if "totalMass" in toks:
+        hdr["totalMass"] = nums("totalMass", 1)[0]
+        hdr["enforceMass"] = nums("enforceMass", 1, int)[0]
     return hdr
 
 

@@ -181,8 +181,12 @@ void initLB(LB& lb, DEM& dem, const Args& a) {
     lb.initializeWalls(dem.walls, dem.cylinders, dem.objects);
     lb.cleanLists();
     lb.totalMass = 0.0;
-    for (unsigned it = 0; it < lb.nodes.size(); ++it)
-        if (lb.types[it].isActive() && !lb.types[it].isInsideParticle()) lb.totalMass += lb.nodes[it]->mass;
+    if (problemName == DRUM) {  // LB.cpp:205-209
+        lb.totalMass = lb.fluidMass / lb.unit.Mass;
+    } else {
+        for (unsigned it = 0; it < lb.nodes.size(); ++it)
+            if (lb.types[it].isActive() && !lb.types[it].isInsideParticle()) lb.totalMass += lb.nodes[it]->mass;
+    }
 }
 
 template <class T> void wr(FILE* f, const T* p, size_t n) {
@@ -224,6 +228,22 @@ void dumpState(const LB& lb, const DEM& dem, const std::string& path, unsigned s
         std::vector<uint32_t> d((size_t)19 * N);
         for (unsigned i = 0; i < N; ++i) for (int j = 0; j < 19; ++j) d[(size_t)19 * i + j] = lb.neighbors[i].d[j];
         wr(fp, d.data(), d.size());
+    }
+    // trailer: curved-wall cells (LB::curves, node.h:133-148): count, cell indices, delta[19] each (delta[0] is never
+    // initialised by the reference nor read: written as 0), then totalMass (LB::enforceMassConservation's target)
+    {
+        const char cm[8] = { 'C', 'U', 'R', 'V', 'E', 'S', '1', 0 };
+        wr(fp, cm, 8);
+        std::vector<uint32_t> idx;
+        for (unsigned i = 0; i < N; ++i) if (lb.curves[i] != 0) idx.push_back(i);
+        uint32_t nc = (uint32_t)idx.size();
+        wr(fp, &nc, 1);
+        wr(fp, idx.data(), idx.size());
+        std::vector<double> dl((size_t)19 * idx.size(), 0.0);
+        for (size_t k = 0; k < idx.size(); ++k) for (int j = 1; j < 19; ++j) dl[19 * k + j] = lb.curves[idx[k]]->delta[j];
+        wr(fp, dl.data(), dl.size());
+        double tm = lb.totalMass;
+        wr(fp, &tm, 1);
     }
     fclose(fp);
 }
@@ -299,6 +319,7 @@ int main(int argc, char** argv) {
                 lb.initVelocity.x, lb.initVelocity.y, lb.initVelocity.z, lb.boundary[0], lb.boundary[1], lb.boundary[2],
                 lb.boundary[3], lb.boundary[4], lb.boundary[5], (int)lb.freeSurface, (int)lb.forceField,
                 (int)lb.nonNewtonian, (int)lb.turbulenceOn);
+        fprintf(logFp, "# totalMass %.17g enforceMass %d\n", lb.totalMass, (int)(problemName == DRUM));
         if (a.dumps.count(0)) dumpState(lb, dem, a.out + "_state000000.bin", 0, a.dumpNeighbors);
     }
     auto writeTypes = [&]() {

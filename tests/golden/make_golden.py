@@ -41,6 +41,7 @@ STEPS = {
     "cfg3_mini": 40, "sphere_kin": 40, "two_spheres_kin": 40, "cluster_dem": 40,
     "cfg4_mini": 100, "dam_newtonian": 100, "droplet": 100, "bubble_periodic": 100,
     "cfg1_mini": 100, "cfg5_mini": 100,
+    "drum_mini": 300, "drum_bingham": 200,
 }
 
 
@@ -78,6 +79,8 @@ def generate(name, workdir="/tmp/hb_golden"):
         forces=np.fromfile(out + "_forces.bin", dtype="<f8"),
         types=np.fromfile(out + "_types.bin", dtype=np.uint8).reshape(-1, N),
     )
+    if len(st0.get("curve_cells", ())):
+        d["curve_cells"] = st0["curve_cells"]; d["curve_delta"] = st0["curve_delta"]
     d["sha_init_f"] = sha(st0["f"][np.isin(st0["type"], (0, 3))] + 0.0)
     for s in cs:
         st = lbo.read_state(out + "_state%06d.bin" % s)

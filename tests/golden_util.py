@@ -54,6 +54,14 @@ class Golden:
         z = self.z
         return (z["init_type_flags"], z["init_solidIndex"], z["init_n"], z["init_u"], z["init_mass"], z["init_visc"])
 
+    def configure(self, engine):
+        """Curved-wall data and the DRUM mass target, for either engine (oracle or GPU mirror)."""
+        if "curve_cells" in self.z.files:
+            (engine.setCurves if hasattr(engine, "setCurves") else engine.set_curves)(self.z["curve_cells"], self.z["curve_delta"])
+        if self.params.get("enforceMass"):
+            (engine.setMassTarget if hasattr(engine, "setMassTarget") else engine.set_mass_target)(self.params["totalMass"])
+        return engine
+
     def hashes(self, step):
         return {k: str(self.z["sha_%s_%d" % (k, step)]) for k in FIELDS}
 

@@ -25,7 +25,7 @@ def _gpu(g):
     prm = dict(g.params)
     lb = LB(prm)
     lb.latticeBolzmannInit(*g.init_arrays())
-    return lb
+    return g.configure(lb)
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -33,7 +33,7 @@ def test_gpu_matches_reference_golden_and_oracle(name, oracle_lib):
     import lbo
     g = gu.Golden(name)
     lb = _gpu(g)
-    o = lbo.Oracle(dict(g.params), *g.init_arrays())
+    o = g.configure(lbo.Oracle(dict(g.params), *g.init_arrays()))
     it_o = gu.replay(g, o, None)
     exact_fail = []
     for s, F, M, V, W in gu.replay(g, lb, None):

@@ -72,7 +72,7 @@ def test_shipped_config_through_both_drivers(tmp_path):
         assert np.allclose(a, b, rtol=2e-5, atol=1e-12), (name, np.abs(a - b).max())
 
 
-@pytest.mark.parametrize("name,steps", [("cfg3_mini", 60), ("cluster_dem", 40), ("cfg1_mini", 60)])
+@pytest.mark.parametrize("name,steps", [("cfg3_mini", 60), ("cluster_dem", 40), ("cfg1_mini", 60), ("drum_mini", 150)])
 def test_verify_mode_reference_steps_alongside(name, steps, tmp_path):
     _need_binaries()
     case = dict(cases.catalogue()[name])

@@ -23,6 +23,7 @@ def _run(g, n_slabs, steps):
     prm["nLocalSlabs"] = n_slabs
     lb = LB(prm)
     lb.latticeBolzmannInit(*g.init_arrays())
+    g.configure(lb)
     forces = []
     for s, F, M, V, W in gu.replay(g, lb, None):
         forces.append((F.copy(), M.copy(), V.copy(), W.copy()))
@@ -34,7 +35,7 @@ def _run(g, n_slabs, steps):
 
 
 @pytest.mark.parametrize("name", ["cfg2_mini", "cfg3_mini", "cfg4_mini", "cfg5_mini", "periodic_all", "bubble_periodic",
-                                  "couette_dyn", "slip_dyn", "two_spheres_kin", "cluster_dem"])
+                                  "couette_dyn", "slip_dyn", "two_spheres_kin", "cluster_dem", "drum_mini"])
 @pytest.mark.parametrize("n_slabs", [2, 3])
 def test_slabs_on_one_device_match_the_undivided_lattice(name, n_slabs):
     g = gu.Golden(name)

@@ -11,7 +11,7 @@ NAMES = gu.names()
 
 
 def test_fixtures_present():
-    assert len(NAMES) >= 20, "golden fixtures missing: run tests/golden/make_golden.py where /root/reference exists"
+    assert len(NAMES) >= 22, "golden fixtures missing: run tests/golden/make_golden.py where /root/reference exists"
 
 
 @pytest.mark.parametrize("name", NAMES)
@@ -20,7 +20,7 @@ def test_oracle_matches_reference_golden(name, oracle_lib):
     g = gu.Golden(name)
     tf, si, n, u, mass, visc = g.init_arrays()
     prm = dict(g.params)
-    o = lbo.Oracle(prm, tf, si, n, u, mass, visc)  # f=None: equilibrium of (n,u), node::initialize
+    o = g.configure(lbo.Oracle(prm, tf, si, n, u, mass, visc))  # f=None: equilibrium of (n,u), node::initialize
     active0 = np.isin(tf & 0x0F, (0, 3))
     assert gu.sha(np.array(o.f)[active0] + 0.0) == str(g.z["sha_init_f"]), "initial populations differ"
     assert np.array_equal(o.type_flags & 0x1F, g.types[0])
