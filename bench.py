@@ -324,7 +324,12 @@ def main_ours(args, rank, world, local_rank):
                      "kernel_ms": kern_avg_ms},
         "e2e": {"value": e2e_mlups, "unit": "MLUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "call": "lbGpuStep(host particle/element arrays) + lbGpuParticleForces(host) per step",
-                "fetch_fields_ms": fetch_ms, "fetch_fields_bytes": fetch_bytes},
+                "fetch_fields_ms": fetch_ms, "fetch_fields_bytes": fetch_bytes,
+                # the other two host-facing calls of a run, once each: lbGpuInit (state upload from pageable host
+                # arrays) and lbGpuFetchFields (what an export step of the reference's IO reads)
+                "init_upload_ms": 1e3 * info["upload_s"], "init_upload_bytes": info["upload_bytes"],
+                "job_value": active_total * K / (info["upload_s"] + ms_dev * 1e-3 + fetch_ms * 1e-3) / 1e6,
+                "job": "lbGpuInit(host state) + %d steps + one lbGpuFetchFields(host), rank 0's copies" % K},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -95,6 +95,9 @@ struct Slab {
     DevBuf<uint8_t> type0, type1, mark;
     DevBuf<uint32_t> solidIndex, bulk;
     DevBuf<uint32_t> curveRow;  // curved walls: row of the handle's curveDelta per cell
+    // particle coupling: the flagged cells as a list (k_plist_*), {count clamped, -, count} and the per-block scan scratch
+    DevBuf<uint32_t> pList, pCounts, pBlockCount;
+    uint32_t pCap = 0, pGroups = 0, pScanBlocks = 0;
     DevBuf<uint32_t> staticList, staticCount;  // PART 2 of the split step kernel: owned non-bulk cells that can be active
     uint32_t nStatic = 0;
     // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
@@ -109,7 +112,7 @@ struct Slab {
     DevBuf<unsigned long long> counters;  // [0] nInterface [1..3] k_count scratch
     DevBuf<uint32_t> status;              // [0] type error, [1] flood-fill counter
     // host copies of what lbGpuInit received for the ghost cells (they are dead cells of the reference)
-    std::vector<uint32_t> ghostIdx, ghostSolid;
+    std::vector<uint32_t> ghostIdx, ghostSrc, ghostSolid;
     std::vector<uint8_t> ghostType;
     // z-periodic lattice cut into several slabs: the reference's shell planes z=0 / z=Z-1 are replaced by remote ghost
     // planes on the device; what lbGpuInit received for them is kept for lbGpuFetchFields
@@ -438,7 +441,7 @@ int build_lists(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
-        const uint32_t nT = s->blocks, tb = (nT + BLOCK - 1) / BLOCK;
+        const uint32_t nT = s->blocks * TILES_PER_BLOCK, tb = (nT + BLOCK - 1) / BLOCK;  // tiles of 32 cells
         k_list_count<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p);
         k_list_offsets<<<1, 1024, 0, st>>>(s->listBlockCount.p, s->listBlocks, s->listCounts.p, 0, s->cellCap);
         k_list_write<<<s->listBlocks, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p, s->listBlockCount.p, s->cellList.p, s->cellCap);
@@ -577,6 +580,14 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
         return 0;
     }
     const uint32_t wb = (h->nParts * 32 + BLOCK - 1) / BLOCK;
+    for (auto& sp : h->slabs) {  // list buffers, on first use
+        Slab* s = sp.get();
+        if (s->pCap) continue;
+        s->pGroups = (s->N + 15u) / 16u;
+        s->pScanBlocks = (s->pGroups + BLOCK - 1) / BLOCK;
+        s->pCap = s->N / 2 + 4096;
+        CU(s->pList.alloc(s->pCap)); CU(s->pCounts.alloc(4)); CU(s->pBlockCount.alloc(s->pScanBlocks));
+    }
     if (rescan) {
         for (auto& sp : h->slabs) {
             k_clear_p<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()));
@@ -584,27 +595,64 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
             k_rescan<1><<<wb, BLOCK, 0, st>>>(dev_for(h, sp.get()));
             h->launches += 3;
         }
+        if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;  // the list below holds the flagged ghost cells too
     }
-    for (auto& sp : h->slabs) {
-        k_find_new_active<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()));
-        ++h->launches;
-    }
-    if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
-    Slab* s0 = h->slabs[0].get();
-    for (int gen = 0; gen < 4096; ++gen) {
+    // flagged cells (ghosts included) of every slab as a list: count - scan - write
+    auto build_plist = [&](int gateSlot) -> int {
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
-            const Dev d = dev_for(h, s);
-            CU(cudaMemsetAsync(s->status.p + 1, 0, sizeof(uint32_t), st));
-            k_find_new_solid<<<own_blocks(s), BLOCK, 0, st>>>(d, s->status.p + 1);
-            k_commit_pending<<<own_blocks(s), BLOCK, 0, st>>>(d);
+            const uint32_t* gate = gateSlot >= 0 ? s->status.p + gateSlot : nullptr;
+            k_plist_count<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, gate);
+            if (gateSlot < 0) k_list_offsets<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap);
+            else k_list_offsets_gated<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap, gate);
+            k_plist_write<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, s->pList.p, s->pCap, gate);
+            h->launches += 3;
+        }
+        return 0;
+    };
+    auto list_dev = [&](Slab* s) {
+        Dev d = dev_for(h, s);
+        d.list = s->pList.p; d.nList = s->pCounts.p;
+        return d;
+    };
+    const uint32_t lg = (uint32_t)h->numSMs * 16u;
+    if ((rc = build_plist(-1))) return rc;
+    for (auto& sp : h->slabs) {
+        k_find_new_active<<<lg, BLOCK, 0, st>>>(list_dev(sp.get()));
+        ++h->launches;
+    }
+    if ((rc = exchange(h, G_TYPE | G_SOLID | G_HF))) return rc;
+    Slab* s0 = h->slabs[0].get();
+    // Flood fill, one generation per round.  The count of cells a generation flagged lives in status[1 + (gen & 1)] of
+    // every slab (the global sum); the next generation's launches are gated on it, so the first SPEC generations are
+    // issued without waiting for the host -- only then is the count read back, once per further generation.
+    constexpr int SPEC = 3;
+    for (int gen = 0; gen < 4096; ++gen) {
+        const int cur = 1 + (gen & 1), prev = 1 + ((gen + 1) & 1);
+        const int gate = gen > 0 ? prev : -1;
+        // generation 0 reuses the list (flags were only cleared since); later ones see the cells flagged meanwhile
+        if (gen > 0) { if ((rc = build_plist(gate))) return rc; }
+        for (auto& sp : h->slabs) {
+            Slab* s = sp.get();
+            CU(cudaMemsetAsync(s->status.p + cur, 0, sizeof(uint32_t), st));
+            k_find_new_solid<<<lg, BLOCK, 0, st>>>(list_dev(s), s->status.p + cur, gate >= 0 ? s->status.p + gate : nullptr);
+            k_commit_pending<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->status.p + cur);
             h->launches += 2;
         }
-        for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_u32<<<1, 32, 0, st>>>(s0->status.p + 1, h->slabs[k]->status.p + 1, 1); ++h->launches; }
-        if ((rc = allreduce_sum(h, s0->status.p + 1, 1, lbcomm::ncclUint32))) return rc;
-        CU(cudaMemcpyAsync(h->pinnedStatus, s0->status.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CU(cudaStreamSynchronize(st));
-        if (*h->pinnedStatus == 0) break;
+        for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_u32<<<1, 32, 0, st>>>(s0->status.p + cur, h->slabs[k]->status.p + cur, 1); ++h->launches; }
+        if ((rc = allreduce_sum(h, s0->status.p + cur, 1, lbcomm::ncclUint32))) return rc;
+        for (size_t k = 1; k < h->slabs.size(); ++k)
+            CU(cudaMemcpyAsync(h->slabs[k]->status.p + cur, s0->status.p + cur, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        if (gen + 1 >= SPEC) {
+            CU(cudaMemcpyAsync(h->pinnedStatus, s0->status.p + cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            for (auto& sp : h->slabs)
+                CU(cudaMemcpyAsync(h->pinnedStatus + 16 + sp->slot, sp->pCounts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (auto& sp : h->slabs)
+                if (h->pinnedStatus[16 + sp->slot] > sp->pCap)
+                    return fail(LBGPU_EUNSUPPORTED, "particle coupling: %u flagged cells exceed the list capacity %u", h->pinnedStatus[16 + sp->slot], sp->pCap);
+            if (*h->pinnedStatus == 0) break;
+        }
         if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
     }
     CU(cudaGetLastError());
@@ -647,7 +695,7 @@ int lb_step(LbGpuHandle* h) {
             // one tile per block, sized with the tile count of the last list build that has reached the host (any
             // value is correct: the kernel strides over the list)
             d.list = s->tileList.p; d.nList = s->listCounts.p + 1;
-            uint32_t g = h->pinnedCounts[8 * s->slot + 1];
+            uint32_t g = (h->pinnedCounts[8 * s->slot + 1] + TILES_PER_BLOCK - 1) / TILES_PER_BLOCK;
             g = g + g / 16 + 8;
             if (g > s->blocks) g = s->blocks;
             k<<<g, BLOCK, 0, st>>>(d);
@@ -798,8 +846,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         s->candCap = 4 * s->cellCap;
         CU(s->candList.alloc(s->candCap)); CU(s->candOwned.alloc((size_t)Q * s->cellCap));
         CU(s->candBlockCount.alloc(((size_t)Q * s->cellCap + BLOCK - 1) / BLOCK + 1));
-        CU(s->tileFlags.alloc((size_t)s->listBlocks * LIST_TILES + 16)); CU(s->tileList.alloc(s->blocks)); CU(s->cellList.alloc(s->cellCap));
-        CU(s->listCounts.alloc(8)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc((s->blocks + BLOCK - 1) / BLOCK + 1));
+        CU(s->tileFlags.alloc((size_t)s->listBlocks * LIST_TILES * TILES_PER_BLOCK + 16)); CU(s->tileList.alloc((size_t)s->blocks * TILES_PER_BLOCK)); CU(s->cellList.alloc(s->cellCap));
+        CU(s->listCounts.alloc(8)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc(((size_t)s->blocks * TILES_PER_BLOCK + BLOCK - 1) / BLOCK + 1));
         CU(cudaMemsetAsync(s->listCounts.p, 0, 8 * sizeof(uint32_t), st));
         CU(cudaMemsetAsync(s->tileFlags.p, 0, s->tileFlags.n, st));
         s->listGrid = (uint32_t)h->numSMs * 16u;
@@ -886,7 +934,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             CU(cudaMemcpyAsync(s->gSrc.p, gs.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
             CU(cudaMemcpyAsync(s->gPop.p, gp.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
-            s->ghostIdx = gd;
+            s->ghostIdx = gd; s->ghostSrc = gs;
             s->ghostType.resize(s->nGhost); s->ghostSolid.resize(s->nGhost);
             for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]]; }
         }
@@ -1030,7 +1078,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         const double L = prm->unitLength, Tm = prm->unitTime, D = prm->unitDensity;
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
         h->uForce = D * L * L * L * L / Tm / Tm; h->uTorque = D * L * L * L * L * L / Tm / Tm;
-        CU(cudaMallocHost((void**)&h->pinnedStatus, 64));
+        CU(cudaMallocHost((void**)&h->pinnedStatus, 4096));
         CU(cudaMallocHost((void**)&h->pinnedCounts, sizeof(uint32_t) * 8 * (size_t)nLocal));
         memset(h->pinnedCounts, 0, sizeof(uint32_t) * 8 * (size_t)nLocal);
         for (int k = 0; k < nLocal; ++k) {
@@ -1094,6 +1142,8 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
 int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, const double* delta) {
     if (!h) return fail(LBGPU_EINVAL, "lbGpuSetCurves: null handle");
     if (nCurves && (!cells || !delta)) return fail(LBGPU_EINVAL, "lbGpuSetCurves: null array");
+    if (h->prm.boundary[4] == T_PERIODIC && h->nSlabsGlobal > 1)
+        return fail(LBGPU_EUNSUPPORTED, "lbGpuSetCurves: curved walls on a z-periodic lattice cut into slabs");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(h->curveDelta.alloc((size_t)nCurves * Q + 1));
@@ -1108,6 +1158,9 @@ int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, cons
             const long long loc = (long long)cells[k] - shift;
             if (loc >= 0 && loc < (long long)s->N) row[(size_t)loc] = k;
         }
+        // a periodic ghost cell stands for the cell it mirrors (the reference's own curve object of a shell cell is
+        // never reached: LB.cpp:438-472 wraps the links away from it)
+        for (size_t k = 0; k < s->ghostIdx.size(); ++k) row[s->ghostIdx[k]] = row[s->ghostSrc[k]];
         CU(s->curveRow.alloc(s->N));
         CU(cudaMemcpy(s->curveRow.p, row.data(), sizeof(uint32_t) * s->N, cudaMemcpyHostToDevice));
     }

@@ -147,17 +147,101 @@ class Neighbors:
         return np.where(self.shell, self.idx, link)
 
 
+class Stencil:
+    """What `a[nb[j]]` and `out[nb[j][mask]] = True` compute with the table of `Neighbors`, evaluated on shifted 3-D
+    views instead of index gathers (a 1024x256x256 lattice is built in seconds instead of minutes).  The periodic wrap is
+    served the way the engine does it: the shell planes of a periodic axis are filled with the opposite interior plane
+    (x, then y, then z, whole planes, so edges and corners wrap twice / three times as LB.cpp:438-472 does)."""
+
+    def __init__(self, nb: Neighbors):
+        self.nb = nb
+        X, Y, Z = nb.size
+        self.full = len(nb.planes) == Z
+        b = nb.boundary
+        self.per = (b[0] == PERIODIC, b[2] == PERIODIC, b[4] == PERIODIC)
+        # per stored plane l: the stored plane holding the +z / -z neighbour plane (-1: not stored or l is a shell plane)
+        g = nb.planes
+        def target(cz):
+            gz = g + cz
+            if self.per[2]:
+                gz = np.where(gz == Z - 1, 1, gz)
+                gz = np.where(gz == 0, Z - 2, gz)
+            t = nb.local_of[np.clip(gz, 0, Z - 1)]
+            return np.where((g >= 1) & (g <= Z - 2), t, -1)
+        self.zt = {1: target(1), -1: target(-1), 0: np.where((g >= 1) & (g <= Z - 2), np.arange(len(g)), -1)}
+
+    def _filled(self, A):
+        X, Y, _ = self.nb.size
+        if not (self.per[0] or self.per[1]):
+            return A
+        E = A.copy()
+        if self.per[0]:
+            E[:, :, 0] = E[:, :, X - 2]; E[:, :, X - 1] = E[:, :, 1]
+        if self.per[1]:
+            E[:, 0, :] = E[:, Y - 2, :]; E[:, Y - 1, :] = E[:, 1, :]
+        return E
+
+    def gather(self, a, j):
+        """a[nb[j]] for j >= 1 (shell cells link to themselves)."""
+        X, Y, _ = self.nb.size
+        nz = len(self.nb.planes)
+        A = a.reshape(nz, Y, X)
+        E = self._filled(A)
+        out = A.copy()
+        cx, cy, cz = int(CX[j]), int(CY[j]), int(CZ[j])
+        zt = self.zt[cz]
+        ys, xs = slice(1 + cy, Y - 1 + cy), slice(1 + cx, X - 1 + cx)
+        if self.full and not (cz and self.per[2]):
+            out[1:nz - 1, 1:Y - 1, 1:X - 1] = E[1 + cz:nz - 1 + cz, ys, xs]
+        else:
+            for l in np.nonzero(zt >= 0)[0]:
+                out[l, 1:Y - 1, 1:X - 1] = E[zt[l], ys, xs]
+        return out.reshape(-1)
+
+    def scatter_or(self, out, mask, j):
+        """out[nb[j][mask]] = True."""
+        X, Y, _ = self.nb.size
+        nz = len(self.nb.planes)
+        O = out.reshape(nz, Y, X)
+        M = mask.reshape(nz, Y, X)
+        shell = self.nb.shell.reshape(nz, Y, X)
+        O |= M & shell  # shell cells link to themselves
+        if j == 0:  # d[0] of interior cells is never assigned: it stays 0 (LB.cpp:377-387)
+            if (M & ~shell).any():
+                out[0] = True
+            return
+        cx, cy, cz = int(CX[j]), int(CY[j]), int(CZ[j])
+        zt = self.zt[cz]
+        T = np.zeros((nz, Y, X), dtype=bool)
+        ys, xs = slice(1 + cy, Y - 1 + cy), slice(1 + cx, X - 1 + cx)
+        for l in np.nonzero(zt >= 0)[0]:
+            T[zt[l], ys, xs] |= M[l, 1:Y - 1, 1:X - 1]
+        # targets on the shell plane of a periodic axis wrap to the opposite interior plane
+        if cy and self.per[1]:
+            T[:, Y - 2, :] |= T[:, 0, :]; T[:, 1, :] |= T[:, Y - 1, :]; T[:, 0, :] = False; T[:, Y - 1, :] = False
+        if cx and self.per[0]:
+            T[:, :, X - 2] |= T[:, :, 0]; T[:, :, 1] |= T[:, :, X - 1]; T[:, :, 0] = False; T[:, :, X - 1] = False
+        O |= T
+
+
 def window_planes(Z, periodic_z, zlo, zhi, margin=2):
     """Global planes a slab window [zlo, zhi) needs for the init stencils: the window itself plus `margin` planes
     on either side, wrapped through the periodic boundary (LB.cpp:438-472) or clipped at a wall."""
     want = set(range(zlo, zhi))
-    for g in list(range(zlo - margin, zlo)) + list(range(zhi, zhi + margin)):
-        if periodic_z:
+    if periodic_z:
+        # the interior planes 1..Z-2 form a ring (plane 0 stands for Z-2, plane Z-1 for 1): margins are counted from
+        # the window's interior planes
+        inner = [g for g in range(zlo, zhi) if 1 <= g <= Z - 2]
+        def wrap(g):
             while g < 1: g += Z - 2
             while g > Z - 2: g -= Z - 2
-            want.add(g)
-        elif 0 <= g < Z:
-            want.add(g)
+            return g
+        for k in range(1, margin + 1):
+            want.add(wrap(min(inner) - k)); want.add(wrap(max(inner) + k))
+    else:
+        for g in list(range(zlo - margin, zlo)) + list(range(zhi, zhi + margin)):
+            if 0 <= g < Z:
+                want.add(g)
     return np.array(sorted(want), dtype=np.int64)
 
 
@@ -273,15 +357,18 @@ def build_state(case: dict, parts=None, window=None, reduce_max=None) -> Lattice
             ins = d2 < s[3] * s[3]
             gas |= ins if inside_is_gas else ~ins
     t[(t == FLUID) & gas] = GAS
+    st3 = Stencil(nb)
     if (t == GAS).any():
         fluid = t == FLUID
+        is_gas = t == GAS
         near_gas = np.zeros(N, dtype=bool)
         for j in range(1, 19):
-            near_gas |= t[nb[j]] == GAS
+            near_gas |= st3.gather(is_gas, j)
         t[fluid & near_gas] = INTERFACE
+        is_fluid = t == FLUID
         near_fluid = np.zeros(N, dtype=bool)
         for j in range(1, 19):
-            near_fluid |= t[nb[j]] == FLUID
+            near_fluid |= st3.gather(is_fluid, j)
         t[(t == INTERFACE) & ~near_fluid] = GAS
 
     # initializeVariables (LB.cpp:909-944): hydrostatic density below the highest active cell
@@ -312,7 +399,7 @@ def build_state(case: dict, parts=None, window=None, reduce_max=None) -> Lattice
     nonwall = ~is_wall(t)
     linked = np.zeros(N, dtype=bool)
     for j in range(19):
-        linked[nb[j][nonwall]] = True
+        st3.scatter_or(linked, nonwall, j)
     wall_node = linked & is_wall(t)
     n[wall_node] = 1.0
     wvel = np.zeros((len(walls), 3))

@@ -118,9 +118,14 @@ def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None)
         dist.all_reduce(t)
         active_total = int(t.item())
         par = "%d z-slabs, one rank per GPU, NCCL send/recv halo (5 populations per face)" % world
+    import time
     lb = LB(st.params, device=device)
+    t0 = time.perf_counter()
     lb.latticeBolzmannInit(st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)
-    info = dict(params=st.params, active_local=active, active_total=active_total, global_z=Zg, parallelism=par,
+    lb.synchronize()
+    upload_s = time.perf_counter() - t0
+    upload_bytes = int(sum(a.nbytes for a in (st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)))
+    info = dict(upload_s=upload_s, upload_bytes=upload_bytes, params=st.params, active_local=active, active_total=active_total, global_z=Zg, parallelism=par,
                 parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
                 bytes_resident=2 * 19 * 8 * st.type_flags.size + 60 * st.type_flags.size)
     return lb, info

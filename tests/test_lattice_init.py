@@ -53,3 +53,27 @@ def test_neighbor_table_periodic_wrap():
     assert nb[0][c] == 0
     s = idx(0, 5, 5)
     assert all(nb[j][s] == s for j in range(19))
+
+
+@pytest.mark.parametrize("bnd", [[4, 4, 4, 4, 7, 7], [4, 4, 4, 4, 4, 4], [7, 7, 4, 4, 8, 7], [7, 5, 7, 7, 4, 4]])
+@pytest.mark.parametrize("window", [None, (0, 6), (3, 9), (5, 11)])
+def test_stencil_views_equal_the_neighbor_table(bnd, window):
+    """The shifted-view stencil used by build_state == gathers / scatters through the explicit neighbour table."""
+    size = (9, 7, 11)
+    planes = None if window is None else li.window_planes(size[2], bnd[4] == 4, window[0], window[1])
+    nb = li.Neighbors(size, bnd, planes)
+    st3 = li.Stencil(nb)
+    rng = np.random.default_rng(7)
+    n = nb.idx.size
+    a = rng.integers(0, 1000, n)
+    mask = rng.random(n) < 0.3
+    for j in range(19):
+        if j:
+            assert np.array_equal(st3.gather(a, j), a[nb[j]]), j
+        want = np.zeros(n, dtype=bool); want[nb[j][mask]] = True
+        got = np.zeros(n, dtype=bool); st3.scatter_or(got, mask, j)
+        if window is None:
+            assert np.array_equal(got, want), j
+        else:  # links leaving the stored planes are only defined on the (discarded) margin: compare the window's cells
+            keep = (nb.z >= window[0]) & (nb.z < window[1])
+            assert np.array_equal(got[keep], want[keep]), j
