@@ -149,6 +149,7 @@ struct LbGpuHandle {
     uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
     // curved walls (type 9) and LB::enforceMassConservation (problemName DRUM)
+    int fsGridPerSM = 0;  // > 0: persistent launch of the free-surface step kernel, this many blocks per SM (LBGPU_FS_GRID)
     bool hasCurved = false, curvesSet = false, enforceMass = false;
     double totalMass = 0.0;
     DevBuf<double> curveDelta;
@@ -698,6 +699,7 @@ int lb_step(LbGpuHandle* h) {
             uint32_t g = (h->pinnedCounts[8 * s->slot + 1] + TILES_PER_BLOCK - 1) / TILES_PER_BLOCK;
             g = g + g / 16 + 8;
             if (g > s->blocks) g = s->blocks;
+            if (h->fsGridPerSM > 0 && g > (uint32_t)(h->fsGridPerSM * h->numSMs)) g = (uint32_t)(h->fsGridPerSM * h->numSMs);
             k<<<g, BLOCK, 0, st>>>(d);
         } else {
             k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
@@ -735,15 +737,16 @@ int lb_step(LbGpuHandle* h) {
     if ((rc = exchange(h, what, true, !overlap))) return rc;
     if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
     Slab* s0 = h->slabs[0].get();
-    if (h->hasCurved && fsOn) {
-        // extraMass of the curved links, after every cell's n, u of this step are in place (ghosts included)
+    if (h->hasCurved) {
+        // streaming through the curved links + their extraMass, after every cell's n, u of this step are in place
+        // (ghosts included) and after the population exchange of the step
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             if (!s->nStatic) continue;
             Dev d = dev_for(h, s);
             d.pStride = s->blocks; d.pBase = 0;
             d.list = s->staticList.p; d.nList = s->staticCount.p + 1;
-            k_curved_extra_mass<<<(s->nStatic + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
+            k_curved_stream<<<(s->nStatic + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
             ++h->launches;
         }
     }
@@ -770,7 +773,7 @@ int lb_step(LbGpuHandle* h) {
         }
     }
     if (h->nElmts > 0 && couple) {
-        const uint32_t eb = (h->nElmts * 32 + BLOCK - 1) / BLOCK;
+        const uint32_t eb = h->nElmts;  // one block per element
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             k_element_forces<<<eb, BLOCK, 0, st>>>(dev_for(h, s), h->uForce, h->uTorque, h->uVolume, s->elemOut.p);
@@ -1067,6 +1070,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->kev0.resize(LbGpuHandle::KEV); h->kev1.resize(LbGpuHandle::KEV);
         for (uint32_t k = 0; k < LbGpuHandle::KEV; ++k) { CU(cudaEventCreate(&h->kev0[k])); CU(cudaEventCreate(&h->kev1[k])); }
         h->fs = prm->freeSurface != 0;
+        if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);
         // curved links use the moving-wall machinery: stored n, u and the extraMass sum (LB.cpp:1278-1319)

@@ -13,7 +13,7 @@ import cases  # noqa: E402
 
 name = sys.argv[1]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-case = cases.catalogue()[name]
+case = cases.materialise(dict(cases.catalogue()[name]))
 t0 = time.time()
 prm = li.params_from_case(case)
 tr = common.KinematicTrace(case, prm)

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --durations=5 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -12 gpurun_out/pytest_gpu.log
+for c in cfg5 cfg3; do
+bash tools/ab.sh $c 60 hybird_b200/_ab/lib_c4s5.so hybird_b200/_ab/lib_c5s5.so > gpurun_out/ab_$c.log 2>&1
+cat gpurun_out/ab_$c.log
+done
