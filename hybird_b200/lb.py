@@ -113,7 +113,8 @@ class LB:
         return F, M, V, W
 
     def run(self, steps, free_surface=None):
-        """`steps` cycles without particles, issued back to back (no host round trip)."""
+        """`steps` cycles issued back to back (no host round trip); the particles of the last coupling step, if any,
+        stay resident and fixed (lbGpuRun)."""
         fs = self.freeSurface if free_surface is None else free_surface
         abi.check(self.lib.lbGpuRun(self.h, int(fs), int(steps)))
         self.time += int(steps)

@@ -99,6 +99,41 @@ def test_run_equals_step_loop():
     a.close(); b.close()
 
 
+def test_run_keeps_resident_particles_coupled():
+    """lbGpuRun(count) with particles uploaded earlier == count x (coupling step + LB step) with the same particles."""
+    g = gu.Golden("cfg5_mini")
+    parts, elmts, comps, _ = g.trace[0]
+    a, b = _gpu(g), _gpu(g)
+    for lb in (a, b):
+        lb.latticeBoltzmannFreeSurfaceStep()
+        lb.latticeBoltzmannCouplingStep(True, elmts, parts, comps)
+        lb.latticeBolzmannStep(elmts, parts)
+    a.run(12)
+    Fa = a.forces()
+    for _ in range(12):
+        b.latticeBoltzmannFreeSurfaceStep()
+        b.latticeBoltzmannCouplingStep(False, elmts, parts, comps)
+        Fb = b.latticeBolzmannStep(elmts, parts)
+    sa, sb = a.fetch(), b.fetch()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    for x, y in zip(Fa, Fb):
+        assert np.array_equal(x, y)
+    assert np.abs(Fa[0]).max() > 0
+    a.close(); b.close()
+
+
+def test_curved_cells_need_their_curves():
+    """A lattice with type-9 cells steps only after lbGpuSetCurves (the engine does not guess link fractions)."""
+    from hybird_b200 import LB, LbGpuError
+    g = gu.Golden("drum_mini")
+    lb = LB(dict(g.params))
+    lb.latticeBolzmannInit(*g.init_arrays())
+    with pytest.raises(LbGpuError):
+        lb.run(1)
+    lb.close()
+
+
 def test_bad_arguments_fail_loudly():
     from hybird_b200 import LB, LbGpuError
     g = gu.Golden("cfg2_mini")
