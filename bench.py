@@ -33,6 +33,18 @@ BYTES_PER_UPDATE = 2 * 19 * 8  # 19 fp64 populations read + 19 w
 METRIC = "MLUPS (fp64 D3Q19) at 1/2/4/8 B200 and % of HBM roofline vs ref CPU"
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -179,7 +191,7 @@ def main_reference(args, rank, world):
             "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -335,7 +347,7 @@ def main_ours(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -353,10 +365,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner ...) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if world == 1 and args.gpus > 1:
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        os.dup2(_REAL_STDOUT, 1)  # the ranks inherit the real stdout and keep it clean themselves
         return subprocess.call(cmd)
     if args.impl == "reference":
         return main_reference(args, rank, world)
