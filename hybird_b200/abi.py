@@ -32,7 +32,7 @@ class LbGpuParams(C.Structure):
 
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
-           "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
+           "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
            "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize")
 
@@ -76,6 +76,12 @@ def load_library(build_if_missing=True):
     L.lbGpuParticleForces.argtypes = [vp, vp, vp, vp, vp]
     L.lbGpuFetchFields.restype = C.c_int
     L.lbGpuFetchFields.argtypes = [vp] * 10
+    L.lbGpuStateBytes.restype = C.c_int
+    L.lbGpuStateBytes.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.lbGpuSaveState.restype = C.c_int
+    L.lbGpuSaveState.argtypes = [vp, vp, C.c_uint64]
+    L.lbGpuLoadState.restype = C.c_int
+    L.lbGpuLoadState.argtypes = [vp, vp, C.c_uint64]
     L.lbGpuCounts.restype = C.c_int
     L.lbGpuCounts.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     L.lbGpuSynchronize.restype = C.c_int

@@ -1469,6 +1469,117 @@ int lbGpuSelfTest(uint64_t count, uint64_t seed, uint64_t result[3]) {
     return LBGPU_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Checkpoint / restart (the reference has none for the fluid, IO.cpp:486-535 covers the particles).
+// The blob is the dynamic device state of the handle in a fixed order behind a small header; everything derived from
+// the static geometry (bulk bitmap, static list, ghost lists, curves) is rebuilt by lbGpuInit / lbGpuSetCurves on the
+// handle the state is loaded into, the per-step lists are rebuilt by the next step.
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+struct StateHeader {
+    char magic[8];
+    uint32_t version, nSlabs;
+    int32_t size[3], fs;
+    uint64_t cellsTotal, steps;
+    uint32_t cur, macroValid, lastStepFirst, lastStepCoupled, nParts, nElmts, nComps, pad;
+};
+
+// visits every piece of dynamic state in a fixed order: fn(device pointer, bytes)
+template <class F>
+int visit_state(LbGpuHandle* h, F&& fn) {
+    int rc;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        auto buf = [&](auto& b) -> int { return b.n ? fn((void*)b.p, b.n * sizeof(*b.p)) : 0; };
+        if ((rc = buf(s->fA)) || (rc = buf(s->fB)) || (rc = buf(s->n)) || (rc = buf(s->ux)) || (rc = buf(s->uy)) || (rc = buf(s->uz)) ||
+            (rc = buf(s->mass)) || (rc = buf(s->newMass)) || (rc = buf(s->visc)) || (rc = buf(s->shearRate)) || (rc = buf(s->hfx)) ||
+            (rc = buf(s->hfy)) || (rc = buf(s->hfz)) || (rc = buf(s->type0)) || (rc = buf(s->type1)) || (rc = buf(s->mark)) ||
+            (rc = buf(s->solidIndex)) || (rc = buf(s->counters)) || (rc = buf(s->scal)) || (rc = buf(s->sums)) || (rc = buf(s->status)))
+            return rc;
+        if (h->nElmts && (rc = fn((void*)s->elemOut.p, sizeof(double) * 7 * h->nElmts))) return rc;
+    }
+    if (h->nParts && (rc = fn((void*)h->parts.p, sizeof(lb::Particle) * h->nParts))) return rc;
+    if (h->nElmts && (rc = fn((void*)h->elmts.p, sizeof(lb::Element) * h->nElmts))) return rc;
+    if (h->nComps && (rc = fn((void*)h->comps.p, sizeof(uint32_t) * h->nComps))) return rc;
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int lbGpuStateBytes(LbGpuHandle* h, uint64_t* bytes) {
+    if (!h || !bytes) return fail(LBGPU_EINVAL, "lbGpuStateBytes: null argument");
+    uint64_t total = sizeof(StateHeader);
+    visit_state(h, [&](void*, size_t b) { total += b; return 0; });
+    *bytes = total;
+    return LBGPU_OK;
+}
+
+int lbGpuSaveState(LbGpuHandle* h, void* buffer, uint64_t bytes) {
+    if (!h || !buffer) return fail(LBGPU_EINVAL, "lbGpuSaveState: null argument");
+    uint64_t need = 0;
+    lbGpuStateBytes(h, &need);
+    if (bytes < need) return fail(LBGPU_EINVAL, "lbGpuSaveState: buffer of %llu bytes, %llu needed", (unsigned long long)bytes, (unsigned long long)need);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (int rc = check_status(h)) return rc;
+    StateHeader hd;
+    memset(&hd, 0, sizeof hd);
+    memcpy(hd.magic, "LBGPUST", 8);
+    hd.version = 1; hd.nSlabs = (uint32_t)h->slabs.size();
+    for (int k = 0; k < 3; ++k) hd.size[k] = h->prm.size[k];
+    hd.fs = h->fs ? 1 : 0;
+    for (auto& sp : h->slabs) hd.cellsTotal += sp->N;
+    hd.steps = h->steps; hd.cur = (uint32_t)h->cur; hd.macroValid = h->macroValid; hd.lastStepFirst = h->lastStepFirst;
+    hd.lastStepCoupled = h->lastStepCoupled; hd.nParts = h->nParts; hd.nElmts = h->nElmts; hd.nComps = h->nComps;
+    char* out = (char*)buffer;
+    memcpy(out, &hd, sizeof hd);
+    size_t off = sizeof hd;
+    return visit_state(h, [&](void* p, size_t b) -> int {
+        CU(cudaMemcpy(out + off, p, b, cudaMemcpyDeviceToHost));
+        off += b;
+        return 0;
+    });
+}
+
+int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes) {
+    if (!h || !buffer || bytes < sizeof(StateHeader)) return fail(LBGPU_EINVAL, "lbGpuLoadState: bad argument");
+    StateHeader hd;
+    memcpy(&hd, buffer, sizeof hd);
+    uint64_t cells = 0;
+    for (auto& sp : h->slabs) cells += sp->N;
+    if (memcmp(hd.magic, "LBGPUST", 8) != 0 || hd.version != 1) return fail(LBGPU_EINVAL, "lbGpuLoadState: not a state blob of this library");
+    if (hd.nSlabs != h->slabs.size() || hd.cellsTotal != cells || hd.size[0] != h->prm.size[0] || hd.size[1] != h->prm.size[1] ||
+        hd.size[2] != h->prm.size[2] || (hd.fs != 0) != h->fs)
+        return fail(LBGPU_EINVAL, "lbGpuLoadState: the state was saved from a different lattice (size / slabs / free surface)");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    // room for the particle lists of the saved state (as upload_particles provides it)
+    if (hd.nParts > h->rawParts.n) { CU(h->rawParts.alloc(hd.nParts + 16)); CU(h->parts.alloc(h->rawParts.n)); }
+    if (hd.nElmts > h->rawElmts.n) {
+        CU(h->rawElmts.alloc(hd.nElmts + 16));
+        CU(h->elmts.alloc(h->rawElmts.n));
+        for (auto& s : h->slabs) CU(s->elemOut.alloc(h->rawElmts.n * 7));
+    }
+    if (hd.nComps > h->comps.n) CU(h->comps.alloc(hd.nComps + 16));
+    h->nParts = hd.nParts; h->nElmts = hd.nElmts; h->nComps = hd.nComps;
+    uint64_t need = 0;
+    lbGpuStateBytes(h, &need);
+    if (bytes < need) return fail(LBGPU_EINVAL, "lbGpuLoadState: blob of %llu bytes, %llu expected", (unsigned long long)bytes, (unsigned long long)need);
+    const char* in = (const char*)buffer;
+    size_t off = sizeof hd;
+    if (int rc = visit_state(h, [&](void* p, size_t b) -> int {
+            CU(cudaMemcpy(p, in + off, b, cudaMemcpyHostToDevice));
+            off += b;
+            return 0;
+        }))
+        return rc;
+    h->steps = hd.steps; h->cur = (int)hd.cur; h->macroValid = hd.macroValid != 0; h->lastStepFirst = hd.lastStepFirst != 0;
+    h->lastStepCoupled = hd.lastStepCoupled != 0;
+    h->typesFlipped = false; h->listsFresh = false;
+    return LBGPU_OK;
+}
+
 int lbGpuFinalize(LbGpuHandle* h) {
     if (!h) return LBGPU_OK;
     cudaSetDevice(h->device);

@@ -154,6 +154,23 @@ class LB:
         abi.check(self.lib.lbGpuFetchFields(self.h, *[abi.ptr(out.get(k)) for k in order]))
         return out
 
+    # -- checkpoint / restart (no counterpart in the reference) --------------------------------------
+    def save_state(self) -> np.ndarray:
+        n = C.c_uint64()
+        abi.check(self.lib.lbGpuStateBytes(self.h, C.byref(n)))
+        blob = np.empty(int(n.value), dtype=np.uint8)
+        abi.check(self.lib.lbGpuSaveState(self.h, abi.ptr(blob), n))
+        return blob
+
+    def load_state(self, blob, last_particles=None):
+        """`last_particles` = (parts, elmts, comps) the saved run coupled last, if forces() is to be called before the
+        next coupling step."""
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        abi.check(self.lib.lbGpuLoadState(self.h, abi.ptr(blob), C.c_uint64(blob.size)))
+        if last_particles is not None:
+            self._last = last_particles
+        return self
+
     def close(self):
         if self.h:
             self.lib.lbGpuFinalize(self.h)

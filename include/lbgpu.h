@@ -144,6 +144,15 @@ int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHy
 int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, double* n, double* u, double* mass,
                      double* visc, double* shearRate, double* hydroForce, double* f);
 
+/* Checkpoint / restart of the fluid state (the reference has none: SURVEY.md 5; DEM's recycle file covers the particles,
+ * IO.cpp:486-535).  The blob holds the dynamic device state (populations, types, macroscopic fields, masses, resident
+ * particle lists, step counter); it is loaded into a handle created by lbGpuInit with the SAME parameters and wall
+ * geometry (+ lbGpuSetCurves / lbGpuSetMassTarget where used) -- the initial field values of that handle do not matter.
+ * A run continued from a loaded state is bit-identical to the uninterrupted run.  Call between cycles only. */
+int lbGpuStateBytes(LbGpuHandle* h, uint64_t* bytes);
+int lbGpuSaveState(LbGpuHandle* h, void* buffer, uint64_t bytes);
+int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes);
+
 /* counters: [0]=fluid cells, [1]=interface cells, [2]=cells with p flag, [3]=LB steps done */
 int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]);
 int lbGpuSynchronize(LbGpuHandle* h);
