@@ -100,6 +100,8 @@ struct Slab {
     uint32_t pCap = 0, pGroups = 0, pScanBlocks = 0;
     DevBuf<uint32_t> staticList, staticCount;  // PART 2 of the split step kernel: owned non-bulk cells that can be active
     uint32_t nStatic = 0;
+    DevBuf<uint32_t> wallCells, wallMasks;     // wall-push list (k_wall_push): bulk cells with links to static no-slip walls
+    uint32_t nWallPush = 0;
     // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
     // listCounts = {interface cells, tiles, interface cells before clamping to the capacity}
     DevBuf<uint8_t> tileFlags;
@@ -149,6 +151,10 @@ struct LbGpuHandle {
     uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
     // curved walls (type 9) and LB::enforceMassConservation (problemName DRUM)
+    bool wallPushAllowed = true;  // LBGPU_WALL_PUSH=0 keeps the list-driven launch for every wall-adjacent cell (A/B)
+    bool ghostCopy = false;  // with wallPush, single process: the periodic mirrors are written by k_fill_ghosts after the step
+                             // instead of by the step kernel, so the cells next to periodic faces take the bulk path too
+    bool wallPush = false;  // static no-slip links are served by slots pre-stored in the wall cells (k_wall_push)
     int fsGridPerSM = 0;  // > 0: persistent launch of the free-surface step kernel, this many blocks per SM (LBGPU_FS_GRID)
     bool hasCurved = false, curvesSet = false, enforceMass = false;
     double totalMass = 0.0;
@@ -216,6 +222,7 @@ Dev dev_for(LbGpuHandle* h, Slab* s) {
     d.list = s->cellList.p; d.nList = s->listCounts.p;  // list-driven kernels: the interface cells unless told otherwise
     d.cand = s->candList.p; d.nCand = s->listCounts.p + 3;
     d.lazyMass = 0;
+    if (h->ghostCopy) d.push = 0;
     d.curveRow = s->curveRow.p; d.curveDelta = h->curveDelta.p; d.shearState = h->shear ? 1 : 0;
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
@@ -660,6 +667,59 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
     return 0;
 }
 
+// Bulk bitmap, static list (PART 2 of the split step kernel) and wall-push list of one slab: count - scan - write.
+// Built at init and once more when a pure-fluid lattice switches to the split kernel (first particles).
+int build_static(LbGpuHandle* h, Slab* s) {
+    cudaStream_t st = h->stream;
+    const int wallOk = h->wallPush ? 1 : 0;
+    // without a free surface cell activity never changes; with one the bitmap holds the static part
+    if (!s->bulk.p) CU(s->bulk.alloc((size_t)s->blocks * (BLOCK / 32) + 1));
+    CU(cudaMemsetAsync(s->bulk.p, 0, sizeof(uint32_t) * s->bulk.n, st));
+    if (h->fs) k_build_bulk<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, wallOk);
+    else k_build_bulk<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, wallOk);
+    ++h->launches;
+    s->dev.bulk = s->bulk.p;
+    DevBuf<uint32_t> bc;
+    CU(bc.alloc(s->blocks));
+    if (!s->staticCount.p) CU(s->staticCount.alloc(4));
+    CU(cudaMemsetAsync(s->staticCount.p, 0, 4 * sizeof(uint32_t), st));
+    if (h->fs) k_static_count<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
+    else k_static_count<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
+    k_list_offsets<<<1, 1024, 0, st>>>(bc.p, s->blocks, s->staticCount.p, 1, s->N);
+    CU(cudaMemcpyAsync(h->pinnedStatus + 8, s->staticCount.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    s->nStatic = h->pinnedStatus[8];
+    CU(s->staticList.alloc(s->nStatic + 1));
+    if (h->fs) k_static_write<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
+    else k_static_write<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
+    h->launches += 3;
+    s->nWallPush = 0;
+    if (h->wallPush) {
+        k_wall_count<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
+        k_list_offsets<<<1, 1024, 0, st>>>(bc.p, s->blocks, s->staticCount.p, 3, s->N);
+        CU(cudaMemcpyAsync(h->pinnedStatus + 8, s->staticCount.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        s->nWallPush = h->pinnedStatus[8];
+        CU(s->wallCells.alloc(s->nWallPush + 1)); CU(s->wallMasks.alloc(s->nWallPush + 1));
+        k_wall_write<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->wallCells.p, s->wallMasks.p);
+        h->launches += 3;
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// bounce-back slots of the static no-slip walls from the populations in buffer `buf` (k_wall_push)
+int wall_push(LbGpuHandle* h, int buf) {
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        if (!s->nWallPush) continue;
+        k_wall_push<<<(s->nWallPush + BLOCK - 1) / BLOCK, BLOCK, 0, h->stream>>>(dev_for(h, s), s->wallCells.p, s->wallMasks.p, s->nWallPush, s->fbuf(buf));
+        ++h->launches;
+    }
+    return 0;
+}
+
 int lb_step(LbGpuHandle* h) {
     const bool first = (h->steps == 0);
     const bool couple = h->nParts > 0;
@@ -671,6 +731,14 @@ int lb_step(LbGpuHandle* h) {
         return fail(LBGPU_EINVAL, "the lattice has curved-wall cells (type 9): call lbGpuSetCurves before the first step");
     const int nSums = 1 + 3 * h->prm.nWalls;
     const bool split = step_is_split(h->shear, macro, couple, fsOn, h->dynWall);
+    if (split && !h->wallPush && h->wallPushAllowed) {
+        // a pure-fluid lattice got its first particles: from now on the split kernel runs, with the cells next to plain
+        // walls on the bulk path; their slots are filled from the current post-collision populations
+        h->wallPush = true;
+        h->ghostCopy = !lbcomm::active();
+        for (auto& sp : h->slabs) { if ((rc = build_static(h, sp.get()))) return rc; }
+        if (h->steps > 0) wall_push(h, h->cur);
+    }
     StepKernel k = select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, split ? 1 : 0);
     StepKernel k2 = split ? select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, 2) : nullptr;
     StepKernel k3 = (split && fsOn) ? select_step(h->force, h->shear, macro, couple, fsOn, h->dynWall, 3) : nullptr;
@@ -734,7 +802,9 @@ int lb_step(LbGpuHandle* h) {
     for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
     CU(cudaEventRecord(h->kev1[ke], st));
     ++h->kevCount;
-    if ((rc = exchange(h, what, true, !overlap))) return rc;
+    // ghostCopy: the mirrors of everything the step kernel stored are copied now (the kernel did not push them)
+    const uint32_t whatLocal = what | (h->ghostCopy ? ((macro ? G_MACRO : 0u) | (h->shear ? G_VISC : 0u) | (couple ? G_HF : 0u)) : 0u);
+    if ((rc = exchange(h, whatLocal, !h->ghostCopy, !overlap))) return rc;
     if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
     Slab* s0 = h->slabs[0].get();
     if (h->hasCurved) {
@@ -750,6 +820,7 @@ int lb_step(LbGpuHandle* h) {
             ++h->launches;
         }
     }
+    if (h->wallPush) wall_push(h, h->cur ^ 1);  // bounce-back slots of the plain walls for the next pull
     if (h->dynWall) {
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
@@ -923,7 +994,9 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
                     for (int j = 1; j < Q; ++j) {
                         // population j is pulled out of this ghost by the cell at ghost + c_j, if that is an interior cell
                         const int tx = x + CXh(j), ty = y + CYh(j), tz = z + CZh(j);
-                        if (tx >= 1 && tx <= X - 2 && ty >= 1 && ty <= Y - 2 && tz >= 1 && tz <= Zl - 2) pm |= 1u << j;
+                        // (across a slab cut the pulling cell is the neighbour slab's: its copy of this plane is taken from here)
+                        if (tx >= 1 && tx <= X - 2 && ty >= 1 && ty <= Y - 2 && tz >= (s->remoteLo ? 0 : 1) && tz <= (s->remoteHi ? Zl - 1 : Zl - 2))
+                            pm |= 1u << j;
                     }
                     if (h->slip) pm = (1u << Q) - 1u;
                     gd.push_back(idx(x, y, z)); gs.push_back(idx(sx, sy, sz)); gp.push_back(pm);
@@ -1071,6 +1144,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         for (uint32_t k = 0; k < LbGpuHandle::KEV; ++k) { CU(cudaEventCreate(&h->kev0[k])); CU(cudaEventCreate(&h->kev1[k])); }
         h->fs = prm->freeSurface != 0;
         if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
+        if (const char* e = getenv("LBGPU_WALL_PUSH")) h->wallPushAllowed = atoi(e) != 0;
 
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);
@@ -1079,6 +1153,10 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->dynWall = anyDyn || anyCurved;
         h->slip = anySlip;
         h->macroAlways = h->fs || anyDyn || anyCurved || anyGas || anyIface;
+        // lattices that run the split step kernel from the start serve plain-wall links through pre-stored slots
+        h->wallPush = h->wallPushAllowed && step_is_split(h->shear, h->macroAlways, false, h->fs, h->dynWall);
+        // (between processes the face planes travel before the step ends: there the step kernel keeps pushing)
+        h->ghostCopy = h->wallPush && !lbcomm::active();
         // measureUnits::setComposite (node.cpp:476-488)
         const double L = prm->unitLength, Tm = prm->unitTime, D = prm->unitDensity;
         h->uLength = L; h->uVolume = L * L * L; h->uSpeed = L / Tm; h->uAngVel = 1.0 / Tm;
@@ -1101,30 +1179,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             if (h->fs) CU(cudaMemcpyAsync(s->type1.p, s->type0.p, s->type0.n, cudaMemcpyDeviceToDevice, st));
-            {
-                // built once: without a free surface cell activity never changes; with one the bitmap holds the static part
-                CU(s->bulk.alloc((size_t)s->blocks * (BLOCK / 32) + 1));
-                CU(cudaMemsetAsync(s->bulk.p, 0, sizeof(uint32_t) * s->bulk.n, st));
-                if (h->fs) k_build_bulk<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
-                else k_build_bulk<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p);
-                ++h->launches;
-                s->dev.bulk = s->bulk.p;
-                // the static list of the split step kernel (count - scan - write, once)
-                DevBuf<uint32_t> bc;
-                CU(bc.alloc(s->blocks)); CU(s->staticCount.alloc(4));
-                CU(cudaMemsetAsync(s->staticCount.p, 0, 4 * sizeof(uint32_t), st));
-                if (h->fs) k_static_count<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
-                else k_static_count<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
-                k_list_offsets<<<1, 1024, 0, st>>>(bc.p, s->blocks, s->staticCount.p, 1, s->N);
-                CU(cudaMemcpyAsync(h->pinnedStatus + 8, s->staticCount.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                CU(cudaStreamSynchronize(st));
-                s->nStatic = h->pinnedStatus[8];
-                CU(s->staticList.alloc(s->nStatic + 1));
-                if (h->fs) k_static_write<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
-                else k_static_write<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p, s->staticList.p);
-                CU(cudaStreamSynchronize(st));
-                h->launches += 3;
-            }
+            if (int r = build_static(h, s)) return r;
             // initial interface count (LB::redistributeMass divides by interfaceNodes.size())
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
             ++h->launches;
@@ -1577,6 +1632,7 @@ int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes) {
     h->steps = hd.steps; h->cur = (int)hd.cur; h->macroValid = hd.macroValid != 0; h->lastStepFirst = hd.lastStepFirst != 0;
     h->lastStepCoupled = hd.lastStepCoupled != 0;
     h->typesFlipped = false; h->listsFresh = false;
+    if (h->wallPush && h->steps > 0) wall_push(h, h->cur);
     return LBGPU_OK;
 }
 
