@@ -31,7 +31,7 @@ class LbGpuParams(C.Structure):
 
 
 # every symbol include/lbgpu.h declares
-EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
+EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuInitBox", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
            "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize")
@@ -62,6 +62,8 @@ def load_library(build_if_missing=True):
     L.lbGpuSlabRange.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.lbGpuInit.restype = C.c_int
     L.lbGpuInit.argtypes = [C.POINTER(LbGpuParams), vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    L.lbGpuInitBox.restype = C.c_int
+    L.lbGpuInitBox.argtypes = [C.POINTER(LbGpuParams), vp, vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(vp)]
     L.lbGpuSetCurves.restype = C.c_int
     L.lbGpuSetCurves.argtypes = [vp, C.c_uint32, vp, vp]
     L.lbGpuSetMassTarget.restype = C.c_int

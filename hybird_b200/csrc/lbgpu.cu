@@ -1012,10 +1012,12 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             CU(cudaStreamSynchronize(st));
             s->ghostIdx = gd; s->ghostSrc = gs;
             s->ghostType.resize(s->nGhost); s->ghostSolid.resize(s->nGhost);
-            for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]]; }
+            if (type_flags)
+                for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]]; }
         }
     }
 
+    if (!type_flags) { CU(cudaGetLastError()); return 0; }  // device-side initialisation fills the arrays (device_init)
     if (perZ && s->remoteLo && s->zBegin == 1) {
         s->shellTypeLo.assign(type_flags + hostOff, type_flags + hostOff + s->XY);
         s->shellSolidLo.assign(solidIndex + hostOff, solidIndex + hostOff + s->XY);
@@ -1076,9 +1078,113 @@ int lbGpuSlabRange(int32_t sizeZ, int32_t nSlabs, int32_t slab, int32_t* zBegin,
     return LBGPU_OK;
 }
 
-int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
-              const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out) {
-    if (!prm || !type_flags || !solidIndex || !n || !u || !mass || !visc || !out) return fail(LBGPU_EINVAL, "lbGpuInit: null argument");
+}  // extern "C"
+
+namespace {
+
+struct BoxSetup {
+    InitBox box;
+    std::vector<InitRegion> regions;
+    const LbGpuParticle* parts = nullptr;
+    uint32_t nParts = 0;
+};
+
+__global__ void k_set_cell0_node(Dev p, InitBox b) {
+    // the reference's wall-node loop starts at j = 0, where neighbors[i].d[0] of interior cells is 0 (never assigned,
+    // LB.cpp:377-387, 955): cell 0 gets a node whenever it is a wall
+    const uint8_t tb = p.type[0];
+    const int t = tb & TYPE_MASK;
+    if (!is_wall_type(t) || (tb & NODE_BIT)) return;
+    p.type[0] = tb | NODE_BIT;
+    p.n[0] = 1.0;
+    if (t == T_DYN_WALL || t == T_SLIP_DYN)
+        for (int k = 0; k < 6; ++k)
+            if (b.wallOfBoundary[k] == (int)p.solidIndex[0]) { p.ux[0] = b.wallVel[k][0]; p.uy[0] = b.wallVel[k][1]; p.uz[0] = b.wallVel[k][2]; }
+}
+
+// LB::latticeBolzmannInit for a box problem, on the device (kernels: lb_kernels.cuh, k_init_*)
+int device_init(LbGpuHandle* h, const BoxSetup& bs) {
+    cudaStream_t st = h->stream;
+    const InitBox& b = bs.box;
+    int rc;
+    DevBuf<InitRegion> dreg;
+    DevBuf<uint32_t> flag;
+    DevBuf<int> maxp;
+    CU(dreg.alloc(bs.regions.size() + 1)); CU(flag.alloc(1)); CU(maxp.alloc(3));
+    if (!bs.regions.empty()) CU(cudaMemcpyAsync(dreg.p, bs.regions.data(), sizeof(InitRegion) * bs.regions.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(flag.p, 0, sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(maxp.p, 0xff, 3 * sizeof(int), st));  // -1
+    for (auto& sp : h->slabs) { k_init_types<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()), b); ++h->launches; }
+    // what the reference holds in the cells the device treats as periodic ghosts (dead cells; lbGpuFetchFields reports them)
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        if (!s->nGhost) continue;
+        std::vector<uint8_t> t(s->N);
+        std::vector<uint32_t> si(s->N);
+        CU(cudaMemcpyAsync(t.data(), s->type0.p, s->N, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(si.data(), s->solidIndex.p, sizeof(uint32_t) * s->N, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = t[s->ghostIdx[k]]; s->ghostSolid[k] = si[s->ghostIdx[k]]; }
+        // cell 0 of the lattice (see k_set_cell0_node) when it is such a dead cell
+        if (s->zBegin == 1)
+            for (uint32_t k = 0; k < s->nGhost; ++k)
+                if (s->ghostIdx[k] == 0 && is_wall_type(s->ghostType[k] & TYPE_MASK)) s->ghostType[k] |= NODE_BIT;
+    }
+    if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
+    if (bs.nParts) {
+        // LB::initializeParticleBoundaries (LB.cpp:475-495)
+        if ((rc = upload_particles(h, bs.parts, bs.nParts, nullptr, 0, nullptr, 0))) return rc;
+        const uint32_t wb = (bs.nParts * 32 + BLOCK - 1) / BLOCK;
+        for (auto& sp : h->slabs) {
+            k_rescan<0><<<wb, BLOCK, 0, st>>>(dev_for(h, sp.get()));
+            k_rescan<1><<<wb, BLOCK, 0, st>>>(dev_for(h, sp.get()));
+            h->launches += 2;
+        }
+        if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
+        CU(cudaStreamSynchronize(st));
+        h->nParts = 0; h->nElmts = 0; h->nComps = 0;  // the particles become resident with the first coupling step
+    }
+    if (!bs.regions.empty()) {
+        for (auto& sp : h->slabs) { k_init_gas<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()), dreg.p, (int)bs.regions.size(), flag.p); ++h->launches; }
+        CU(cudaMemcpyAsync(h->pinnedStatus, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*h->pinnedStatus) {
+            if ((rc = exchange(h, G_TYPE))) return rc;
+            for (auto& sp : h->slabs) { k_init_closure<0><<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get())); ++h->launches; }
+            if ((rc = exchange(h, G_TYPE))) return rc;
+            for (auto& sp : h->slabs) { k_init_closure<1><<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get())); ++h->launches; }
+            if ((rc = exchange(h, G_TYPE))) return rc;
+        }
+    }
+    for (auto& sp : h->slabs) { k_init_maxp<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()), maxp.p); ++h->launches; }
+    int mp[3];
+    CU(cudaMemcpyAsync(mp, maxp.p, sizeof mp, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const bool any = mp[0] >= 0;
+    for (auto& sp : h->slabs) {
+        k_init_fields<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()), b, any ? (double)mp[0] : 0.0, any ? (double)mp[1] : 0.0, any ? (double)mp[2] : 0.0);
+        ++h->launches;
+    }
+    if ((rc = exchange(h, G_TYPE))) return rc;
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        k_init_wall_nodes<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), b);
+        ++h->launches;
+        if (s->zBegin == 1 && !s->dev.ghost[0] && !s->dev.ghost[2] && !s->remoteLo) { k_set_cell0_node<<<1, 1, 0, st>>>(dev_all(h, s), b); ++h->launches; }
+    }
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        k_upload_f<<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), nullptr, s->fbuf(0), s->fbuf(1));
+        ++h->launches;
+    }
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
+              const double* n, const double* u, const double* mass, const double* visc, const BoxSetup* box, LbGpuHandle** out) {
+    if (!prm || !out || (!box && (!type_flags || !solidIndex || !n || !u || !mass || !visc))) return fail(LBGPU_EINVAL, "lbGpuInit: null argument");
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -1112,7 +1218,14 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     const unsigned long long Nh = XY * (unsigned long long)(zHi - zLo + 2);  // cells in the host arrays
     if (Nh >= (1ull << 31)) return fail(LBGPU_EINVAL, "lbGpuInit: %llu cells exceed the 2^31 index range", Nh);
     bool anyDyn = false, anyGas = false, anyIface = false, anySlip = false, anyCurved = false;
-    for (unsigned long long i = 0; i < Nh; ++i) {
+    if (box) {
+        for (int k = 0; k < 6; ++k) {
+            anyDyn |= (prm->boundary[k] == T_DYN_WALL || prm->boundary[k] == T_SLIP_DYN);
+            anySlip |= (prm->boundary[k] == T_SLIP_STAT || prm->boundary[k] == T_SLIP_DYN);
+        }
+        anyGas = anyIface = !box->regions.empty();
+    }
+    for (unsigned long long i = 0; type_flags && i < Nh; ++i) {
         const int t = type_flags[i] & LBGPU_TYPE_MASK;
         anyCurved |= (t == T_CURVED);
         if (t == 1 || t > 9) return fail(LBGPU_EINVAL, "lbGpuInit: cell %llu has undefined type %d", i, t);
@@ -1173,6 +1286,7 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
             s->zBegin = zb; s->zEnd = ze;
             if (int r = build_slab(h, s, zLo - 1, type_flags, solidIndex, f, n, u, mass, visc)) return r;
         }
+        if (box) { if (int r = device_init(h, *box)) return r; }
         // ghosts of every field, both population buffers
         if (int r = exchange(h, G_POPS | G_POPS_SRC | G_TYPE | G_SOLID | G_MASS | G_MACRO | G_VISC | G_HF)) return r;
         cudaStream_t st = h->stream;
@@ -1197,6 +1311,48 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
     if (rc) { lbGpuFinalize(h); return rc; }
     *out = h;
     return LBGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
+              const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out) {
+    if (!type_flags) return fail(LBGPU_EINVAL, "lbGpuInit: null argument");
+    return init_impl(prm, type_flags, solidIndex, f, n, u, mass, visc, nullptr, out);
+}
+
+int lbGpuInitBox(const LbGpuParams* prm, const double initVelocity[3], const double* wallVelocity, const LbGpuRegion* regions,
+                 uint32_t nRegions, const LbGpuParticle* parts, uint32_t nParts, LbGpuHandle** out) {
+    if (!prm || !out || (nRegions && !regions) || (nParts && !parts)) return fail(LBGPU_EINVAL, "lbGpuInitBox: null argument");
+    if (lbcomm::active()) return fail(LBGPU_EUNSUPPORTED, "lbGpuInitBox: one process only (slabs of other processes: use lbGpuInit with host arrays)");
+    if (prm->boundary[4] == T_PERIODIC && prm->nSlabs > 1) return fail(LBGPU_EUNSUPPORTED, "lbGpuInitBox: z-periodic lattice cut into slabs");
+    BoxSetup bs;
+    memset(&bs.box, 0, sizeof bs.box);
+    int nWalls = 0;
+    const double speed = prm->unitLength / prm->unitTime;  // measureUnits::setComposite (node.cpp:476-488)
+    for (int k = 0; k < 6; ++k) {
+        const int bt = prm->boundary[k];
+        if (bt < T_PERIODIC || bt > T_DYN_WALL) return fail(LBGPU_EINVAL, "lbGpuInitBox: boundary%d = %d (4..8 expected)", k, bt);
+        bs.box.boundary[k] = bt;
+        bs.box.wallOfBoundary[k] = (bt >= T_SLIP_STAT) ? nWalls++ : -1;  // DEM::initializeWalls (DEM.cpp:435-640)
+        const bool moving = (bt == T_SLIP_DYN || bt == T_DYN_WALL);
+        for (int c = 0; c < 3; ++c) bs.box.wallVel[k][c] = (moving && wallVelocity) ? wallVelocity[3 * k + c] / speed : 0.0;
+    }
+    if (nWalls != prm->nWalls) return fail(LBGPU_EINVAL, "lbGpuInitBox: %d boundaries are walls but nWalls = %d", nWalls, prm->nWalls);
+    bs.box.nRegions = (int)nRegions;
+    for (int c = 0; c < 3; ++c) { bs.box.lbF[c] = prm->lbF[c]; bs.box.initVelocity[c] = initVelocity ? initVelocity[c] : 0.0; }
+    bs.box.initVisc = prm->initDynVisc;
+    for (uint32_t r = 0; r < nRegions; ++r) {
+        InitRegion g;
+        g.kind = regions[r].kind; g.gasInside = regions[r].gasInside;
+        if (g.kind < 0 || g.kind > 2) return fail(LBGPU_EINVAL, "lbGpuInitBox: region %u has kind %d", r, g.kind);
+        for (int c = 0; c < 6; ++c) g.a[c] = regions[r].a[c];
+        bs.regions.push_back(g);
+    }
+    bs.parts = parts; bs.nParts = nParts;
+    return init_impl(prm, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &bs, out);
 }
 
 int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, const double* delta) {

@@ -107,6 +107,21 @@ int lbGpuCommFinalize(void);
 int lbGpuInit(const LbGpuParams* params, const uint8_t* type_flags, const uint32_t* solidIndex, const double* f,
               const double* n, const double* u, const double* mass, const double* visc, LbGpuHandle** out);
 
+/* The same state built ON THE DEVICE for a box problem -- a lattice bounded by its six planes (problemName NONE /
+ * demChute): LB::latticeBolzmannInit's cell types, DEM wall indices, particle flags, gas region with the interface
+ * closure, hydrostatic density, initial velocity, masses and wall nodes (LB.cpp:190-219, 324-996; DEM.cpp:435-640)
+ * computed per cell, instead of by the reference's serial O(N x n_geom) host loops and a 35 GB host mirror at 67 M
+ * cells.  Bit-identical to uploading the host-built state.  One process (any number of local slabs).
+ *   initVelocity   lattice units (LB.cpp:143)
+ *   wallVelocity   6 x 3, physical units, velocity of the DEM wall of boundary k (used where boundary k is 6 or 8); may be NULL
+ *   regions        applied in order to fluid cells: a cell inside (gasInside) / outside (!gasInside) becomes gas
+ *                  kind 0: box a0<=x<=a1, a2<=y<=a3, a4<=z<=a5;  1: sphere centre (a0,a1,a2) radius a3 (strictly inside);
+ *                  2: half space z > a0 (demChute: a0 = 0.025/unit.Length + 0.5, LB.cpp:612-627)       [lattice units]
+ *   parts          particles in physical units as in lbGpuStep (LB::initializeParticleBoundaries) */
+typedef struct { int32_t kind, gasInside; double a[6]; } LbGpuRegion;
+int lbGpuInitBox(const LbGpuParams* params, const double initVelocity[3], const double* wallVelocity, const LbGpuRegion* regions,
+                 uint32_t nRegions, const LbGpuParticle* parts, uint32_t nParts, LbGpuHandle** out);
+
 /* Curved walls (type 9; problem geometries with a cylinder: DRUM / AVALANCHE / NET).  LB::curves (LB.h:63-64) as
  * LB::initializeCurved (LB.cpp:589-603) left it: cells[k] is the cell index of the k-th `curve` object in the host
  * arrays' order, delta[19*k + j] its curve::delta[j] (node.h:133-148; m1, m2 and chi follow from delta, node.cpp:458-472).
