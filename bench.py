@@ -215,7 +215,8 @@ def main_ours(args, rank, world, local_rank):
 
     case = workload_case(args.workload, world)
     t_init = time.time()
-    lb, info = slabs.build_engine(case, rank, world, device=local_rank, dist=dist if world > 1 else None)
+    lb, info = slabs.build_engine(case, rank, world, device=local_rank, dist=dist if world > 1 else None,
+                                  device_init=(world == 1 and not args.host_init))
     active_local = info["active_local"]
     active_total = info["active_total"]
     t_init = time.time() - t_init
@@ -329,7 +330,7 @@ def main_ours(args, rank, world, local_rank):
                    "lattice": [int(size[0]), int(size[1]), int(info["global_z"])], "active_cells": int(active_total),
                    "parallelism": info["parallelism"],
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (info["bytes_resident"] / 1e9),
-                   "init_upload_s": round(t_init, 2)},
+                   "init_s": round(t_init, 2), "init": info["init"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": info["kernel"],
                      "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(active_local),
@@ -339,9 +340,9 @@ def main_ours(args, rank, world, local_rank):
                 "fetch_fields_ms": fetch_ms, "fetch_fields_bytes": fetch_bytes,
                 # the other two host-facing calls of a run, once each: lbGpuInit (state upload from pageable host
                 # arrays) and lbGpuFetchFields (what an export step of the reference's IO reads)
-                "init_upload_ms": 1e3 * info["upload_s"], "init_upload_bytes": info["upload_bytes"],
+                "init_ms": 1e3 * info["upload_s"], "init_upload_bytes": info["upload_bytes"],
                 "job_value": active_total * K / (info["upload_s"] + ms_dev * 1e-3 + fetch_ms * 1e-3) / 1e6,
-                "job": "lbGpuInit(host state) + %d steps + one lbGpuFetchFields(host), rank 0's copies" % K},
+                "job": "%s + %d steps + one lbGpuFetchFields(host), rank 0's copies" % (info["init"], K)},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -361,6 +362,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-init", action="store_true", help="build the initial state on the host and upload it (lbGpuInit) "
+                    "instead of initialising the lattice on the device (lbGpuInitBox; one process only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -116,6 +116,7 @@ struct Slab {
     // host copies of what lbGpuInit received for the ghost cells (they are dead cells of the reference)
     std::vector<uint32_t> ghostIdx, ghostSrc, ghostSolid;
     std::vector<uint8_t> ghostType;
+    std::vector<double> ghostN, ghostU;  // density / velocity of the dead cells that carry a wall node (cell 0 at most)
     // z-periodic lattice cut into several slabs: the reference's shell planes z=0 / z=Z-1 are replaced by remote ghost
     // planes on the device; what lbGpuInit received for them is kept for lbGpuFetchFields
     std::vector<uint8_t> shellTypeLo, shellTypeHi;
@@ -1012,8 +1013,15 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             CU(cudaStreamSynchronize(st));
             s->ghostIdx = gd; s->ghostSrc = gs;
             s->ghostType.resize(s->nGhost); s->ghostSolid.resize(s->nGhost);
+            s->ghostN.assign(s->nGhost, 0.0); s->ghostU.assign((size_t)3 * s->nGhost, 0.0);
             if (type_flags)
-                for (uint32_t k = 0; k < s->nGhost; ++k) { s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]]; }
+                for (uint32_t k = 0; k < s->nGhost; ++k) {
+                    s->ghostType[k] = type_flags[hostOff + gd[k]]; s->ghostSolid[k] = solidIndex[hostOff + gd[k]];
+                    if (s->ghostType[k] & NODE_BIT) {
+                        s->ghostN[k] = n[hostOff + gd[k]];
+                        for (int c = 0; c < 3; ++c) s->ghostU[3 * k + c] = u[3 * (hostOff + gd[k]) + c];
+                    }
+                }
         }
     }
 
@@ -1128,7 +1136,15 @@ int device_init(LbGpuHandle* h, const BoxSetup& bs) {
         // cell 0 of the lattice (see k_set_cell0_node) when it is such a dead cell
         if (s->zBegin == 1)
             for (uint32_t k = 0; k < s->nGhost; ++k)
-                if (s->ghostIdx[k] == 0 && is_wall_type(s->ghostType[k] & TYPE_MASK)) s->ghostType[k] |= NODE_BIT;
+                if (s->ghostIdx[k] == 0 && is_wall_type(s->ghostType[k] & TYPE_MASK)) {
+                    s->ghostType[k] |= NODE_BIT;
+                    s->ghostN[k] = 1.0;  // node::initialize(initDensity, wall velocity, ...) (LB.cpp:946-996)
+                    const int t0 = s->ghostType[k] & TYPE_MASK;
+                    if (t0 == T_DYN_WALL || t0 == T_SLIP_DYN)
+                        for (int kb = 0; kb < 6; ++kb)
+                            if (b.wallOfBoundary[kb] == (int)s->ghostSolid[k])
+                                for (int c = 0; c < 3; ++c) s->ghostU[3 * k + c] = b.wallVel[kb][c];
+                }
     }
     if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
     if (bs.nParts) {
@@ -1567,6 +1583,12 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         };
         int rc;
         if (n && (rc = scalar(s->n.p, n, 0))) return rc;
+        if (n) {
+            // a dead cell of the reference (periodic shell) that carries a node is a wall node: density initDensity = 1
+            // (LB.cpp:946-996; only cell 0 can be one, through d[0] = 0 of the interior cells)
+            for (uint32_t k = 0; k < s->nGhost; ++k)
+                if ((s->ghostType[k] & NODE_BIT) && is_wall_type(s->ghostType[k] & TYPE_MASK)) n[hBase + s->ghostIdx[k]] = s->ghostN[k];
+        }
         if (mass && (rc = scalar(s->mass.p, mass, 0))) return rc;
         if (visc && (rc = scalar(s->visc.p, visc, 0))) return rc;
         if (shearRate && (rc = scalar(s->shearRate.p, shearRate, 1))) return rc;
@@ -1575,6 +1597,9 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             CU(cudaMemcpyAsync(u + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
             shell_zero(u, 3);
+            for (uint32_t k = 0; k < s->nGhost; ++k)
+                if ((s->ghostType[k] & NODE_BIT) && is_wall_type(s->ghostType[k] & TYPE_MASK))
+                    for (int c = 0; c < 3; ++c) u[3 * (hBase + s->ghostIdx[k]) + c] = s->ghostU[3 * k + c];
         }
         if (hydroForce) {
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->hfx.p, s->hfy.p, s->hfz.p, tmp.p, 1);

@@ -270,6 +270,22 @@ def advance_kinematic(parts, elmts, x0_elmt, dt):
     return parts
 
 
+def regions_from_case(case: dict, prm: dict):
+    """The gas regions of a case as (kind, gasInside, values) in the order build_state applies them (lbGpuInitBox)."""
+    out = []
+    if case.get("problemName") == "demChute":  # LB.cpp:612-627
+        out.append((2, 1, [0.025 / prm["unitLength"] + 0.5]))
+    if "fluid_box" in case:
+        out.append((0, 0, [float(v) for v in case["fluid_box"]]))
+    if "gas_box" in case:
+        out.append((0, 1, [float(v) for v in case["gas_box"]]))
+    if "gas_sphere" in case:
+        out.append((1, 1, [float(v) for v in case["gas_sphere"]]))
+    if "fluid_sphere" in case:
+        out.append((1, 0, [float(v) for v in case["fluid_sphere"]]))
+    return out
+
+
 def build_state(case: dict, parts=None, window=None, reduce_max=None) -> LatticeState:
     """LB::latticeBolzmannInit (LB.cpp:190-219) for a box case (see oracle/cases.py for the keys).
 

@@ -64,6 +64,27 @@ class LB:
                                      abi.ptr(m_), abi.ptr(v_), C.byref(self.h)))
         return self
 
+    # -- the same, built on the device for a box problem (lbGpuInitBox) ------------------------------
+    def latticeBolzmannInitBox(self, case: dict, particles=None):
+        """`case`: hybird configuration keys + set-up options as in hybird_b200.workloads (what
+        lattice_init.build_state restates on the host)."""
+        from . import lattice_init as li
+        if self.planes != (0, int(self.params["size"][2])):
+            raise ValueError("latticeBolzmannInitBox: one process only")
+        regions = li.regions_from_case(case, self.params)
+        reg = np.zeros(len(regions), dtype=np.dtype([("kind", "<i4"), ("gasInside", "<i4"), ("a", "<f8", 6)], align=True))
+        for k, (kind, inside, a) in enumerate(regions):
+            reg[k]["kind"] = kind; reg[k]["gasInside"] = inside; reg[k]["a"][:len(a)] = a
+        iv = np.ascontiguousarray(self.params.get("initVelocity", [0.0, 0.0, 0.0]), dtype=np.float64)
+        wv = np.zeros((6, 3))
+        walls = li.make_walls(self.params, case.get("wall_vel", ()))
+        for w in walls:
+            wv[2 * w.axis + w.side] = w.vel
+        parts = None if particles is None or len(particles) == 0 else np.ascontiguousarray(particles)
+        abi.check(self.lib.lbGpuInitBox(C.byref(self.P), abi.ptr(iv), abi.ptr(wv), abi.ptr(reg) if len(reg) else None, len(reg),
+                                        abi.ptr(parts), 0 if parts is None else len(parts), C.byref(self.h)))
+        return self
+
     # -- LB::curves (LB.h:63-64) as LB::initializeCurved left them; LB::totalMass for problemName DRUM -------
     def setCurves(self, cells, delta):
         cells = np.ascontiguousarray(cells, dtype=np.uint32)

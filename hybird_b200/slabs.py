@@ -96,13 +96,29 @@ def owned_active(st, window, Z: int, world: int, rank: int) -> int:
     return int(np.count_nonzero(np.isin(t & 0x0F, (0, 3))))
 
 
-def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None):
+def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None, device_init: bool = False):
     """State of this rank's slab built directly (never the whole lattice), uploaded to `device`.
-    For world > 1 the communicator must exist already (init_comm)."""
+    For world > 1 the communicator must exist already (init_comm).
+    device_init (one process): the lattice is initialised on the device (lbGpuInitBox), no host state at all."""
+    import time
     prm = li.params_from_case(case)
     Zg = prm["size"][2]
     elements = case.get("elements", [])
     parts, elmts, comps = li.expand_elements(elements, prm["unitLength"])
+    if world == 1 and device_init:
+        prm["nWalls"] = len(li.make_walls(prm))
+        lb = LB(prm, device=device)
+        t0 = time.perf_counter()
+        lb.latticeBolzmannInitBox(case, parts if len(parts) else None)
+        lb.synchronize()
+        init_s = time.perf_counter() - t0
+        c = lb.counts()
+        active = c["fluid"] + c["interface"]
+        N = int(np.prod(prm["size"]))
+        info = dict(upload_s=init_s, upload_bytes=0, params=prm, active_local=active, active_total=active, global_z=Zg,
+                    parallelism="1 GPU", parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
+                    bytes_resident=2 * 19 * 8 * N + 60 * N, init="device (lbGpuInitBox)")
+        return lb, info
     if world == 1:
         st = li.build_state(case, parts if len(parts) else None)
         active = int(np.count_nonzero(np.isin(st.type_flags & 0x0F, (0, 3))))
@@ -118,7 +134,6 @@ def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None)
         dist.all_reduce(t)
         active_total = int(t.item())
         par = "%d z-slabs, one rank per GPU, NCCL send/recv halo (5 populations per face)" % world
-    import time
     lb = LB(st.params, device=device)
     t0 = time.perf_counter()
     lb.latticeBolzmannInit(st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)
@@ -127,7 +142,7 @@ def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None)
     upload_bytes = int(sum(a.nbytes for a in (st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)))
     info = dict(upload_s=upload_s, upload_bytes=upload_bytes, params=st.params, active_local=active, active_total=active_total, global_z=Zg, parallelism=par,
                 parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
-                bytes_resident=2 * 19 * 8 * st.type_flags.size + 60 * st.type_flags.size)
+                bytes_resident=2 * 19 * 8 * st.type_flags.size + 60 * st.type_flags.size, init="host arrays (lbGpuInit)")
     return lb, info
 
 
