@@ -5,7 +5,7 @@ the reference: hybird.cpp:132-223, LB.cpp:85-188, DEM.cpp:13-183) plus harness o
 gas regions, wall velocities, particle list, prescribed particle motion).  The same dict feeds
 
   * oracle/_ref/ref_harness   (the unmodified reference, via a generated .cfg + particle file),
-  * oracle/lb_oracle.c        (the C restatement, via hybird_b200.host.CaseSetup),
+  * oracle/lb_oracle.c        (the C restatement, via hybird_b200.lattice_init.build_state),
   * the CUDA engine           (via the C ABI in include/lbgpu.h),
 
 so that all three see identical inputs.  The five BASELINE.json configs are `cfg1`..`cfg5`;
