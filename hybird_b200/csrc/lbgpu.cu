@@ -144,6 +144,11 @@ struct LbGpuHandle {
     DevBuf<uint32_t> comps;
     void* pinned = nullptr;
     size_t pinnedBytes = 0;
+    // bulk transfers between the caller's pageable arrays and the device go through two pinned stages (the CPU copy of
+    // one chunk overlaps the DMA of the other; a plain cudaMemcpy from pageable memory serialises the two)
+    char* stage[2] = { nullptr, nullptr };
+    cudaEvent_t stageEv[2] = { nullptr, nullptr };
+    static constexpr size_t STAGE = 32u << 20;
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
@@ -236,6 +241,65 @@ Dev dev_all(LbGpuHandle* h, Slab* s) {  // same, covering every cell including r
     return d;
 }
 uint32_t own_blocks(const Slab* s) { return (s->ownEnd - s->ownBegin + BLOCK - 1) / BLOCK; }
+
+int ensure_stages(LbGpuHandle* h) {
+    for (int k = 0; k < 2; ++k) {
+        if (!h->stage[k]) CU(cudaMallocHost((void**)&h->stage[k], LbGpuHandle::STAGE));
+        if (!h->stageEv[k]) CU(cudaEventCreateWithFlags(&h->stageEv[k], cudaEventDisableTiming));
+    }
+    return 0;
+}
+// pageable host -> device, chunked through the two pinned stages; asynchronous on the handle's stream for the caller
+// (the source may be reused on return)
+int h2d_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
+    if (bytes < LbGpuHandle::STAGE) {  // small lattices: not worth pinning two stages
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    if (int rc = ensure_stages(h)) return rc;
+    size_t off = 0;
+    for (int k = 0; off < bytes; ++k, off += LbGpuHandle::STAGE) {
+        const size_t len = bytes - off < LbGpuHandle::STAGE ? bytes - off : LbGpuHandle::STAGE;
+        const int b = k & 1;
+        if (k >= 2) CU(cudaEventSynchronize(h->stageEv[b]));
+        memcpy(h->stage[b], (const char*)src + off, len);
+        CU(cudaMemcpyAsync((char*)dst + off, h->stage[b], len, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(h->stageEv[b], h->stream));
+    }
+    CU(cudaEventSynchronize(h->stageEv[0]));
+    CU(cudaEventSynchronize(h->stageEv[1]));
+    return 0;
+}
+// device -> pageable host, the same way; complete on return
+int d2h_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
+    if (bytes < LbGpuHandle::STAGE) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    if (int rc = ensure_stages(h)) return rc;
+    size_t off = 0, done = 0;
+    int k = 0;
+    for (; off < bytes; ++k, off += LbGpuHandle::STAGE) {
+        const size_t len = bytes - off < LbGpuHandle::STAGE ? bytes - off : LbGpuHandle::STAGE;
+        const int b = k & 1;
+        if (k >= 2) {  // the chunk that used this stage two rounds ago has landed: hand it to the caller
+            CU(cudaEventSynchronize(h->stageEv[b]));
+            memcpy((char*)dst + done, h->stage[b], LbGpuHandle::STAGE);
+            done += LbGpuHandle::STAGE;
+        }
+        CU(cudaMemcpyAsync(h->stage[b], (const char*)src + off, len, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->stageEv[b], h->stream));
+    }
+    for (int r = (k >= 2 ? k - 2 : 0); r < k; ++r) {
+        const int b = r & 1;
+        const size_t len = bytes - done < LbGpuHandle::STAGE ? bytes - done : LbGpuHandle::STAGE;
+        CU(cudaEventSynchronize(h->stageEv[b]));
+        memcpy((char*)dst + done, h->stage[b], len);
+        done += len;
+    }
+    return 0;
+}
 
 int ensure_pinned(LbGpuHandle* h, size_t bytes) {
     if (bytes <= h->pinnedBytes) return 0;
@@ -1036,15 +1100,16 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         s->shellSolidHi.assign(solidIndex + o, solidIndex + o + s->XY);
     }
     // staged upload: host (pageable) -> device scratch -> SoA
-    CU(cudaMemcpyAsync(s->type0.p, type_flags + hostOff, N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->solidIndex.p, solidIndex + hostOff, sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->n.p, n + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->mass.p, mass + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(s->visc.p, visc + hostOff, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+    { int rc;
+      if ((rc = h2d_staged(h, s->type0.p, type_flags + hostOff, N))) return rc;
+      if ((rc = h2d_staged(h, s->solidIndex.p, solidIndex + hostOff, sizeof(uint32_t) * N))) return rc;
+      if ((rc = h2d_staged(h, s->n.p, n + hostOff, sizeof(double) * N))) return rc;
+      if ((rc = h2d_staged(h, s->mass.p, mass + hostOff, sizeof(double) * N))) return rc;
+      if ((rc = h2d_staged(h, s->visc.p, visc + hostOff, sizeof(double) * N))) return rc; }
     {
         DevBuf<double> tmp;
         CU(tmp.alloc((size_t)3 * N));
-        CU(cudaMemcpyAsync(tmp.p, u + 3 * hostOff, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+        if (int rc = h2d_staged(h, tmp.p, u + 3 * hostOff, sizeof(double) * 3 * N)) return rc;
         k_split3<<<s->blocks, BLOCK, 0, st>>>(N, tmp.p, s->ux.p, s->uy.p, s->uz.p);
         CU(cudaStreamSynchronize(st));
     }
@@ -1052,7 +1117,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     if (f) {
         DevBuf<double> tmp;
         CU(tmp.alloc((size_t)Q * N));
-        CU(cudaMemcpyAsync(tmp.p, f + (size_t)Q * hostOff, sizeof(double) * Q * N, cudaMemcpyHostToDevice, st));
+        if (int rc = h2d_staged(h, tmp.p, f + (size_t)Q * hostOff, sizeof(double) * Q * N)) return rc;
         k_upload_f<<<s->blocks, BLOCK, 0, st>>>(dd, tmp.p, s->fbuf(0), s->fbuf(1));
         CU(cudaStreamSynchronize(st));
     } else {
@@ -1559,14 +1624,14 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             DevBuf<uint8_t> tmp;
             CU(tmp.alloc(s->N));
             k_fetch_types<<<B, BLOCK, 0, st>>>(d, tmp.p);
-            CU(cudaMemcpyAsync(type_flags + hOff, tmp.p + cOff, cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, type_flags + hOff, tmp.p + cOff, cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             for (uint32_t k = 0; k < s->nGhost; ++k) type_flags[hBase + s->ghostIdx[k]] = s->ghostType[k];
             if (!s->shellTypeLo.empty()) memcpy(type_flags + hBase, s->shellTypeLo.data(), s->XY);
             if (!s->shellTypeHi.empty()) memcpy(type_flags + hTop, s->shellTypeHi.data(), s->XY);
         }
         if (solidIndex) {
-            CU(cudaMemcpyAsync(solidIndex + hOff, s->solidIndex.p + cOff, sizeof(uint32_t) * cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, solidIndex + hOff, s->solidIndex.p + cOff, sizeof(uint32_t) * cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             for (uint32_t k = 0; k < s->nGhost; ++k) solidIndex[hBase + s->ghostIdx[k]] = s->ghostSolid[k];
             if (!s->shellSolidLo.empty()) memcpy(solidIndex + hBase, s->shellSolidLo.data(), sizeof(uint32_t) * s->XY);
@@ -1576,7 +1641,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         if (n || u || mass || visc || shearRate || hydroForce) CU(tmp.alloc((size_t)3 * s->N));
         auto scalar = [&](const double* src, double* dst, int activeOnly) -> int {
             k_fetch_scalar<<<B, BLOCK, 0, st>>>(d, src, tmp.p, activeOnly);
-            CU(cudaMemcpyAsync(dst + hOff, tmp.p + cOff, sizeof(double) * cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, dst + hOff, tmp.p + cOff, sizeof(double) * cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             shell_zero(dst, 1);
             return 0;
@@ -1594,7 +1659,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         if (shearRate && (rc = scalar(s->shearRate.p, shearRate, 1))) return rc;
         if (u) {
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->ux.p, s->uy.p, s->uz.p, tmp.p, 0);
-            CU(cudaMemcpyAsync(u + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, u + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             shell_zero(u, 3);
             for (uint32_t k = 0; k < s->nGhost; ++k)
@@ -1603,7 +1668,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
         }
         if (hydroForce) {
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->hfx.p, s->hfy.p, s->hfz.p, tmp.p, 1);
-            CU(cudaMemcpyAsync(hydroForce + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, hydroForce + 3 * hOff, tmp.p + 3 * cOff, sizeof(double) * 3 * cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             shell_zero(hydroForce, 3);
         }
@@ -1611,7 +1676,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             DevBuf<double> tf;
             CU(tf.alloc((size_t)Q * s->N));
             k_download_f<<<B, BLOCK, 0, st>>>(d, s->fbuf(h->cur), tf.p);
-            CU(cudaMemcpyAsync(f + (size_t)Q * hOff, tf.p + (size_t)Q * cOff, sizeof(double) * Q * cCnt, cudaMemcpyDeviceToHost, st));
+            if (int rc2 = d2h_staged(h, f + (size_t)Q * hOff, tf.p + (size_t)Q * cOff, sizeof(double) * Q * cCnt)) return rc2;
             CU(cudaStreamSynchronize(st));
             shell_zero(f, Q);
         }
@@ -1830,6 +1895,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     for (cudaEvent_t e : h->kev0) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->kev1) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
+    for (int k = 0; k < 2; ++k) { if (h->stage[k]) cudaFreeHost(h->stage[k]); if (h->stageEv[k]) cudaEventDestroy(h->stageEv[k]); }
     if (h->pinnedStatus) cudaFreeHost(h->pinnedStatus);
     if (h->pinnedCounts) cudaFreeHost(h->pinnedCounts);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -1,4 +1,4 @@
-"""Summarise one GPU visit (tools/gpu_round.sh) into profiles/: launch list shares, raw ncu metrics of the
+"""Summarise one GPU visit (tools/gpu_final.sh) into profiles/: launch list shares, raw ncu metrics of the
 fused kernel, stall/opcode mix.  python tools/profile_summary.py <tag>"""
 import collections, csv, json, os, subprocess, sys
 tag = sys.argv[1]
