@@ -14,7 +14,7 @@ import cases  # noqa: E402
 pytestmark = pytest.mark.reference
 
 LIVE = ["cfg2_mini", "channel_oblique", "bingham_smago", "slip_dyn", "couette_dyn", "cfg3_mini", "two_spheres_kin",
-        "cluster_dem", "cfg4_mini", "bubble_periodic", "cfg1_mini", "cfg5_mini"]
+        "cluster_dem", "cfg4_mini", "bubble_periodic", "cfg1_mini", "cfg5_mini", "drum_mini", "drum_bingham"]
 
 
 @pytest.mark.parametrize("name", LIVE)
