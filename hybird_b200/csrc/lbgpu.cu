@@ -658,7 +658,7 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
         if (s->pCap) continue;
         s->pGroups = (s->N + 15u) / 16u;
         s->pScanBlocks = (s->pGroups + BLOCK - 1) / BLOCK;
-        s->pCap = s->N / 2 + 4096;
+        s->pCap = s->N + 16;  // every cell may be flagged (a packed bed)
         CU(s->pList.alloc(s->pCap)); CU(s->pCounts.alloc(4)); CU(s->pBlockCount.alloc(s->pScanBlocks));
     }
     if (rescan) {
