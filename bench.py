@@ -183,7 +183,8 @@ def run_port(case, steps, warmup, threads):
 def main_reference(args, rank, world):
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 20))
+    # a bounded sample: ~0.12 s per step on 16 threads -> at most ~12 s of CPU work
+    steps = max(1, min(args.steps, 100))
     warmup = max(1, min(args.warmup, 3))
     r = run_reference(args.workload, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MLUPS", "n_gpus": args.gpus,
@@ -357,7 +358,7 @@ def main_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference(args.workload, 8, 2)
+            r = run_reference(args.workload, 60, 3)  # ~8 s of CPU work on 16 threads
             cpu = {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
