@@ -699,8 +699,9 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
     // Flood fill, one generation per round.  The count of cells a generation flagged lives in status[1 + (gen & 1)] of
     // every slab (the global sum); the next generation's launches are gated on it, so the first SPEC generations are
     // issued without waiting for the host -- only then is the count read back, once per further generation.
-    constexpr int SPEC = 3;
-    for (int gen = 0; gen < 4096; ++gen) {
+    constexpr int SPEC = 3, MAX_GEN = 4096;
+    bool converged = false;
+    for (int gen = 0; gen < MAX_GEN; ++gen) {
         const int cur = 1 + (gen & 1), prev = 1 + ((gen + 1) & 1);
         const int gate = gen > 0 ? prev : -1;
         // generation 0 reuses the list (flags were only cleared since); later ones see the cells flagged meanwhile
@@ -724,10 +725,11 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
             for (auto& sp : h->slabs)
                 if (h->pinnedStatus[16 + sp->slot] > sp->pCap)
                     return fail(LBGPU_EUNSUPPORTED, "particle coupling: %u flagged cells exceed the list capacity %u", h->pinnedStatus[16 + sp->slot], sp->pCap);
-            if (*h->pinnedStatus == 0) break;
+            if (*h->pinnedStatus == 0) { converged = true; break; }
         }
         if ((rc = exchange(h, G_TYPE | G_SOLID))) return rc;
     }
+    if (!converged) return fail(LBGPU_EUNSUPPORTED, "particle coupling: the flood fill of LB::findNewSolid did not finish in %d generations", MAX_GEN);
     CU(cudaGetLastError());
     return 0;
 }
@@ -817,7 +819,10 @@ int lb_step(LbGpuHandle* h) {
     // interior is updated.  Moving walls keep the plain order (their per-block partial sums are indexed by block).
     int down = -1, up = -1;
     if (lbcomm::active()) neighbour_ranks(h, &down, &up);
-    const bool overlap = lbcomm::active() && !h->dynWall;
+    // (an edge slab with fewer than three owned planes has no interior to hide the transport behind: its face launch
+    // would be the whole slab, so such handles use the plain order too)
+    bool overlap = lbcomm::active() && !h->dynWall;
+    if (overlap && ((down >= 0 && h->slabs.front()->dev.Z < 5) || (up >= 0 && h->slabs.back()->dev.Z < 5))) overlap = false;
     auto launch = [&](Slab* s, uint32_t begin, uint32_t end) {
         if (end <= begin) return;
         Dev d = dev_for(h, s);
@@ -853,9 +858,8 @@ int lb_step(LbGpuHandle* h) {
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
         uint32_t b = s->ownBegin, e = s->ownEnd;
-        const bool thick = s->dev.Z >= 5;  // at least three owned planes
-        if (overlap && thick && q == 0 && down >= 0) { launch(s, b, b + s->XY); b += s->XY; }
-        if (overlap && thick && q + 1 == h->slabs.size() && up >= 0) { launch(s, e - s->XY, e); e -= s->XY; }
+        if (overlap && q == 0 && down >= 0) { launch(s, b, b + s->XY); b += s->XY; }
+        if (overlap && q + 1 == h->slabs.size() && up >= 0) { launch(s, e - s->XY, e); e -= s->XY; }
         rest[q] = { b, e };
     }
     if (overlap) {
@@ -1461,6 +1465,7 @@ int lbGpuSetCurves(LbGpuHandle* h, uint32_t nCurves, const uint32_t* cells, cons
         CU(s->curveRow.alloc(s->N));
         CU(cudaMemcpy(s->curveRow.p, row.data(), sizeof(uint32_t) * s->N, cudaMemcpyHostToDevice));
     }
+    CU(cudaDeviceSynchronize());  // the copies ran on the legacy stream; the handle's stream does not order against it
     h->curvesSet = true;
     return LBGPU_OK;
 }
@@ -1482,10 +1487,13 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
     h->kevCount = 0;
     int rc;
     if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
-    if (doCoupling) {
+    // LB::computeHydroForces (LB.cpp:1851-1919) applies the direct forcing on every cell flagged inside a particle whether
+    // or not goCycle ran the coupling step (demSolve = 0 keeps the flags of the initialisation): the particle lists
+    // become resident whenever they are given, only the flag update is tied to doCoupling
+    if (doCoupling || nParts > 0) {
         if ((rc = upload_particles(h, parts, nParts, elmts, nElmts, components, nComponents))) return rc;
-        if ((rc = coupling_step(h, rescanParticles != 0))) return rc;
     }
+    if (doCoupling) { if ((rc = coupling_step(h, rescanParticles != 0))) return rc; }
     if ((rc = lb_step(h))) return rc;
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
@@ -1878,6 +1886,7 @@ int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes) {
     h->steps = hd.steps; h->cur = (int)hd.cur; h->macroValid = hd.macroValid != 0; h->lastStepFirst = hd.lastStepFirst != 0;
     h->lastStepCoupled = hd.lastStepCoupled != 0;
     h->typesFlipped = false; h->listsFresh = false;
+    CU(cudaDeviceSynchronize());  // (see lbGpuSetCurves)
     if (h->wallPush && h->steps > 0) wall_push(h, h->cur);
     return LBGPU_OK;
 }

@@ -110,12 +110,24 @@ class LB:
         return False
 
     # -- LB::latticeBolzmannStep (LB.h:159) ------------------------------------------------------
-    def latticeBolzmannStep(self, elmts=None, particles=None, fetch_forces=True):
+    def latticeBolzmannStep(self, elmts=None, particles=None, fetch_forces=True, components=None):
+        """`elmts`, `particles` as the reference passes them to LB::latticeBolzmannStep; they only matter when no
+        coupling step was requested this cycle (demSolve = 0: the flags of the initialisation stay, the direct forcing
+        of LB::computeHydroForces still acts on them) -- `components` = the flattened elmts[].components then
+        (default: every element's particles in index order, as DEM::initializeParticle numbers them)."""
         fs = int(self._fs_requested and self.freeSurface)
         if self._couple is not None:
             rescan, parts, els, comps = self._couple
             self._last = (parts, els, comps)
             abi.check(self.lib.lbGpuStep(self.h, fs, 1, int(rescan), abi.ptr(parts), len(parts), abi.ptr(els), len(els),
+                                         abi.ptr(comps), len(comps)))
+        elif particles is not None and len(particles) and elmts is not None and len(elmts):
+            parts, els = np.ascontiguousarray(particles), np.ascontiguousarray(elmts)
+            if components is None:
+                components = self._last[2] if len(self._last[2]) else np.arange(len(parts), dtype=np.uint32)
+            comps = np.ascontiguousarray(components, dtype=np.uint32)
+            self._last = (parts, els, comps)
+            abi.check(self.lib.lbGpuStep(self.h, fs, 0, 0, abi.ptr(parts), len(parts), abi.ptr(els), len(els),
                                          abi.ptr(comps), len(comps)))
         else:
             abi.check(self.lib.lbGpuStep(self.h, fs, 0, 0, None, 0, None, 0, None, 0))

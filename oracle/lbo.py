@@ -166,9 +166,8 @@ class Oracle:
 # ---------------------------------------------------------------------------------------------
 def read_state(path):
     """Parse one PREFIX_stateNNNNNN.bin written by oracle/ref_harness.cpp::dumpState."""
-    with open(path, "rb") as fh:
-        raw = fh.read()
-    assert raw[:7] == b"HBDUMP2", raw[:8]
+    raw = np.memmap(path, dtype=np.uint8, mode="r")  # full-size dumps are several GB: mapped, not read
+    assert bytes(raw[:7]) == b"HBDUMP2", bytes(raw[:8])
     hdr = np.frombuffer(raw, dtype="<u4", count=8, offset=8)
     X, Y, Z, step, nE, nW, withNb, nP = [int(v) for v in hdr]
     N = X * Y * Z
@@ -183,7 +182,10 @@ def read_state(path):
     out["type"] = take("u1", N)
     out["flags"] = take("u1", N)
     out["solidIndex"] = take("<u4", N)
-    out["f"] = take("<f8", 19 * N, (N, 19))
+    lite = bool(withNb & 2)
+    withNb &= 1
+    if not lite:
+        out["f"] = take("<f8", 19 * N, (N, 19))
     out["fs"] = take("<f8", 19 * N, (N, 19))
     out["n"] = take("<f8", N)
     out["u"] = take("<f8", 3 * N, (N, 3))
@@ -193,7 +195,7 @@ def read_state(path):
     out["shearRate"] = take("<f8", N)
     if withNb:
         out["neighbors"] = take("<u4", 19 * N, (N, 19))
-    if raw[off:off + 7] == b"CURVES1":  # curved-wall cells and the mass target (trailer)
+    if bytes(raw[off:off + 7]) == b"CURVES1":  # curved-wall cells and the mass target (trailer)
         off += 8
         nc = int(take("<u4", 1)[0])
         out["curve_cells"] = take("<u4", nc)

@@ -19,6 +19,8 @@
 // Usage: ref_harness -c case.cfg [-key value ...] --out PREFIX --steps K [options]
 //   --dump a,b,c        full state dumps after these LB steps (0 = after init)
 //   --types-every       append the 1-byte type|p map after every step to PREFIX_types.bin
+//   --types-until K     ... only after init and after the steps <= K (and after every --dump step)
+//   --lite              state dumps without the pre-collision f (full-size lattices: 238 instead of 390 B per cell)
 //   --fluid-box x0 x1 y0 y1 z0 z1    fluid cells outside the (inclusive) box become gas
 //   --gas-box   x0 x1 y0 y1 z0 z1    fluid cells inside the (inclusive) box become gas
 //   --gas-sphere cx cy cz r          fluid cells with |pos-c|<r become gas
@@ -53,7 +55,8 @@ struct WallVel { int idx; double v[3]; };
 
 struct Args {
     std::string cfg, out = "ref";
-    unsigned steps = 1, warmup = 0, rescanEvery = 0;
+    unsigned steps = 1, warmup = 0, rescanEvery = 0, typesUntil = 0xffffffffu;
+    bool lite = false;
     std::set<unsigned> dumps;
     bool typesEvery = false, timeMode = false, dumpNeighbors = false;
     std::string motion = "none";
@@ -84,6 +87,8 @@ Args parseArgs(int argc, char** argv) {
             while (std::getline(ss, tok, ',')) a.dumps.insert((unsigned)atoi(tok.c_str()));
         }
         else if (s == "--types-every") a.typesEvery = true;
+        else if (s == "--types-until") { need(1); a.typesEvery = true; a.typesUntil = atoi(argv[++i]); }
+        else if (s == "--lite") a.lite = true;
         else if (s == "--dump-neighbors") a.dumpNeighbors = true;
         else if (s == "--time") a.timeMode = true;
         else if (s == "--motion") { need(1); a.motion = argv[++i]; }
@@ -193,14 +198,14 @@ template <class T> void wr(FILE* f, const T* p, size_t n) {
     if (fwrite(p, sizeof(T), n, f) != n) { perror("fwrite"); exit(3); }
 }
 
-void dumpState(const LB& lb, const DEM& dem, const std::string& path, unsigned step, bool withNeighbors) {
+void dumpState(const LB& lb, const DEM& dem, const std::string& path, unsigned step, bool withNeighbors, bool lite = false) {
     FILE* fp = fopen(path.c_str(), "wb");
     if (!fp) { perror(path.c_str()); exit(3); }
     const unsigned N = lb.totNodes;
     const char magic[8] = { 'H', 'B', 'D', 'U', 'M', 'P', '2', 0 };
     wr(fp, magic, 8);
     uint32_t hdr[8] = { lb.lbSize[0], lb.lbSize[1], lb.lbSize[2], step, (uint32_t)dem.elmts.size(),
-                        (uint32_t)dem.walls.size(), (uint32_t)withNeighbors, (uint32_t)dem.particles.size() };
+                        (uint32_t)dem.walls.size(), (uint32_t)withNeighbors | (lite ? 2u : 0u), (uint32_t)dem.particles.size() };
     wr(fp, hdr, 8);
     std::vector<uint8_t> t(N), fl(N);
     std::vector<uint32_t> si(N);
@@ -216,7 +221,7 @@ void dumpState(const LB& lb, const DEM& dem, const std::string& path, unsigned s
         for (unsigned i = 0; i < N; ++i) if (lb.nodes[i]) get(*lb.nodes[i], &buf[(size_t)width * i]);
         wr(fp, buf.data(), (size_t)width * N);
     };
-    field(19, [](const node& nd, double* o) { for (int j = 0; j < 19; ++j) o[j] = nd.f[j]; });
+    if (!lite) field(19, [](const node& nd, double* o) { for (int j = 0; j < 19; ++j) o[j] = nd.f[j]; });
     field(19, [](const node& nd, double* o) { for (int j = 0; j < 19; ++j) o[j] = nd.fs[j]; });
     field(1, [](const node& nd, double* o) { o[0] = nd.n; });
     field(3, [](const node& nd, double* o) { o[0] = nd.u.x; o[1] = nd.u.y; o[2] = nd.u.z; });
@@ -320,7 +325,7 @@ int main(int argc, char** argv) {
                 lb.boundary[3], lb.boundary[4], lb.boundary[5], (int)lb.freeSurface, (int)lb.forceField,
                 (int)lb.nonNewtonian, (int)lb.turbulenceOn);
         fprintf(logFp, "# totalMass %.17g enforceMass %d\n", lb.totalMass, (int)(problemName == DRUM));
-        if (a.dumps.count(0)) dumpState(lb, dem, a.out + "_state000000.bin", 0, a.dumpNeighbors);
+        if (a.dumps.count(0)) dumpState(lb, dem, a.out + "_state000000.bin", 0, a.dumpNeighbors, a.lite);
     }
     auto writeTypes = [&]() {
         std::vector<uint8_t> t(N);
@@ -375,7 +380,7 @@ int main(int argc, char** argv) {
                 wr(elmtFp, d, 7);
             }
             for (const wall& w : dem.walls) { double d[3] = { w.FHydro.x, w.FHydro.y, w.FHydro.z }; wr(elmtFp, d, 3); }
-            if (typesFp) writeTypes();
+            if (typesFp && (s <= a.typesUntil || a.dumps.count(s))) writeTypes();
             double mass = 0.0;
             for (unsigned i = 0; i < N; ++i)
                 if (lb.types[i].isActive() && !lb.types[i].isInsideParticle()) mass += lb.nodes[i]->mass;
@@ -384,7 +389,7 @@ int main(int argc, char** argv) {
             if (a.dumps.count(s)) {
                 char name[64];
                 snprintf(name, sizeof name, "_state%06u.bin", s);
-                dumpState(lb, dem, a.out + name, s, false);
+                dumpState(lb, dem, a.out + name, s, false, a.lite);
             }
         }
     }

@@ -38,7 +38,7 @@ STEPS = {
     "cfg2_mini": 30, "channel_oblique": 30, "box_noforce": 20, "periodic_all": 30,
     "smago_channel": 30, "bingham_channel": 30, "bingham_smago": 30,
     "couette_dyn": 30, "slip_box": 30, "slip_dyn": 30,
-    "cfg3_mini": 40, "sphere_kin": 40, "two_spheres_kin": 40, "cluster_dem": 40,
+    "sphere_fixed": 40, "cfg3_mini": 40, "sphere_kin": 40, "two_spheres_kin": 40, "cluster_dem": 40,
     "cfg4_mini": 100, "dam_newtonian": 100, "droplet": 100, "bubble_periodic": 100,
     "cfg1_mini": 100, "cfg5_mini": 100,
     "drum_mini": 300, "drum_bingham": 200,
@@ -72,7 +72,7 @@ def generate(name, workdir="/tmp/hb_golden"):
     st0 = lbo.read_state(out + "_state%06d.bin" % 0)
     N = int(np.prod(hdr["size"]))
     d = dict(
-        meta=json.dumps(dict(params=hdr, steps=steps, check_steps=cs, case=name)),
+        meta=json.dumps(dict(params=hdr, steps=steps, check_steps=cs, case=name, dem_solve=int(case.get("demSolve", 1)))),
         init_type_flags=st0["type_flags"], init_solidIndex=st0["solidIndex"], init_n=st0["n"], init_u=st0["u"],
         init_mass=st0["mass"], init_visc=st0["visc"],
         trace=np.fromfile(out + "_parts.bin", dtype=np.uint8),

@@ -34,6 +34,7 @@ class Golden:
         self.params = meta["params"]
         self.steps = int(meta["steps"])
         self.check_steps = [int(s) for s in meta["check_steps"]]
+        self.dem_solve = bool(meta.get("dem_solve", 1))  # goCycle runs the coupling step only with demSolve (hybird.cpp:53,61)
         self.N = int(np.prod(self.params["size"]))
         self.types = z["types"]
         with tempfile.NamedTemporaryFile(suffix=".bin", delete=False) as fh:
@@ -76,10 +77,12 @@ def state_hashes(state):
     return out
 
 
-def replay(g: Golden, engine, get_state, dem_solve=True, on_step=None):
+def replay(g: Golden, engine, get_state, dem_solve=None, on_step=None):
     """Drive `engine` (oracle or GPU LB mirror) with the reference's recorded inputs.
     Yields (step, F, M, V, wallF)."""
     prm = g.params
+    if dem_solve is None:
+        dem_solve = g.dem_solve
     for s in range(1, g.steps + 1):
         parts, elmts, comps, flag = g.trace[s - 1]
         if prm["freeSurface"]:
