@@ -126,36 +126,51 @@ def workload_case(name, n_slabs=1):
 # ---------------------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation (unmodified, oracle/_ref/ref_harness)
 # ---------------------------------------------------------------------------------------------
-def reference_sample_case(name):
-    """Bounded sample of the workload for the CPU runs: same physics and boundaries, the periodic
-    channel cropped in y (the flow is invariant along x and y) so a step takes ~1 s of CPU."""
+def reference_sample_case(name, full=False):
+    """The workload for the CPU runs.  full: the lattice of the GPU arm itself (the reference arm); else a bounded sample
+    -- same physics and boundaries, the periodic channel cropped in y (the flow is invariant along y) so that a step
+    takes ~0.1 s on 16 threads and the 1-thread run of BASELINE.md section 4 stays within seconds."""
     case = workload_case(name)
-    if name == "cfg2":
+    if name == "cfg2" and not full:
         case["lbSizeY"] = 34
         sample = "cfg2 channel cropped to 256x34x256 (2.2 M cells, same physics/boundaries)"
     else:
-        sample = name + " at full size"
+        sample = "%s at full size (%sx%sx%s)" % (name, case["lbSizeX"], case["lbSizeY"], case["lbSizeZ"])
     case["name"] = name + "_cpu_sample"
     return case, sample
 
 
-def run_reference(name, steps, warmup, threads=None):
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(name, steps, warmup, threads=None, full=False):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cases
     threads = threads or (os.cpu_count() or 1)
-    case, sample = reference_sample_case(name)
+    case, sample = reference_sample_case(name, full)
     kind = "reference"
+    phases = None
     with tempfile.TemporaryDirectory() as wd:
         if os.path.exists(cases.REF_HARNESS):
             _, so = cases.run_reference(case, wd, steps, time_mode=True, warmup=warmup, threads=threads)
             rec = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
             mlups, ms, act = rec["mlups_active"], rec["ms_per_step"], rec["active_mean"]
             threads = rec["threads"]
+            tot = sum(rec["phase_ms"].values()) or 1.0
+            phases = {k: round(100.0 * v / tot, 1) for k, v in rec["phase_ms"].items()}  # per cent of the step
         else:  # the C restatement (port) when the compiled reference did not travel
             kind = "port"
             mlups, ms, act = run_port(case, steps, warmup, threads)
     return dict(value=mlups, unit="MLUPS", cores=int(threads), kind=kind, sample=sample + ", %d steps after %d warm-up" % (steps, warmup),
-                ms_per_step=ms, active_cells=act)
+                ms_per_step=ms, active_cells=act, phase_pct=phases, cpu=cpu_model(), host_cores=os.cpu_count(),
+                lattice=[int(round(float(case["lbSize" + a]))) for a in "XYZ"])
 
 
 def run_port(case, steps, warmup, threads):
@@ -183,15 +198,19 @@ def run_port(case, steps, warmup, threads):
 def main_reference(args, rank, world):
     if rank != 0:
         return 0
-    # a bounded sample: ~0.12 s per step on 16 threads -> at most ~12 s of CPU work
-    steps = max(1, min(args.steps, 100))
-    warmup = max(1, min(args.warmup, 3))
-    r = run_reference(args.workload, steps, warmup)
+    # the GPU arm's own lattice (same config): cfg2 at 256^3 takes ~1-3 s per step on the box's host cores plus ~15 s
+    # of the reference's serial initialisation, so the step count is bounded to keep the run within a few minutes
+    full = not args.ref_crop
+    steps = max(1, min(args.steps, 20 if full else 100))
+    warmup = max(1, min(args.warmup, 2 if full else 3))
+    r = run_reference(args.workload, steps, warmup, full=full)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_label(args.workload, args.gpus), "sample": r["sample"]},
-            "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "cpu_baseline": {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                             "cpu": r["cpu"], "host_cores": r["host_cores"], "lattice": r["lattice"],
+                             "active_cells": r["active_cells"], "phase_pct": r["phase_pct"]},
             "e2e": {"value": r["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -201,6 +220,83 @@ def main_reference(args, rank, world):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def resident_run(name, args, rank, world, local_rank, dist, K, W, with_clocks):
+    """Device-resident throughput of one workload: W warm-up steps, then exactly K steps back to back (lbGpuRun; the
+    free-surface update, particle-flag update, LB step and force reduction of every cycle), CUDA events on the engine's
+    stream, barrier + synchronize on both sides, maximum over the ranks.  Returns (engine, info, result dict)."""
+    import torch
+    from hybird_b200 import slabs
+    case = workload_case(name, world)
+    t_init = time.time()
+    lb, info = slabs.build_engine(case, rank, world, device=local_rank, dist=dist if world > 1 else None,
+                                  device_init=not args.host_init)
+    t_init = time.time() - t_init
+
+    def barrier():
+        lb.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    parts, elmts, comps = info["parts"], info["elmts"], info["comps"]
+    fs = bool(info["params"]["freeSurface"])
+    if len(parts):
+        # particle state becomes resident with the first coupling step (rescan, as dem.newNeighborList does)
+        if fs:
+            lb.latticeBoltzmannFreeSurfaceStep()
+        lb.latticeBoltzmannCouplingStep(True, elmts, parts, comps)
+        lb.latticeBolzmannStep(elmts, parts)
+    lb.run(W)
+    barrier()
+    sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = lb.launch_count()
+    barrier()
+    t0w = time.time()
+    lb.run(K)
+    lb.synchronize()
+    ms_dev = lb.last_step_ms()             # CUDA events on the engine's stream around the K steps
+    kern_ms, kern_n = lb.last_kernel_ms()  # CUDA events around each step-kernel group (last <=512 of the K)
+    kern_ms = kern_ms / max(kern_n, 1)
+    t1w = time.time()
+    launches = lb.launch_count() - l0
+    barrier()
+    clocks = {}
+    if sampler:
+        time.sleep(0.2)
+        sampler.stop()
+        clocks = sampler.summary(t0w, t1w)
+    if world > 1:
+        t = torch.tensor([ms_dev, kern_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, kern_ms = float(t[0]), float(t[1])
+    peak, peak_src = load_peaks()
+    active_total, active_local = info["active_total"], info["active_local"]
+    achieved = BYTES_PER_UPDATE * active_local / (kern_ms * 1e-3) / 1e9
+    size = info["params"]["size"]
+    res = dict(value=active_total * K / (ms_dev * 1e-3) / 1e6, ms_per_step=ms_dev / K, launches=int(launches), clocks=clocks,
+               init_s=round(t_init, 2), barrier=barrier,
+               lattice=[int(size[0]), int(size[1]), int(info["global_z"])], active_cells=int(active_total),
+               roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "kernel": info["kernel"], "bytes_per_update": BYTES_PER_UPDATE,
+                         "updates_per_launch": int(active_local), "kernel_ms": kern_ms,
+                         "whole_step_frac": BYTES_PER_UPDATE * active_local / (ms_dev / K * 1e-3) / 1e9 / peak})
+    return lb, info, res
+
+
+def traffic_of(name):
+    """DRAM bytes per step-kernel launch from the committed ncu capture (profiles/traffic.json): a citation of that
+    capture, not a measurement of this run."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        rec = json.load(open(tp)).get(name, {})
+        return rec.get("dram_bytes_per_launch"), "profiles/traffic.json (%s)" % rec.get("source", "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum")
+    except Exception:
+        return None, None
+
+
 def main_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -214,58 +310,15 @@ def main_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        slabs.init_comm(rank, world, local_rank, dist)  # the engine's own NCCL communicator (halo send/recv, sums)
-
-    case = workload_case(args.workload, world)
-    t_init = time.time()
-    lb, info = slabs.build_engine(case, rank, world, device=local_rank, dist=dist if world > 1 else None,
-                                  device_init=(world == 1 and not args.host_init))
-    active_local = info["active_local"]
-    active_total = info["active_total"]
-    t_init = time.time() - t_init
-
-    def barrier():
-        lb.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        slabs.init_comm(rank, world, local_rank, dist)  # the engine's own NCCL communicator (set-up, sums, in-cycle planes)
 
     K, W = args.steps, max(args.warmup, 3)
+    lb, info, res = resident_run(args.workload, args, rank, world, local_rank, dist, K, W, True)
+    barrier = res.pop("barrier")
+    active_total = info["active_total"]
     parts, elmts, comps = info["parts"], info["elmts"], info["comps"]
     fs = bool(info["params"]["freeSurface"])
-    if len(parts):
-        # particle state becomes resident with the first coupling step (rescan, as dem.newNeighborList does)
-        if fs:
-            lb.latticeBoltzmannFreeSurfaceStep()
-        lb.latticeBoltzmannCouplingStep(True, elmts, parts, comps)
-        lb.latticeBolzmannStep(elmts, parts)
-    # ---- device-resident throughput: W warm-up steps, then exactly K steps (free-surface update, particle-flag
-    # update, LB step and force reduction every step; particles resident and fixed) ----
-    lb.run(W)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    l0 = lb.launch_count()
-    barrier()
-    t0w = time.time()
-    lb.run(K)
-    lb.synchronize()
-    ms_dev = lb.last_step_ms()          # CUDA events on the engine's stream around the K steps
-    kern_ms, kern_n = lb.last_kernel_ms()  # CUDA events around each fused k_step launch (last <=512 of the K)
-    kern_ms = kern_ms / max(kern_n, 1)
-    t1w = time.time()
-    launches = lb.launch_count() - l0
-    barrier()
-    if sampler:
-        time.sleep(0.2)
-        sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms_dev, kern_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, kern_ms = float(t[0]), float(t[1])
-    mlups = active_total * K / (ms_dev * 1e-3) / 1e6
+    case = workload_case(args.workload, world)
 
     # ---- end to end through the C ABI with host buffers: lbGpuStep + lbGpuParticleForces per step ----
     Ke = min(K, 200)
@@ -294,9 +347,11 @@ def main_ours(args, rank, world, local_rank):
     e2e_mlups = active_total * Ke / te / 1e6
 
     # ---- the whole job through the C ABI with host buffers: lbGpuInit from the caller's host arrays (what the drop-in
-    # shim does after the reference's host initialisation), K steps as above, one lbGpuFetchFields into host arrays
-    # (what an export step of the reference's IO reads).  One process: a second engine, one contiguous timed region;
-    # several processes: this rank's measured upload + steps + fetch, maximum over the ranks. ----
+    # shim does after the reference's host initialisation), K steps as above, one lbGpuFetchFields into the caller's
+    # host arrays (what an export step of the reference's IO reads; the caller's mirrors exist before the job, as the
+    # shim's do).  One process: a second engine, one contiguous timed region ("measured").  Several processes: this
+    # rank's own slab uploaded from host arrays + steps + fetch, composed from separately timed legs, maximum over the
+    # ranks ("composed"). ----
     FIELDS = ("type_flags", "n", "u", "mass")
     if world == 1:
         Kj = min(K, 1000)
@@ -304,9 +359,11 @@ def main_ours(args, rank, world, local_rank):
         upload_bytes = int(sum(a.nbytes for a in (st_host.type_flags, st_host.solidIndex, st_host.n, st_host.u, st_host.mass, st_host.visc)))
         xj = parts["x0"].copy() if len(parts) else None
         pj = parts.copy()
+        mirrors = LB.host_mirrors(st_host.type_flags.size, FIELDS)  # the caller's (touched) output arrays: not timed
         tj = time.perf_counter()
         lbj = LB(st_host.params, device=local_rank)
         lbj.latticeBolzmannInit(st_host.type_flags, st_host.solidIndex, st_host.n, st_host.u, st_host.mass, st_host.visc)
+        t_up = time.perf_counter() - tj
         for k in range(Kj):
             if fs:
                 lbj.latticeBoltzmannFreeSurfaceStep()
@@ -314,87 +371,119 @@ def main_ours(args, rank, world, local_rank):
                 li.advance_kinematic(pj, elmts, xj, 1.0)
                 lbj.latticeBoltzmannCouplingStep(k == 0, elmts, pj, comps)
             lbj.latticeBolzmannStep(elmts, pj)
-        fields = lbj.fetch(FIELDS)
+        tf = time.perf_counter()
+        fields = lbj.fetch(FIELDS, out=mirrors)
         job_s = time.perf_counter() - tj
+        fetch_ms = 1e3 * (time.perf_counter() - tf)
+        init_ms = 1e3 * t_up
         fetch_bytes = int(sum(v.nbytes for v in fields.values()))
-        del fields
+        del fields, mirrors
         lbj.close()
         del st_host
-        tf = time.perf_counter()
-        fields = lb.fetch(FIELDS)
-        fetch_ms = 1e3 * (time.perf_counter() - tf)
-        del fields
-        init_ms = 1e3 * info["upload_s"]
+        e2e_kind = "measured"
     else:
         Kj = K
+        st_host, _ = slabs.build_slab_state(case, rank, world, parts if len(parts) else None, dist)  # not timed
+        upload_bytes = int(sum(a.nbytes for a in (st_host.type_flags, st_host.solidIndex, st_host.n, st_host.u, st_host.mass, st_host.visc)))
+        mirrors = LB.host_mirrors(lb.N, FIELDS)
         tf = time.perf_counter()
-        fields = lb.fetch(FIELDS)
+        fields = lb.fetch(FIELDS, out=mirrors)
         fetch_ms = 1e3 * (time.perf_counter() - tf)
         fetch_bytes = int(sum(v.nbytes for v in fields.values()))
-        del fields
-        upload_bytes = info["upload_bytes"]
-        init_ms = 1e3 * info["upload_s"]
-        t = torch.tensor([info["upload_s"] + K * te / Ke + 1e-3 * fetch_ms], dtype=torch.float64, device="cuda")
+        del fields, mirrors
+        barrier()
+        lb.close()
+        tj = time.perf_counter()
+        lbj = LB(st_host.params, device=local_rank)
+        lbj.latticeBolzmannInit(st_host.type_flags, st_host.solidIndex, st_host.n, st_host.u, st_host.mass, st_host.visc)
+        lbj.synchronize()
+        init_ms = 1e3 * (time.perf_counter() - tj)
+        lb = lbj
+        del st_host
+        t = torch.tensor([1e-3 * init_ms + K * te / Ke + 1e-3 * fetch_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         job_s = float(t[0])
+        e2e_kind = "composed"
     job_mlups = active_total * Kj / job_s / 1e6
+    if world > 1:
+        dist.barrier()
+    lb.close()
+
+    # ---- the other configurations, device-resident, so that they are measured by the same driver run ----
+    extra = {}
+    if args.workload == "cfg2" and not args.no_extra:
+        for nm in (("cfg3", "cfg4", "cfg5") if world == 1 else ("cfg5",)):
+            try:
+                Kx = min(K, 100)
+                lbx, infx, rx = resident_run(nm, args, rank, world, local_rank, dist, Kx, W, False)
+                rx.pop("barrier")
+                rx.pop("clocks")
+                rx["steps"] = Kx
+                rx["scaling"] = "strong"
+                rx["launches_per_step"] = round(rx.pop("launches") / Kx, 1)
+                rx["workload"] = workload_label(nm, world)
+                rx["roofline"]["traffic"], rx["roofline"]["traffic_source"] = traffic_of(nm)
+                rx["peer_halo"] = lbx.peer_halo() if world > 1 else None
+                if world > 1:
+                    dist.barrier()
+                lbx.close()
+                extra[nm] = rx
+            except Exception as e:  # noqa: BLE001
+                extra[nm] = {"error": str(e)[:300]}
+                break  # the ranks may no longer be in step
 
     if rank != 0:
         if world > 1:
+            slabs.finalize_comm()
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = load_peaks()
-    kern_avg_ms = kern_ms
-    achieved = BYTES_PER_UPDATE * active_local / (kern_avg_ms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    clocks = sampler.summary(t0w, t1w) if sampler else {}
+    roof = res["roofline"]
+    roof["traffic"], roof["traffic_source"] = traffic_of(args.workload)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = run_reference(args.workload, 60, 3)  # ~8 s of CPU work on 16 threads
-            cpu = {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+            r = run_reference(args.workload, 60, 3)    # ~8 s of CPU work on 16 threads
+            r1 = run_reference(args.workload, 4, 1, threads=1)  # the same at one thread
+            cpu = {"value": r["value"], "unit": "MLUPS", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
+                   "cpu": r["cpu"], "host_cores": r["host_cores"], "lattice": r["lattice"], "active_cells": r["active_cells"],
+                   "phase_pct": r["phase_pct"], "value_1_thread": r1["value"], "phase_pct_1_thread": r1["phase_pct"]}
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": "MLUPS", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(e)[:200]}
-    size = info["params"]["size"]
     line = {
-        "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak" if args.workload == "cfg2" else "strong",
+        "metric": METRIC, "value": res["value"], "unit": "MLUPS", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak" if args.workload == "cfg2" else "strong",
         "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_label(args.workload, world),
-                   "lattice": [int(size[0]), int(size[1]), int(info["global_z"])], "active_cells": int(active_total),
+                   "lattice": res["lattice"], "active_cells": res["active_cells"],
                    "parallelism": info["parallelism"],
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (info["bytes_resident"] / 1e9),
-                   "init_s": round(t_init, 2), "init": info["init"]},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": info["kernel"],
-                     "bytes_per_update": BYTES_PER_UPDATE, "updates_per_launch": int(active_local),
-                     "kernel_ms": kern_avg_ms},
+                   "init_s": res["init_s"], "init": info["init"]},
+        "roofline": roof,
         # value: the whole job through the C ABI with host buffers -- state upload, every step's particle arrays in and
         # forces out, one field fetch; step_value: the per-step calls alone (what the reference arm's per-step time is
         # the counterpart of; a pure-fluid step has no host input)
-        "e2e": {"value": job_mlups, "unit": "MLUPS",
+        "e2e": {"value": job_mlups, "unit": "MLUPS", "kind": e2e_kind,
                 "h2d_bytes_per_step": int(h2d + upload_bytes / Kj), "d2h_bytes_per_step": int(d2h + fetch_bytes / Kj),
                 "steps": Kj,
                 "call": "lbGpuInit(host arrays) + %d x [lbGpuStep(host particle/element arrays) + lbGpuParticleForces(host)] + "
                         "lbGpuFetchFields(host arrays)" % Kj,
                 "step_value": e2e_mlups, "step_h2d_bytes": h2d, "step_d2h_bytes": d2h, "step_steps": Ke,
                 "init_upload_bytes": upload_bytes, "fetch_fields_bytes": fetch_bytes,
-                "init_ms_this_engine": init_ms, "fetch_fields_ms": fetch_ms},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+                "init_ms": init_ms, "fetch_fields_ms": fetch_ms},
+        "gpu_launches": res["launches"],
+        "clocks": res["clocks"],
     }
+    if world > 1:
+        line["config"]["halo"] = info.get("halo")
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if extra:
+        line["extra"] = extra
     emit(line)
     if world > 1:
+        slabs.finalize_comm()
         dist.destroy_process_group()
     return 0
 
@@ -407,6 +496,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the device-resident lines of the other configurations (extra block)")
+    ap.add_argument("--ref-crop", action="store_true", help="reference arm on the cropped 256x34x256 sample instead of the GPU arm's lattice")
     ap.add_argument("--host-init", action="store_true", help="build the initial state on the host and upload it (lbGpuInit) "
                     "instead of initialising the lattice on the device (lbGpuInitBox; one process only)")
     args = ap.parse_args()

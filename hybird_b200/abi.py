@@ -32,9 +32,9 @@ class LbGpuParams(C.Structure):
 
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuInitBox", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
-           "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuSynchronize", "lbGpuLastStepMs",
+           "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuCountsLocal", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
-           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize")
+           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo")
 
 _lib = None
 
@@ -86,6 +86,8 @@ def load_library(build_if_missing=True):
     L.lbGpuLoadState.argtypes = [vp, vp, C.c_uint64]
     L.lbGpuCounts.restype = C.c_int
     L.lbGpuCounts.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
+    L.lbGpuCountsLocal.restype = C.c_int
+    L.lbGpuCountsLocal.argtypes = [vp, C.POINTER(C.c_uint64 * 4)]
     L.lbGpuSynchronize.restype = C.c_int
     L.lbGpuSynchronize.argtypes = [vp]
     L.lbGpuLastStepMs.restype = C.c_int
@@ -102,6 +104,8 @@ def load_library(build_if_missing=True):
     L.lbGpuCommInit.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.lbGpuCommInfo.restype = C.c_int
     L.lbGpuCommInfo.argtypes = [C.POINTER(C.c_int32)] * 3
+    L.lbGpuPeerHalo.restype = C.c_int
+    L.lbGpuPeerHalo.argtypes = [vp, C.POINTER(C.c_int32)]
     L.lbGpuCommFinalize.restype = C.c_int
     L.lbGpuCommFinalize.argtypes = []
     L.lbGpuFinalize.restype = C.c_int

@@ -20,7 +20,9 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -52,6 +54,47 @@ int fail(int code, const char* fmt, ...) {
         int r_ = (call);                                                                                 \
         if (r_ != lbcomm::ncclSuccess) return fail(LBGPU_ECOMM, "%s failed: %s (%s:%d)", #call, lbcomm::api().GetErrorString(r_), __FILE__, __LINE__); \
     } while (0)
+
+// LBGPU_TRACE=1: wall-clock marks of the bulk-transfer entry points on stderr (lbGpuInit, lbGpuFetchFields)
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    const char* what;
+    explicit Trace(const char* w) : on(getenv("LBGPU_TRACE") != nullptr), what(w) { t0 = last = std::chrono::steady_clock::now(); }
+    void mark(const char* label) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[lbgpu trace] %s: %-28s %8.2f ms (total %8.2f)\n", what, label,
+                std::chrono::duration<double, std::milli>(now - last).count(), std::chrono::duration<double, std::milli>(now - t0).count());
+        last = now;
+    }
+};
+
+// memcpy between pageable host memory and a pinned stage on several threads: one core moves 5-8 GB/s (less when the
+// pages of a freshly allocated destination are touched for the first time), PCIe 5 x16 about 50 GB/s
+int copy_threads() {
+    static int n = 0;
+    if (n == 0) {
+        if (const char* e = getenv("LBGPU_COPY_THREADS")) n = atoi(e);
+        if (n <= 0) { const unsigned hc = std::thread::hardware_concurrency(); n = hc >= 16 ? 8 : (hc >= 8 ? 4 : (hc >= 4 ? 2 : 1)); }
+        if (n > 16) n = 16;
+    }
+    return n;
+}
+void par_memcpy(void* dst, const void* src, size_t bytes) {
+    const int T = copy_threads();
+    if (T <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes + T - 1) / T + 4095) / 4096 * 4096;
+    std::vector<std::thread> th;
+    for (int k = 1; k < T; ++k) {
+        const size_t off = (size_t)k * per;
+        if (off >= bytes) break;
+        const size_t len = bytes - off < per ? bytes - off : per;
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+    }
+    memcpy(dst, src, per < bytes ? per : bytes);
+    for (auto& t : th) t.join();
+}
 
 lb::FastDiv make_div(uint32_t d) {
     lb::FastDiv f;
@@ -126,6 +169,91 @@ struct Slab {
     uint8_t* tbuf(int k) { return k == 0 ? type0.p : type1.p; }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Peer halo: the per-step halo between ranks without NCCL.  Every rank exports the arrays of its two edge slabs
+// (cudaIpcGetMemHandle), maps the ones of its neighbour ranks (NVLink / NVSwitch peers) and, once the face planes of a
+// step are updated, a put kernel on the high-priority comm stream stores them straight into the neighbours' ghost
+// planes, then raises a sequence flag in the neighbour's memory; the neighbour's stream waits on its own flag word
+// before the next kernel that reads the ghosts.  One launch per step instead of a grouped send/recv per plane, no
+// proxy thread, no rendezvous: the sender knows the destination is free because it has itself received the
+// neighbour's flag of the previous step, which the neighbour raises after its last read of that ghost plane.
+// ---------------------------------------------------------------------------------------------
+enum PeerBuf { PB_FA, PB_FB, PB_N, PB_UX, PB_UY, PB_UZ, PB_VISC, PB_HFX, PB_HFY, PB_HFZ, PB_FLAGS, PB_COUNT };
+struct PeerExport {  // what a rank tells the others about one of its edge slabs (side 0: first slab, 1: last slab)
+    cudaIpcMemHandle_t handle[PB_COUNT];
+    unsigned long long offset[PB_COUNT];
+    uint32_t valid[PB_COUNT];
+    unsigned long long stride, pad;
+    uint32_t Z, XY;
+};
+constexpr int PUT_MAX = 64;
+struct PutPlan {  // one launch of k_put_halo: plane copies into peer memory + the flags to raise afterwards
+    int n;
+    const char* src[PUT_MAX];
+    char* dst[PUT_MAX];
+    uint32_t bytes[PUT_MAX];
+    uint32_t* flagDst[2];
+    uint32_t* counter;
+    uint32_t chunk;
+};
+struct PeerHalo {
+    bool on = false;
+    std::string note;                    // why it is off
+    char* nb[2][PB_COUNT] = {};          // [0] neighbour below (its LAST slab), [1] neighbour above (its FIRST slab)
+    PeerExport nbInfo[2];
+    std::vector<std::pair<cudaIpcMemHandle_t, void*>> opened;
+    DevBuf<uint32_t> flags;              // [0] raised by the rank below, [1] by the rank above, [8] block counter of the put kernel
+    uint32_t seq = 0;
+    PutPlan plan[2];
+    uint32_t planWhat[2] = { 0, 0 };
+};
+
+__global__ void __launch_bounds__(128) k_put_halo(const __grid_constant__ PutPlan pl, uint32_t seq) {
+    const int e = blockIdx.y;
+    const size_t begin = (size_t)blockIdx.x * pl.chunk;
+    const uint32_t bytes = pl.bytes[e];
+    if (begin < bytes) {
+        const size_t len = bytes - begin < pl.chunk ? bytes - begin : pl.chunk;
+        const char* s = pl.src[e] + begin;
+        char* d = pl.dst[e] + begin;
+        if ((((uintptr_t)s | (uintptr_t)d | len) & 15) == 0) {
+            const uint4* s4 = (const uint4*)s; uint4* d4 = (uint4*)d;
+            for (size_t k = threadIdx.x; k < len / 16; k += blockDim.x) d4[k] = s4[k];
+        } else if ((((uintptr_t)s | (uintptr_t)d | len) & 7) == 0) {
+            const unsigned long long* s8 = (const unsigned long long*)s; unsigned long long* d8 = (unsigned long long*)d;
+            for (size_t k = threadIdx.x; k < len / 8; k += blockDim.x) d8[k] = s8[k];
+        } else {
+            for (size_t k = threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+        }
+    }
+    // every block's stores are ordered before its count; the last block to count raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        if (atomicAdd(pl.counter, 1u) == total - 1) {
+            *pl.counter = 0;
+            __threadfence_system();
+            for (int k = 0; k < 2; ++k)
+                if (pl.flagDst[k]) *(volatile uint32_t*)pl.flagDst[k] = seq;
+        }
+    }
+}
+
+// the stream stalls until the neighbours' flags reach `seq` (their planes of this step have landed in our ghosts)
+__global__ void k_wait_halo(volatile uint32_t* flags, uint32_t seq, int needDown, int needUp, uint32_t* status) {
+    const int k = threadIdx.x;
+    if (k > 1 || !(k == 0 ? needDown : needUp)) return;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int)(flags[k] - seq) < 0) {
+        __nanosleep(200);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 20000000000ull) { atomicExch(&status[3], 1u + (uint32_t)k); return; }  // 20 s: the neighbour is gone
+    }
+    __threadfence_system();
+}
+
 }  // namespace
 
 struct LbGpuHandle {
@@ -135,6 +263,7 @@ struct LbGpuHandle {
     cudaEvent_t evA = nullptr, evB = nullptr;
     cudaStream_t commStream = nullptr;  // halo transport to other processes, overlapped with the interior update
     cudaEvent_t evFaces = nullptr, evHalo = nullptr;
+    PeerHalo peer;                      // neighbour ranks' arrays mapped into this process (see "peer halo")
     std::vector<std::unique_ptr<Slab>> slabs;
     int nSlabsGlobal = 1, firstSlab = 0;
     DevBuf<lb::RawParticle> rawParts;
@@ -148,7 +277,7 @@ struct LbGpuHandle {
     // one chunk overlaps the DMA of the other; a plain cudaMemcpy from pageable memory serialises the two)
     char* stage[2] = { nullptr, nullptr };
     cudaEvent_t stageEv[2] = { nullptr, nullptr };
-    static constexpr size_t STAGE = 32u << 20;
+    static constexpr size_t STAGE = 64u << 20;
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
@@ -262,7 +391,7 @@ int h2d_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
         const size_t len = bytes - off < LbGpuHandle::STAGE ? bytes - off : LbGpuHandle::STAGE;
         const int b = k & 1;
         if (k >= 2) CU(cudaEventSynchronize(h->stageEv[b]));
-        memcpy(h->stage[b], (const char*)src + off, len);
+        par_memcpy(h->stage[b], (const char*)src + off, len);
         CU(cudaMemcpyAsync((char*)dst + off, h->stage[b], len, cudaMemcpyHostToDevice, h->stream));
         CU(cudaEventRecord(h->stageEv[b], h->stream));
     }
@@ -285,7 +414,7 @@ int d2h_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
         const int b = k & 1;
         if (k >= 2) {  // the chunk that used this stage two rounds ago has landed: hand it to the caller
             CU(cudaEventSynchronize(h->stageEv[b]));
-            memcpy((char*)dst + done, h->stage[b], LbGpuHandle::STAGE);
+            par_memcpy((char*)dst + done, h->stage[b], LbGpuHandle::STAGE);
             done += LbGpuHandle::STAGE;
         }
         CU(cudaMemcpyAsync(h->stage[b], (const char*)src + off, len, cudaMemcpyDeviceToHost, h->stream));
@@ -295,7 +424,7 @@ int d2h_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
         const int b = r & 1;
         const size_t len = bytes - done < LbGpuHandle::STAGE ? bytes - done : LbGpuHandle::STAGE;
         CU(cudaEventSynchronize(h->stageEv[b]));
-        memcpy((char*)dst + done, h->stage[b], len);
+        par_memcpy((char*)dst + done, h->stage[b], len);
         done += len;
     }
     return 0;
@@ -420,6 +549,169 @@ int exchange_remote(LbGpuHandle* h, uint32_t what, cudaStream_t st) {
     for (const Xfer& x : rDn) NC(A.Recv(x.ptr, x.bytes, lbcomm::ncclUint8, down, c.comm, st));
     for (const Xfer& x : rUp) NC(A.Recv(x.ptr, x.bytes, lbcomm::ncclUint8, up, c.comm, st));
     NC(A.GroupEnd());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Peer halo set-up (collective over the communicator): export the edge slabs' arrays, gather every rank's records,
+// map the neighbours'.  Any failure on any rank (no peer access, IPC refused) switches every rank back to NCCL
+// send/recv for the step halo.  LBGPU_PEER_HALO=0 does the same (A/B).
+// ---------------------------------------------------------------------------------------------
+void* peer_buf_ptr(Slab* s, int b, LbGpuHandle* h) {
+    switch (b) {
+        case PB_FA: return s->fA.p; case PB_FB: return s->fB.p; case PB_N: return s->n.p;
+        case PB_UX: return s->ux.p; case PB_UY: return s->uy.p; case PB_UZ: return s->uz.p;
+        case PB_VISC: return s->visc.p; case PB_HFX: return s->hfx.p; case PB_HFY: return s->hfy.p; case PB_HFZ: return s->hfz.p;
+        case PB_FLAGS: return h->peer.flags.p;
+    }
+    return nullptr;
+}
+
+int peer_setup(LbGpuHandle* h) {
+    PeerHalo& P = h->peer;
+    P.on = false;
+    if (!lbcomm::active()) return 0;
+    const lbcomm::Comm& c = lbcomm::comm();
+    lbcomm::Api& A = lbcomm::api();
+    cudaStream_t st = h->stream;
+    int down, up;
+    neighbour_ranks(h, &down, &up);
+    CU(P.flags.alloc(64));
+    CU(cudaMemsetAsync(P.flags.p, 0, 64 * sizeof(uint32_t), st));
+    std::string why;
+    if (const char* e = getenv("LBGPU_PEER_HALO")) { if (atoi(e) == 0) why = "LBGPU_PEER_HALO=0"; }
+    if (!A.AllGather) why = "ncclAllGather missing";
+    // export
+    PeerExport mine[2];
+    memset(mine, 0, sizeof mine);
+    for (int side = 0; side < 2 && why.empty(); ++side) {
+        Slab* s = side == 0 ? h->slabs.front().get() : h->slabs.back().get();
+        mine[side].stride = s->stride; mine[side].pad = s->pad; mine[side].Z = (uint32_t)s->dev.Z; mine[side].XY = s->XY;
+        for (int b = 0; b < PB_COUNT; ++b) {
+            void* ptr = peer_buf_ptr(s, b, h);
+            if (!ptr) continue;
+            void* base = nullptr; size_t size = 0;
+            if (lbcomm::address_range(ptr, &base, &size) != 0) { why = "cuMemGetAddressRange unavailable"; break; }
+            if (cudaIpcGetMemHandle(&mine[side].handle[b], base) != cudaSuccess) { cudaGetLastError(); why = "cudaIpcGetMemHandle refused"; break; }
+            mine[side].offset[b] = (unsigned long long)((char*)ptr - (char*)base);
+            mine[side].valid[b] = 1;
+        }
+    }
+    // gather the records of all ranks (a rank that could not export sends invalid records)
+    if (!why.empty()) memset(mine, 0, sizeof mine);
+    DevBuf<char> dsend, dall;
+    CU(dsend.alloc(sizeof mine)); CU(dall.alloc(sizeof mine * (size_t)c.world));
+    CU(cudaMemcpyAsync(dsend.p, mine, sizeof mine, cudaMemcpyHostToDevice, st));
+    std::vector<PeerExport> all((size_t)2 * c.world);
+    if (A.AllGather) {
+        NC(A.AllGather(dsend.p, dall.p, sizeof mine, lbcomm::ncclUint8, c.comm, st));
+        CU(cudaMemcpyAsync(all.data(), dall.p, sizeof mine * (size_t)c.world, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    // map the neighbours' arrays
+    auto open = [&](const cudaIpcMemHandle_t& hd, void** out) -> bool {
+        for (auto& o : P.opened) if (memcmp(&o.first, &hd, sizeof hd) == 0) { *out = o.second; return true; }
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return false; }
+        P.opened.push_back({ hd, base });
+        *out = base;
+        return true;
+    };
+    for (int dir = 0; dir < 2 && why.empty(); ++dir) {
+        const int nb = dir == 0 ? down : up;
+        if (nb < 0) continue;
+        const PeerExport& r = all[(size_t)2 * nb + (dir == 0 ? 1 : 0)];  // below us: its last slab; above us: its first slab
+        P.nbInfo[dir] = r;
+        Slab* s = dir == 0 ? h->slabs.front().get() : h->slabs.back().get();
+        if (!r.valid[PB_FA] || !r.valid[PB_FLAGS]) { why = "rank " + std::to_string(nb) + " exported nothing"; break; }
+        if (r.XY != s->XY) { why = "neighbour slab has another cross-section"; break; }
+        for (int b = 0; b < PB_COUNT; ++b) {
+            P.nb[dir][b] = nullptr;
+            if (!r.valid[b]) continue;
+            void* base = nullptr;
+            if (!open(r.handle[b], &base)) { why = "cudaIpcOpenMemHandle refused (no peer access to rank " + std::to_string(nb) + "?)"; break; }
+            P.nb[dir][b] = (char*)base + r.offset[b];
+        }
+    }
+    // all or nothing across the ranks
+    DevBuf<uint32_t> bad;
+    CU(bad.alloc(1));
+    const uint32_t mineBad = why.empty() ? 0u : 1u;
+    CU(cudaMemcpyAsync(bad.p, &mineBad, sizeof mineBad, cudaMemcpyHostToDevice, st));
+    NC(A.AllReduce(bad.p, bad.p, 1, lbcomm::ncclUint32, lbcomm::ncclSum, c.comm, st));
+    uint32_t anyBad = 0;
+    CU(cudaMemcpyAsync(&anyBad, bad.p, sizeof anyBad, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (anyBad) {
+        P.note = why.empty() ? "another rank could not map its neighbours" : why;
+        if (getenv("LBGPU_VERBOSE")) fprintf(stderr, "[lbgpu rank %d] peer halo off: %s (NCCL send/recv carries the step halo)\n", c.rank, P.note.c_str());
+        return 0;
+    }
+    P.on = true;
+    P.seq = 0;
+    P.planWhat[0] = P.planWhat[1] = 0;
+    if (getenv("LBGPU_VERBOSE")) fprintf(stderr, "[lbgpu rank %d] peer halo on (neighbours %d / %d mapped)\n", c.rank, down, up);
+    return 0;
+}
+
+void peer_teardown(LbGpuHandle* h) {
+    for (auto& o : h->peer.opened) cudaIpcCloseMemHandle(o.second);
+    h->peer.opened.clear();
+    h->peer.on = false;
+}
+
+// the plane copies of one step halo: fields `what`, destination population buffer `buf` (0 = A)
+void build_put_plan(LbGpuHandle* h, uint32_t what, int buf, PutPlan& pl) {
+    PeerHalo& P = h->peer;
+    memset(&pl, 0, sizeof pl);
+    int down, up;
+    neighbour_ranks(h, &down, &up);
+    auto add = [&](const void* src, char* dst, size_t bytes) {
+        if (pl.n >= PUT_MAX) return;
+        pl.src[pl.n] = (const char*)src; pl.dst[pl.n] = dst; pl.bytes[pl.n] = (uint32_t)bytes; ++pl.n;
+    };
+    for (int dir = 0; dir < 2; ++dir) {
+        const int nb = dir == 0 ? down : up;
+        if (nb < 0) continue;
+        const bool isUp = dir == 1;
+        Slab* s = isUp ? h->slabs.back().get() : h->slabs.front().get();
+        const PeerExport& r = P.nbInfo[dir];
+        const size_t XY = s->XY;
+        const size_t sp = isUp ? (size_t)s->dev.Z - 2 : 1;      // my face plane
+        const size_t dp = isUp ? 0 : (size_t)r.Z - 1;           // the neighbour's ghost plane
+        if (what & G_POPS) {
+            const double* f = s->fbuf(buf);
+            double* nf = (double*)P.nb[dir][buf == 0 ? PB_FA : PB_FB] + r.pad;
+            auto pop = [&](int k) { add(f + (size_t)k * s->stride + sp * XY, (char*)(nf + (size_t)k * r.stride + dp * XY), XY * 8); };
+            if (h->slip) { for (int k = 0; k < Q; ++k) pop(k); }
+            else { const int* ks = isUp ? POPS_UP : POPS_DOWN; for (int q = 0; q < 5; ++q) pop(ks[q]); }
+        }
+        auto field = [&](const double* mineP, int b) {
+            if (mineP && P.nb[dir][b]) add(mineP + sp * XY, P.nb[dir][b] + dp * XY * 8, XY * 8);
+        };
+        if (what & G_MACRO) { field(s->n.p, PB_N); field(s->ux.p, PB_UX); field(s->uy.p, PB_UY); field(s->uz.p, PB_UZ); }
+        if (what & G_VISC) field(s->visc.p, PB_VISC);
+        if (what & G_HF) { field(s->hfx.p, PB_HFX); field(s->hfy.p, PB_HFY); field(s->hfz.p, PB_HFZ); }
+        // the flag word the neighbour waits on: we are ITS neighbour above when it is below us, and vice versa
+        pl.flagDst[dir] = (uint32_t*)P.nb[dir][PB_FLAGS] + (isUp ? 0 : 1);
+    }
+    pl.counter = P.flags.p + 8;
+    pl.chunk = 32768;
+}
+
+// step halo through peer memory, on `st` (after the face planes are final)
+int peer_put(LbGpuHandle* h, uint32_t what, cudaStream_t st) {
+    PeerHalo& P = h->peer;
+    const int buf = h->cur ^ 1;
+    if (P.planWhat[buf] != what) { build_put_plan(h, what, buf, P.plan[buf]); P.planWhat[buf] = what; }
+    const PutPlan& pl = P.plan[buf];
+    uint32_t maxBytes = 0;
+    for (int k = 0; k < pl.n; ++k) maxBytes = pl.bytes[k] > maxBytes ? pl.bytes[k] : maxBytes;
+    if (pl.n == 0) return 0;
+    dim3 grid((maxBytes + pl.chunk - 1) / pl.chunk, (unsigned)pl.n);
+    k_put_halo<<<grid, 128, 0, st>>>(pl, P.seq);
+    ++h->launches;
+    CU(cudaGetLastError());
     return 0;
 }
 
@@ -865,7 +1157,8 @@ int lb_step(LbGpuHandle* h) {
     if (overlap) {
         CU(cudaEventRecord(h->evFaces, st));
         CU(cudaStreamWaitEvent(h->commStream, h->evFaces, 0));
-        if ((rc = exchange_remote(h, what, h->commStream))) return rc;
+        if (h->peer.on) { ++h->peer.seq; if ((rc = peer_put(h, what, h->commStream))) return rc; }
+        else if ((rc = exchange_remote(h, what, h->commStream))) return rc;
         CU(cudaEventRecord(h->evHalo, h->commStream));
     }
     for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
@@ -874,7 +1167,13 @@ int lb_step(LbGpuHandle* h) {
     // ghostCopy: the mirrors of everything the step kernel stored are copied now (the kernel did not push them)
     const uint32_t whatLocal = what | (h->ghostCopy ? ((macro ? G_MACRO : 0u) | (h->shear ? G_VISC : 0u) | (couple ? G_HF : 0u)) : 0u);
     if ((rc = exchange(h, whatLocal, !h->ghostCopy, !overlap))) return rc;
-    if (overlap) CU(cudaStreamWaitEvent(st, h->evHalo, 0));
+    if (overlap) {
+        CU(cudaStreamWaitEvent(st, h->evHalo, 0));
+        if (h->peer.on) {  // ... and the neighbours' planes of this step have landed in our ghost planes
+            k_wait_halo<<<1, 32, 0, st>>>(h->peer.flags.p, h->peer.seq, down >= 0, up >= 0, h->slabs[0]->status.p);
+            ++h->launches;
+        }
+    }
     Slab* s0 = h->slabs[0].get();
     if (h->hasCurved) {
         // streaming through the curved links + their extraMass, after every cell's n, u of this step are in place
@@ -935,6 +1234,11 @@ int lb_step(LbGpuHandle* h) {
 }
 
 int check_status(LbGpuHandle* h) {
+    if (h->peer.on) {
+        CU(cudaMemcpyAsync(h->pinnedStatus, h->slabs[0]->status.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*h->pinnedStatus) return fail(LBGPU_ECOMM, "peer halo: the planes of the rank %s never arrived (20 s)", *h->pinnedStatus == 1 ? "below" : "above");
+    }
     for (auto& sp : h->slabs) {
         if (h->fs && h->pinnedCounts[8 * sp->slot + 2] > sp->cellCap)
             return fail(LBGPU_EUNSUPPORTED, "free surface: %u interface cells exceed the list capacity %u", h->pinnedCounts[8 * sp->slot + 2], sp->cellCap);
@@ -956,6 +1260,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
                const double* n, const double* u, const double* mass, const double* visc) {
     const LbGpuParams* prm = &h->prm;
     cudaStream_t st = h->stream;
+    Trace tr("build_slab");
     const int X = prm->size[0], Y = prm->size[1], gZ = prm->size[2];
     const int Zl = s->zEnd - s->zBegin + 2;
     s->XY = (uint32_t)X * (uint32_t)Y;
@@ -1013,6 +1318,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     CU(cudaMemsetAsync(s->status.p, 0, sizeof(uint32_t) * 4, st));
     CU(cudaMemsetAsync(s->partial.p, 0, sizeof(double) * nPartial, st));
 
+    tr.mark("allocations + memsets issued");
     Dev& d = s->dev;
     memset(&d, 0, sizeof d);
     d.X = X; d.Y = Y; d.Z = Zl; d.N = N; d.stride = s->stride;
@@ -1093,6 +1399,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         }
     }
 
+    tr.mark("ghost lists");
     if (!type_flags) { CU(cudaGetLastError()); return 0; }  // device-side initialisation fills the arrays (device_init)
     if (perZ && s->remoteLo && s->zBegin == 1) {
         s->shellTypeLo.assign(type_flags + hostOff, type_flags + hostOff + s->XY);
@@ -1110,6 +1417,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
       if ((rc = h2d_staged(h, s->n.p, n + hostOff, sizeof(double) * N))) return rc;
       if ((rc = h2d_staged(h, s->mass.p, mass + hostOff, sizeof(double) * N))) return rc;
       if ((rc = h2d_staged(h, s->visc.p, visc + hostOff, sizeof(double) * N))) return rc; }
+    tr.mark("type, solidIndex, n, mass, visc up");
     {
         DevBuf<double> tmp;
         CU(tmp.alloc((size_t)3 * N));
@@ -1117,6 +1425,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         k_split3<<<s->blocks, BLOCK, 0, st>>>(N, tmp.p, s->ux.p, s->uy.p, s->uz.p);
         CU(cudaStreamSynchronize(st));
     }
+    tr.mark("u up + split");
     Dev dd = dev_all(h, s);
     if (f) {
         DevBuf<double> tmp;
@@ -1129,6 +1438,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     }
     h->launches += 2;
     CU(cudaGetLastError());
+    tr.mark("populations");
     return 0;
 }
 
@@ -1231,6 +1541,7 @@ int device_init(LbGpuHandle* h, const BoxSetup& bs) {
     }
     if (!bs.regions.empty()) {
         for (auto& sp : h->slabs) { k_init_gas<<<sp->blocks, BLOCK, 0, st>>>(dev_all(h, sp.get()), dreg.p, (int)bs.regions.size(), flag.p); ++h->launches; }
+        if ((rc = allreduce_sum(h, flag.p, 1, lbcomm::ncclUint32))) return rc;  // every rank takes the same branch
         CU(cudaMemcpyAsync(h->pinnedStatus, flag.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*h->pinnedStatus) {
@@ -1242,6 +1553,8 @@ int device_init(LbGpuHandle* h, const BoxSetup& bs) {
         }
     }
     for (auto& sp : h->slabs) { k_init_maxp<<<own_blocks(sp.get()), BLOCK, 0, st>>>(dev_for(h, sp.get()), maxp.p); ++h->launches; }
+    // the reference height of the hydrostatic density is the highest active cell of the WHOLE lattice
+    if (lbcomm::active()) NC(lbcomm::api().AllReduce(maxp.p, maxp.p, 3, lbcomm::ncclInt32, lbcomm::ncclMax, lbcomm::comm().comm, st));
     int mp[3];
     CU(cudaMemcpyAsync(mp, maxp.p, sizeof mp, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -1271,6 +1584,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
               const double* n, const double* u, const double* mass, const double* visc, const BoxSetup* box, LbGpuHandle** out) {
     if (!prm || !out || (!box && (!type_flags || !solidIndex || !n || !u || !mass || !visc))) return fail(LBGPU_EINVAL, "lbGpuInit: null argument");
     *out = nullptr;
+    Trace tr("lbGpuInit");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -1310,16 +1624,38 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         }
         anyGas = anyIface = !box->regions.empty();
     }
-    for (unsigned long long i = 0; type_flags && i < Nh; ++i) {
-        const int t = type_flags[i] & LBGPU_TYPE_MASK;
-        anyCurved |= (t == T_CURVED);
-        if (t == 1 || t > 9) return fail(LBGPU_EINVAL, "lbGpuInit: cell %llu has undefined type %d", i, t);
-        anyDyn |= (t == T_DYN_WALL || t == T_SLIP_DYN);
-        anySlip |= (t == T_SLIP_STAT || t == T_SLIP_DYN);
-        anyGas |= (t == T_GAS);
-        anyIface |= (t == T_INTERFACE);
+    if (type_flags) {
+        // which cell types occur: byte histogram on a few threads (a branch per cell costs 30 ms on 16 M cells)
+        const int T = copy_threads();
+        std::vector<std::vector<unsigned long long>> hist((size_t)T, std::vector<unsigned long long>(256, 0ull));
+        std::vector<std::thread> th;
+        const unsigned long long per = (Nh + T - 1) / T;
+        auto work = [&](int k) {
+            unsigned long long* hk = hist[(size_t)k].data();
+            const unsigned long long b = (unsigned long long)k * per, e = b + per < Nh ? b + per : Nh;
+            for (unsigned long long i = b; i < e; ++i) ++hk[type_flags[i]];
+        };
+        for (int k = 1; k < T; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto& t : th) t.join();
+        bool present[16] = {};
+        for (int k = 0; k < T; ++k) for (int v = 0; v < 256; ++v) if (hist[(size_t)k][(size_t)v]) present[v & LBGPU_TYPE_MASK] = true;
+        for (int t = 0; t < 16; ++t) {
+            if (!present[t]) continue;
+            if (t == 1 || t > 9) {
+                unsigned long long i = 0;
+                while (i < Nh && (type_flags[i] & LBGPU_TYPE_MASK) != t) ++i;
+                return fail(LBGPU_EINVAL, "lbGpuInit: cell %llu has undefined type %d", i, t);
+            }
+        }
+        anyCurved = present[T_CURVED];
+        anyDyn = present[T_DYN_WALL] || present[T_SLIP_DYN];
+        anySlip = present[T_SLIP_STAT] || present[T_SLIP_DYN];
+        anyGas = present[T_GAS];
+        anyIface = present[T_INTERFACE];
     }
 
+    tr.mark("type scan");
     LbGpuHandle* h = new (std::nothrow) LbGpuHandle();
     if (!h) return fail(LBGPU_EINVAL, "out of host memory");
     h->prm = *prm;
@@ -1335,7 +1671,11 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaEventCreate(&h->evA));
         CU(cudaEventCreate(&h->evB));
-        CU(cudaStreamCreateWithFlags(&h->commStream, cudaStreamNonBlocking));
+        {   // the halo transport must not queue behind the interior launch's blocks: highest priority
+            int prLo = 0, prHi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+            CU(cudaStreamCreateWithPriority(&h->commStream, cudaStreamNonBlocking, prHi));
+        }
         CU(cudaEventCreateWithFlags(&h->evFaces, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->evHalo, cudaEventDisableTiming));
         h->kev0.resize(LbGpuHandle::KEV); h->kev1.resize(LbGpuHandle::KEV);
@@ -1362,6 +1702,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         CU(cudaMallocHost((void**)&h->pinnedStatus, 4096));
         CU(cudaMallocHost((void**)&h->pinnedCounts, sizeof(uint32_t) * 8 * (size_t)nLocal));
         memset(h->pinnedCounts, 0, sizeof(uint32_t) * 8 * (size_t)nLocal);
+        tr.mark("streams, events, pinned");
         for (int k = 0; k < nLocal; ++k) {
             h->slabs.emplace_back(new Slab());
             Slab* s = h->slabs.back().get();
@@ -1371,6 +1712,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
             s->zBegin = zb; s->zEnd = ze;
             if (int r = build_slab(h, s, zLo - 1, type_flags, solidIndex, f, n, u, mass, visc)) return r;
         }
+        tr.mark("slabs built");
         if (box) { if (int r = device_init(h, *box)) return r; }
         // ghosts of every field, both population buffers
         if (int r = exchange(h, G_POPS | G_POPS_SRC | G_TYPE | G_SOLID | G_MASS | G_MACRO | G_VISC | G_HF)) return r;
@@ -1390,6 +1732,9 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         for (auto& sp : h->slabs) CU(cudaMemcpyAsync(sp->counters.p, s0->counters.p + 2, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
         CU(cudaStreamSynchronize(st));
         CU(cudaGetLastError());
+        tr.mark("ghosts, static lists, counts");
+        if (int r = peer_setup(h)) return r;
+        tr.mark("peer set-up");
         return 0;
     };
     rc = body();
@@ -1411,7 +1756,6 @@ int lbGpuInit(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
 int lbGpuInitBox(const LbGpuParams* prm, const double initVelocity[3], const double* wallVelocity, const LbGpuRegion* regions,
                  uint32_t nRegions, const LbGpuParticle* parts, uint32_t nParts, LbGpuHandle** out) {
     if (!prm || !out || (nRegions && !regions) || (nParts && !parts)) return fail(LBGPU_EINVAL, "lbGpuInitBox: null argument");
-    if (lbcomm::active()) return fail(LBGPU_EUNSUPPORTED, "lbGpuInitBox: one process only (slabs of other processes: use lbGpuInit with host arrays)");
     if (prm->boundary[4] == T_PERIODIC && prm->nSlabs > 1) return fail(LBGPU_EUNSUPPORTED, "lbGpuInitBox: z-periodic lattice cut into slabs");
     BoxSetup bs;
     memset(&bs.box, 0, sizeof bs.box);
@@ -1597,6 +1941,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
     if (!h) return fail(LBGPU_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
     if (int rc = check_status(h)) return rc;
+    Trace tr("lbGpuFetchFields");
     cudaStream_t st = h->stream;
     const int zLoHost = h->slabs[0]->zBegin - 1;
     if (!h->macroValid && (n || u)) {
@@ -1637,6 +1982,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             for (uint32_t k = 0; k < s->nGhost; ++k) type_flags[hBase + s->ghostIdx[k]] = s->ghostType[k];
             if (!s->shellTypeLo.empty()) memcpy(type_flags + hBase, s->shellTypeLo.data(), s->XY);
             if (!s->shellTypeHi.empty()) memcpy(type_flags + hTop, s->shellTypeHi.data(), s->XY);
+            tr.mark("types");
         }
         if (solidIndex) {
             if (int rc2 = d2h_staged(h, solidIndex + hOff, s->solidIndex.p + cOff, sizeof(uint32_t) * cCnt)) return rc2;
@@ -1662,7 +2008,9 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             for (uint32_t k = 0; k < s->nGhost; ++k)
                 if ((s->ghostType[k] & NODE_BIT) && is_wall_type(s->ghostType[k] & TYPE_MASK)) n[hBase + s->ghostIdx[k]] = s->ghostN[k];
         }
+        tr.mark("n");
         if (mass && (rc = scalar(s->mass.p, mass, 0))) return rc;
+        tr.mark("mass");
         if (visc && (rc = scalar(s->visc.p, visc, 0))) return rc;
         if (shearRate && (rc = scalar(s->shearRate.p, shearRate, 1))) return rc;
         if (u) {
@@ -1673,6 +2021,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
             for (uint32_t k = 0; k < s->nGhost; ++k)
                 if ((s->ghostType[k] & NODE_BIT) && is_wall_type(s->ghostType[k] & TYPE_MASK))
                     for (int c = 0; c < 3; ++c) u[3 * (hBase + s->ghostIdx[k]) + c] = s->ghostU[3 * k + c];
+            tr.mark("u");
         }
         if (hydroForce) {
             k_fetch_vec<<<B, BLOCK, 0, st>>>(d, s->hfx.p, s->hfy.p, s->hfz.p, tmp.p, 1);
@@ -1694,7 +2043,14 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
     return LBGPU_OK;
 }
 
-int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
+}  // extern "C"
+namespace { int counts_impl(LbGpuHandle* h, uint64_t counts[4], bool global); }
+extern "C" {
+int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) { return counts_impl(h, counts, true); }
+int lbGpuCountsLocal(LbGpuHandle* h, uint64_t counts[4]) { return counts_impl(h, counts, false); }
+}  // extern "C"
+namespace {
+int counts_impl(LbGpuHandle* h, uint64_t counts[4], bool global) {
     if (!h || !counts) return fail(LBGPU_EINVAL, "null argument");
     CU(cudaSetDevice(h->device));
     unsigned long long tot[3] = { 0, 0, 0 };
@@ -1708,7 +2064,7 @@ int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
         CU(cudaStreamSynchronize(h->stream));
         for (int k = 0; k < 3; ++k) tot[k] += tmp[k];
     }
-    if (lbcomm::active()) {
+    if (global && lbcomm::active()) {
         Slab* s0 = h->slabs[0].get();
         CU(cudaMemcpyAsync(s0->counters.p + 4, tot, sizeof tot, cudaMemcpyHostToDevice, h->stream));
         if (int rc = allreduce_sum(h, s0->counters.p + 4, 3, lbcomm::ncclUint64)) return rc;
@@ -1718,6 +2074,8 @@ int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]) {
     counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2]; counts[3] = h->steps;
     return LBGPU_OK;
 }
+}  // namespace
+extern "C" {
 
 int lbGpuCommUniqueId(uint8_t id[128]) {
     if (!id) return fail(LBGPU_EINVAL, "null argument");
@@ -1753,6 +2111,13 @@ int lbGpuCommInfo(int32_t* rank, int32_t* world, int32_t* ncclVersion) {
     if (rank) *rank = c.rank;
     if (world) *world = c.comm ? c.world : 1;
     if (ncclVersion) { int v = 0; if (lbcomm::api().GetVersion) lbcomm::api().GetVersion(&v); *ncclVersion = v; }
+    return LBGPU_OK;
+}
+
+int lbGpuPeerHalo(LbGpuHandle* h, int32_t* on) {
+    if (!h || !on) return fail(LBGPU_EINVAL, "null argument");
+    *on = h->peer.on ? 1 : 0;
+    if (!h->peer.on && !h->peer.note.empty()) g_err = h->peer.note;  // why not (lbGpuLastError)
     return LBGPU_OK;
 }
 
@@ -1895,6 +2260,8 @@ int lbGpuFinalize(LbGpuHandle* h) {
     if (!h) return LBGPU_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->commStream) cudaStreamSynchronize(h->commStream);
+    peer_teardown(h);
     h->slabs.clear();
     if (h->evA) cudaEventDestroy(h->evA);
     if (h->evB) cudaEventDestroy(h->evB);

@@ -5,6 +5,11 @@
 // single-GPU user never needs it.  Only point-to-point ncclSend/ncclRecv inside one group per exchange (NVLink 5 /
 // NVSwitch peer copies on a B200 box) and small fp64/u64/u32 sum all-reduces are used; there is no data-path
 // collective (the path shards, the only exchange is the face halo).
+//
+// The per-step population halo itself does not go through NCCL when the neighbour GPUs are peers (NVLink / NVSwitch):
+// each rank maps its neighbours' arrays (cudaIpc) and a put kernel stores the face planes straight into the
+// neighbour's ghost planes and raises a flag there (lbgpu.cu, "peer halo").  NCCL then carries only the handles at
+// start-up, the small sums and the in-cycle byte planes of the free-surface / particle-flag updates.
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -19,8 +24,8 @@ namespace lbcomm {
 typedef struct ncclComm* ncclComm_t;
 struct ncclUniqueId { char internal[128]; };
 enum { ncclSuccess = 0 };
-enum { ncclUint8 = 1, ncclUint32 = 3, ncclUint64 = 5, ncclFloat64 = 8 };
-enum { ncclSum = 0 };
+enum { ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2 };
 
 struct Api {
     void* lib = nullptr;
@@ -30,6 +35,7 @@ struct Api {
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -63,6 +69,7 @@ inline std::string load() {
     a.Send = (decltype(a.Send))sym("ncclSend");
     a.Recv = (decltype(a.Recv))sym("ncclRecv");
     a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
     a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
     a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
     a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
@@ -81,5 +88,24 @@ inline Comm& comm() {
     return c;
 }
 inline bool active() { return comm().comm != nullptr && comm().world > 1; }
+
+// cuMemGetAddressRange of the driver API (bound at run time like NCCL): cudaIpcGetMemHandle describes the whole
+// allocation a pointer lies in (small cudaMalloc blocks are sub-allocated), so the exporter sends the offset along
+inline int address_range(const void* p, void** base, size_t* size) {
+    typedef int (*Fn)(unsigned long long*, size_t*, unsigned long long);
+    static Fn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return -1;
+        fn = (Fn)dlsym(h, "cuMemGetAddressRange_v2");
+        if (!fn) return -1;
+    }
+    unsigned long long b = 0;
+    size_t sz = 0;
+    const int rc = fn(&b, &sz, (unsigned long long)(uintptr_t)p);
+    if (rc != 0) return rc;
+    *base = (void*)(uintptr_t)b; *size = sz;
+    return 0;
+}
 
 }  // namespace lbcomm

@@ -69,8 +69,6 @@ class LB:
         """`case`: hybird configuration keys + set-up options as in hybird_b200.workloads (what
         lattice_init.build_state restates on the host)."""
         from . import lattice_init as li
-        if self.planes != (0, int(self.params["size"][2])):
-            raise ValueError("latticeBolzmannInitBox: one process only")
         regions = li.regions_from_case(case, self.params)
         reg = np.zeros(len(regions), dtype=np.dtype([("kind", "<i4"), ("gasInside", "<i4"), ("a", "<f8", 6)], align=True))
         for k, (kind, inside, a) in enumerate(regions):
@@ -171,18 +169,36 @@ class LB:
         abi.check(self.lib.lbGpuLaunchCount(self.h, C.byref(v)))
         return int(v.value)
 
-    def counts(self):
+    def counts(self, local=False):
         c = (C.c_uint64 * 4)()
-        abi.check(self.lib.lbGpuCounts(self.h, C.byref(c)))
+        abi.check((self.lib.lbGpuCountsLocal if local else self.lib.lbGpuCounts)(self.h, C.byref(c)))
         return dict(fluid=int(c[0]), interface=int(c[1]), particle=int(c[2]), steps=int(c[3]))
 
+    def peer_halo(self):
+        """True when the per-step halo of this handle goes through peer memory (lbGpuPeerHalo)."""
+        on = C.c_int32()
+        abi.check(self.lib.lbGpuPeerHalo(self.h, C.byref(on)))
+        return bool(on.value)
+
     # -- what IO reads from lb.types / lb.nodes (IO.cpp:698-831) ---------------------------------
-    def fetch(self, fields=("type_flags", "solidIndex", "n", "u", "mass", "visc", "shearRate", "hydroForce", "f")):
-        N = self.N
+    @staticmethod
+    def host_mirrors(N, fields):
+        """Host arrays lbGpuFetchFields fills, allocated and touched once (the reference keeps lb.types / lb.nodes for
+        the whole run; a caller that exports repeatedly reuses its mirrors)."""
         shapes = dict(type_flags=((N,), np.uint8), solidIndex=((N,), np.uint32), n=((N,), np.float64),
                       u=((N, 3), np.float64), mass=((N,), np.float64), visc=((N,), np.float64),
                       shearRate=((N,), np.float64), hydroForce=((N, 3), np.float64), f=((N, abi.Q), np.float64))
-        out = {k: np.zeros(shapes[k][0], shapes[k][1]) for k in fields}
+        out = {}
+        for k in fields:
+            out[k] = np.empty(shapes[k][0], shapes[k][1])
+            out[k].fill(0)
+        return out
+
+    def fetch(self, fields=("type_flags", "solidIndex", "n", "u", "mass", "visc", "shearRate", "hydroForce", "f"), out=None):
+        if out is None:
+            out = self.host_mirrors(self.N, fields)
+        else:
+            out = {k: out[k] for k in fields}
         order = ("type_flags", "solidIndex", "n", "u", "mass", "visc", "shearRate", "hydroForce", "f")
         abi.check(self.lib.lbGpuFetchFields(self.h, *[abi.ptr(out.get(k)) for k in order]))
         return out

@@ -105,19 +105,27 @@ def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None,
     Zg = prm["size"][2]
     elements = case.get("elements", [])
     parts, elmts, comps = li.expand_elements(elements, prm["unitLength"])
-    if world == 1 and device_init:
+    if device_init:
+        # every rank initialises its own planes on the device: no host state at all
         prm["nWalls"] = len(li.make_walls(prm))
+        if world > 1:
+            prm.update(nSlabs=world, slabIndex=rank, nLocalSlabs=1)
         lb = LB(prm, device=device)
         t0 = time.perf_counter()
         lb.latticeBolzmannInitBox(case, parts if len(parts) else None)
         lb.synchronize()
         init_s = time.perf_counter() - t0
-        c = lb.counts()
+        c = lb.counts(local=True)
         active = c["fluid"] + c["interface"]
-        N = int(np.prod(prm["size"]))
-        info = dict(upload_s=init_s, upload_bytes=0, params=prm, active_local=active, active_total=active, global_z=Zg,
-                    parallelism="1 GPU", parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
-                    bytes_resident=2 * 19 * 8 * N + 60 * N, init="device (lbGpuInitBox)")
+        c = lb.counts()
+        active_total = c["fluid"] + c["interface"]
+        N = lb.N
+        par = "1 GPU" if world == 1 else "%d z-slabs, one rank per GPU, face planes stored into the neighbour's ghost planes over NVLink (5 populations per face)" % world
+        info = dict(upload_s=init_s, upload_bytes=0, params=prm, active_local=active, active_total=active_total, global_z=Zg,
+                    parallelism=par, parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
+                    bytes_resident=2 * 19 * 8 * N + 60 * N, init="device (lbGpuInitBox)",
+                    halo=None if world == 1 else ("peer memory (cudaIpc over NVLink): one put kernel per step" if lb.peer_halo()
+                                                  else "NCCL send/recv"))
         return lb, info
     if world == 1:
         st = li.build_state(case, parts if len(parts) else None)
@@ -142,7 +150,9 @@ def build_engine(case: dict, rank: int, world: int, device: int = -1, dist=None,
     upload_bytes = int(sum(a.nbytes for a in (st.type_flags, st.solidIndex, st.n, st.u, st.mass, st.visc)))
     info = dict(upload_s=upload_s, upload_bytes=upload_bytes, params=st.params, active_local=active, active_total=active_total, global_z=Zg, parallelism=par,
                 parts=parts, elmts=elmts, comps=comps, kernel="k_step (fused pull stream + collide)",
-                bytes_resident=2 * 19 * 8 * st.type_flags.size + 60 * st.type_flags.size, init="host arrays (lbGpuInit)")
+                bytes_resident=2 * 19 * 8 * st.type_flags.size + 60 * st.type_flags.size, init="host arrays (lbGpuInit)",
+                halo=None if world == 1 else ("peer memory (cudaIpc over NVLink): one put kernel per step" if lb.peer_halo()
+                                              else "NCCL send/recv"))
     return lb, info
 
 

@@ -124,7 +124,7 @@ def catalogue():
     C["sphere_fixed"] = make_case("sphere_fixed", demSolve=0, lbSizeX=20, lbSizeY=18, lbSizeZ=22, boundary0=4, boundary1=4,
                                   lbFX=4e-5, lbFZ=-1e-5, initVisc=0.08,
                                   elements=[dict(size=1, radius=3.4, x0=[9.6, 8.8, 11.3], x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.0]),
-                                            dict(size=2, radius=2.1, x0=[14.2, 9.1, 6.4], x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.0])])
+                                            dict(size=1, radius=2.1, x0=[14.2, 9.1, 6.4], x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.0])])
     C["cluster_dem"] = make_case(
         "cluster_dem", lbSizeX=24, lbSizeY=22, lbSizeZ=26, lbFZ=-3e-5, initVisc=0.1,
         elements=[dict(size=2, radius=2.6, x0=[11.0, 10.5, 17.0], x1=[0.0, 0.0, 0.0], w=[0.01, 0.02, 0.0]),

@@ -97,6 +97,11 @@ int lbGpuCommUniqueId(uint8_t id[128]);
 int lbGpuCommInit(const uint8_t id[128], int32_t rank, int32_t world, int32_t device);
 int lbGpuCommInfo(int32_t* rank, int32_t* world, int32_t* ncclVersion);
 int lbGpuCommFinalize(void);
+/* *on = 1 when this handle's per-step halo goes through peer memory: every rank maps the arrays of its neighbour ranks
+ * (cudaIpc over NVLink / NVSwitch) and one put kernel per step stores the face planes straight into the neighbours'
+ * ghost planes and raises a flag there; 0: NCCL send/recv carries it (no peer access between the GPUs, or
+ * LBGPU_PEER_HALO=0) -- lbGpuLastError() then says why. */
+int lbGpuPeerHalo(LbGpuHandle* h, int32_t* on);
 
 /* Upload the state LB::latticeBolzmannInit produced.
  *   type_flags  N bytes: t | p<<4 | node<<5
@@ -111,7 +116,8 @@ int lbGpuInit(const LbGpuParams* params, const uint8_t* type_flags, const uint32
  * demChute): LB::latticeBolzmannInit's cell types, DEM wall indices, particle flags, gas region with the interface
  * closure, hydrostatic density, initial velocity, masses and wall nodes (LB.cpp:190-219, 324-996; DEM.cpp:435-640)
  * computed per cell, instead of by the reference's serial O(N x n_geom) host loops and a 35 GB host mirror at 67 M
- * cells.  Bit-identical to uploading the host-built state.  One process (any number of local slabs).
+ * cells.  Bit-identical to uploading the host-built state.  Works per slab: with a communicator every rank
+ * initialises its own planes (the hydrostatic reference height is max-reduced over the ranks).
  *   initVelocity   lattice units (LB.cpp:143)
  *   wallVelocity   6 x 3, physical units, velocity of the DEM wall of boundary k (used where boundary k is 6 or 8); may be NULL
  *   regions        applied in order to fluid cells: a cell inside (gasInside) / outside (!gasInside) becomes gas
@@ -170,6 +176,8 @@ int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes);
 
 /* counters: [0]=fluid cells, [1]=interface cells, [2]=cells with p flag, [3]=LB steps done */
 int lbGpuCounts(LbGpuHandle* h, uint64_t counts[4]);
+/* the same over the planes this handle owns only (lbGpuCounts sums over the ranks of the communicator) */
+int lbGpuCountsLocal(LbGpuHandle* h, uint64_t counts[4]);
 int lbGpuSynchronize(LbGpuHandle* h);
 /* device time of the kernels launched by the last lbGpuStep/lbGpuRun call, milliseconds (CUDA events) */
 int lbGpuLastStepMs(LbGpuHandle* h, float* ms);

@@ -1,6 +1,8 @@
 """One rank of a multi-process slab run (launched by torch.distributed.run from tests/test_gpu_slabs.py):
 a golden case cut into WORLD_SIZE z-slabs, one GPU per rank, replayed with the recorded particle inputs;
-rank 0 gathers the fields and writes them to OUT.   python run_slab_ranks.py CASE OUT"""
+rank 0 gathers the fields and writes them to OUT.   python run_slab_ranks.py CASE OUT [--device-init] [--nccl-halo]
+--device-init: every rank initialises its planes on the device (lbGpuInitBox) instead of uploading host arrays;
+--nccl-halo: the step halo travels over NCCL send/recv instead of through peer memory (LBGPU_PEER_HALO=0)."""
 import os
 import sys
 
@@ -13,6 +15,9 @@ import golden_util as gu
 from hybird_b200 import LB, slabs
 
 name, out = sys.argv[1], sys.argv[2]
+device_init = "--device-init" in sys.argv
+if "--nccl-halo" in sys.argv:
+    os.environ["LBGPU_PEER_HALO"] = "0"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -25,7 +30,14 @@ lo, hi = slabs.window_of(Z, world, rank)
 sl = slice(lo * X * Y, hi * X * Y)
 tf, si, n, u, mass, visc = g.init_arrays()
 lb = LB(prm, device=local)
-lb.latticeBolzmannInit(tf[sl], si[sl], n[sl], u[sl], mass[sl], visc[sl])
+if device_init:
+    import cases
+    from hybird_b200 import lattice_init as li
+    case = cases.catalogue()[name]
+    parts0 = li.expand_elements(case.get("elements", []), prm["unitLength"])[0]
+    lb.latticeBolzmannInitBox(case, parts0 if len(parts0) else None)
+else:
+    lb.latticeBolzmannInit(tf[sl], si[sl], n[sl], u[sl], mass[sl], visc[sl])
 steps = min(g.steps, 30)
 Fs, Ms = [], []
 for s, F, M, V, W in gu.replay(g, lb, None):
@@ -36,6 +48,7 @@ fields = slabs.gather_fields(lb, rank, world, dist, ("type_flags", "n", "u", "ma
 cnt = lb.counts()
 if rank == 0:
     np.savez(out, steps=steps, F=np.stack(Fs), M=np.stack(Ms), fluid=cnt["fluid"], **fields)
+dist.barrier()  # nobody unmaps / frees arrays a neighbour may still be writing into
 lb.close()
 slabs.finalize_comm()
 dist.destroy_process_group()

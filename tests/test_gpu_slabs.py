@@ -67,14 +67,20 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("name", ["cfg2_mini", "cfg5_mini", "periodic_all"])
-def test_two_processes_two_gpus_match_one_gpu(name, tmp_path):
+@pytest.mark.parametrize("mode", ["peer", "nccl", "peer+device-init"])
+@pytest.mark.parametrize("name", ["cfg2_mini", "cfg5_mini", "periodic_all", "cfg4_mini", "cfg3_mini"])
+def test_two_processes_two_gpus_match_one_gpu(name, mode, tmp_path):
+    """mode: how the per-step halo travels (peer memory over NVLink, or NCCL send/recv) and where the initial state is
+    built (host arrays per slab, or lbGpuInitBox on every rank)."""
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if mode != "peer" and name in ("periodic_all", "cfg3_mini"):
+        pytest.skip("covered by the other cases")
     out = tmp_path / "ranks.npz"
     port = 29700 + os.getpid() % 200
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), name, str(out)]
+           "--master-port", str(port), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), name, str(out)] + \
+          (["--nccl-halo"] if mode == "nccl" else []) + (["--device-init"] if "device-init" in mode else [])
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     z = np.load(out)
