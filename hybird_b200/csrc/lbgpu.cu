@@ -277,7 +277,7 @@ struct LbGpuHandle {
     // one chunk overlaps the DMA of the other; a plain cudaMemcpy from pageable memory serialises the two)
     char* stage[2] = { nullptr, nullptr };
     cudaEvent_t stageEv[2] = { nullptr, nullptr };
-    static constexpr size_t STAGE = 64u << 20;
+    static constexpr size_t STAGE = 16u << 20;
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
@@ -286,6 +286,7 @@ struct LbGpuHandle {
     uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
     // curved walls (type 9) and LB::enforceMassConservation (problemName DRUM)
+    int pipeBlocks = PIPE_MIN_BLOCKS;  // pure-fluid lattices: blocks per SM of the register-pipelined persistent step kernel; 0 = k_step (LBGPU_PIPE)
     bool wallPushAllowed = true;  // LBGPU_WALL_PUSH=0 keeps the list-driven launch for every wall-adjacent cell (A/B)
     bool ghostCopy = false;  // with wallPush, single process: the periodic mirrors are written by k_fill_ghosts after the step
                              // instead of by the step kernel, so the cells next to periodic faces take the bulk path too
@@ -1131,6 +1132,10 @@ int lb_step(LbGpuHandle* h) {
             if (g > s->blocks) g = s->blocks;
             if (h->fsGridPerSM > 0 && g > (uint32_t)(h->fsGridPerSM * h->numSMs)) g = (uint32_t)(h->fsGridPerSM * h->numSMs);
             k<<<g, BLOCK, 0, st>>>(d);
+        } else if (!split && h->pipeBlocks > 0 && d.bulk != nullptr && end - begin > (uint32_t)(h->pipeBlocks * h->numSMs * BLOCK)) {
+            // pure fluid: persistent register-pipelined kernel (lb_kernels.cuh, k_step_pipe)
+            const uint32_t g = (uint32_t)(h->pipeBlocks * h->numSMs);
+            if (h->force) k_step_pipe<true><<<g, BLOCK, 0, st>>>(d); else k_step_pipe<false><<<g, BLOCK, 0, st>>>(d);
         } else {
             k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
         }
@@ -1279,10 +1284,13 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     const size_t hostOff = (size_t)(s->zBegin - 1 - hostZ0) * s->XY;
 
     CU(s->fA.alloc(s->stride * Q + 2 * s->pad)); CU(s->fB.alloc(s->stride * Q + 2 * s->pad));
+    tr.mark("population buffers allocated");
     CU(cudaMemsetAsync(s->fA.p, 0, sizeof(double) * s->fA.n, st)); CU(cudaMemsetAsync(s->fB.p, 0, sizeof(double) * s->fB.n, st));
+    tr.mark("their memsets issued");
     CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
     CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
     CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
+    tr.mark("macroscopic arrays allocated");
     const size_t NT = ((size_t)N + LIST_CELLS - 1) / LIST_CELLS * LIST_CELLS + BLOCK;  // the last block of a pass reads whole
     CU(s->type0.alloc(NT)); CU(s->solidIndex.alloc(N));
     CU(cudaMemsetAsync(s->type0.p, T_STAT_WALL, NT, st));
@@ -1357,7 +1365,10 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             if ((z == 0 && s->remoteLo) || (z == Zl - 1 && s->remoteHi)) continue;
             for (int y = 0; y < Y; ++y) {
                 const bool ys = (y == 0 || y == Y - 1);
-                for (int x = 0; x < X; ++x) {
+                // rows inside the lattice only touch the two x shell cells (the lattice has 16 M cells, its shell 0.4 M)
+                const bool wholeRow = (ys && gy) || (zs && gzLocal);
+                if (!wholeRow && !gx) continue;
+                for (int x = 0; x < X; x += (wholeRow ? 1 : X - 1)) {
                     const bool xs = (x == 0 || x == X - 1);
                     const bool isG = (xs && gx) || (ys && gy) || (zs && gzLocal);
                     if (!isG) continue;
@@ -1683,6 +1694,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->fs = prm->freeSurface != 0;
         if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
         if (const char* e = getenv("LBGPU_WALL_PUSH")) h->wallPushAllowed = atoi(e) != 0;
+        if (const char* e = getenv("LBGPU_PIPE")) h->pipeBlocks = atoi(e);
 
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);

@@ -26,6 +26,10 @@ for s, F, M, V, W in gu.replay(g, lb, None):
         print("step", s, bad, "wall force rel", werr, "element force rel", ferr)
         if W.size:
             print("W gpu", W.tolist()); print("W ref", Wo.tolist())
+        if F.size:
+            print("F gpu", F.tolist()); print("F ref", Fo.tolist()); print("V gpu", V.tolist(), "ref", Vo.tolist())
+            hf = np.abs(a["hydroForce"] - b["hydroForce"]).max(axis=1)
+            print("hydroForce cells differing:", int(np.count_nonzero(hf)), "of", int(np.count_nonzero(b["type_flags"] & 16)), "flagged")
         act = np.isin(b["type_flags"] & 15, (0, 3))
         for k in ("mass", "n", "visc", "f"):
             d = np.abs(a[k] - b[k]); d = d.reshape(len(act), -1).max(axis=1) * act
