@@ -153,7 +153,8 @@ struct Slab {
     uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
-    DevBuf<double> partial, sums, scal, elemOut;
+    DevBuf<double> partial, sums, scal, elemOut, elemPartial;
+    DevBuf<uint32_t> elemDone;
     DevBuf<unsigned long long> counters;  // [0] nInterface [1..3] k_count scratch
     DevBuf<uint32_t> status;              // [0] type error, [1] flood-fill counter
     // host copies of what lbGpuInit received for the ghost cells (they are dead cells of the reference)
@@ -1217,10 +1218,19 @@ int lb_step(LbGpuHandle* h) {
         }
     }
     if (h->nElmts > 0 && couple) {
-        const uint32_t eb = h->nElmts;  // one block per element
+        // few elements: several blocks share one (the launch should fill the device: ~2 blocks per SM)
+        uint32_t split = 1;
+        while (split < 64 && h->nElmts * split * 2 <= (uint32_t)h->numSMs * 2) split *= 2;
+        const uint32_t eb = h->nElmts * split;
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
-            k_element_forces<<<eb, BLOCK, 0, st>>>(dev_for(h, s), h->uForce, h->uTorque, h->uVolume, s->elemOut.p);
+            if (split > 1 && s->elemPartial.n < (size_t)h->nElmts * split * 7) {
+                CU(s->elemPartial.alloc((size_t)h->rawElmts.n * 64 * 7));
+                CU(s->elemDone.alloc(h->rawElmts.n));
+                CU(cudaMemsetAsync(s->elemDone.p, 0, sizeof(uint32_t) * s->elemDone.n, st));
+            }
+            k_element_forces<<<eb, BLOCK, 0, st>>>(dev_for(h, s), h->uForce, h->uTorque, h->uVolume, s->elemOut.p, split,
+                                                   s->elemPartial.p, s->elemDone.p);
             ++h->launches;
             if (s != s0) { k_add_arrays<<<(7 * h->nElmts + 127) / 128, 128, 0, st>>>(s0->elemOut.p, s->elemOut.p, 7 * h->nElmts); ++h->launches; }
         }
