@@ -287,7 +287,7 @@ struct LbGpuHandle {
     uint32_t* pinnedCounts = nullptr;  // per slab: {interface cells, visited tiles, unclamped interface cells, -} of the last list build
     uint64_t steps = 0, launches = 0;
     // curved walls (type 9) and LB::enforceMassConservation (problemName DRUM)
-    int pipeBlocks = PIPE_MIN_BLOCKS;  // pure-fluid lattices: blocks per SM of the register-pipelined persistent step kernel; 0 = k_step (LBGPU_PIPE)
+    uint32_t prefetchBlocks = 0;  // dense step launches: L2 prefetch distance in blocks (Dev::prefetch; LBGPU_PREFETCH)
     bool wallPushAllowed = true;  // LBGPU_WALL_PUSH=0 keeps the list-driven launch for every wall-adjacent cell (A/B)
     bool ghostCopy = false;  // with wallPush, single process: the periodic mirrors are written by k_fill_ghosts after the step
                              // instead of by the step kernel, so the cells next to periodic faces take the bulk path too
@@ -361,6 +361,7 @@ Dev dev_for(LbGpuHandle* h, Slab* s) {
     d.lazyMass = 0;
     if (h->ghostCopy) d.push = 0;
     d.curveRow = s->curveRow.p; d.curveDelta = h->curveDelta.p; d.shearState = h->shear ? 1 : 0;
+    d.prefetch = h->prefetchBlocks;
     d.parts = h->parts.p; d.elmts = h->elmts.p; d.comps = h->comps.p;
     d.nParts = h->nParts; d.nElmts = h->nElmts;
     d.cellBegin = s->ownBegin; d.cellEnd = s->ownEnd;
@@ -1133,10 +1134,6 @@ int lb_step(LbGpuHandle* h) {
             if (g > s->blocks) g = s->blocks;
             if (h->fsGridPerSM > 0 && g > (uint32_t)(h->fsGridPerSM * h->numSMs)) g = (uint32_t)(h->fsGridPerSM * h->numSMs);
             k<<<g, BLOCK, 0, st>>>(d);
-        } else if (!split && h->pipeBlocks > 0 && d.bulk != nullptr && end - begin > (uint32_t)(h->pipeBlocks * h->numSMs * BLOCK)) {
-            // pure fluid: persistent register-pipelined kernel (lb_kernels.cuh, k_step_pipe)
-            const uint32_t g = (uint32_t)(h->pipeBlocks * h->numSMs);
-            if (h->force) k_step_pipe<true><<<g, BLOCK, 0, st>>>(d); else k_step_pipe<false><<<g, BLOCK, 0, st>>>(d);
         } else {
             k<<<(end - begin + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
         }
@@ -1295,7 +1292,14 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
 
     CU(s->fA.alloc(s->stride * Q + 2 * s->pad)); CU(s->fB.alloc(s->stride * Q + 2 * s->pad));
     tr.mark("population buffers allocated");
-    CU(cudaMemsetAsync(s->fA.p, 0, sizeof(double) * s->fA.n, st)); CU(cudaMemsetAsync(s->fB.p, 0, sizeof(double) * s->fB.n, st));
+    // every cell's 19 slots of both buffers are written by k_upload_f; only the pads in front of / behind the planes and
+    // the (< 32 doubles) tail of each plane need zeros for the speculative pulls (a first touch of 5 GB costs ~40 ms)
+    for (double* fb : { s->fA.p, s->fB.p }) {
+        CU(cudaMemsetAsync(fb, 0, sizeof(double) * s->pad, st));
+        CU(cudaMemsetAsync(fb + s->pad + s->stride * Q, 0, sizeof(double) * s->pad, st));
+        if (s->stride > N)
+            CU(cudaMemset2DAsync(fb + s->pad + N, sizeof(double) * s->stride, 0, sizeof(double) * (s->stride - N), Q, st));
+    }
     tr.mark("their memsets issued");
     CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
     CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
@@ -1406,6 +1410,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             CU(cudaMemcpyAsync(s->gSrc.p, gs.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
             CU(cudaMemcpyAsync(s->gPop.p, gp.data(), 4 * (size_t)s->nGhost, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));
+            tr.mark("ghost lists: built + uploaded");
             s->ghostIdx = gd; s->ghostSrc = gs;
             s->ghostType.resize(s->nGhost); s->ghostSolid.resize(s->nGhost);
             s->ghostN.assign(s->nGhost, 0.0); s->ghostU.assign((size_t)3 * s->nGhost, 0.0);
@@ -1704,7 +1709,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->fs = prm->freeSurface != 0;
         if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
         if (const char* e = getenv("LBGPU_WALL_PUSH")) h->wallPushAllowed = atoi(e) != 0;
-        if (const char* e = getenv("LBGPU_PIPE")) h->pipeBlocks = atoi(e);
+        if (const char* e = getenv("LBGPU_PREFETCH")) h->prefetchBlocks = (uint32_t)atoi(e);
 
         h->shear = prm->nonNewtonian || prm->turbulence;
         h->force = prm->forceField && (prm->lbF[0] != 0.0 || prm->lbF[1] != 0.0 || prm->lbF[2] != 0.0);

@@ -111,8 +111,9 @@ class LB:
     def latticeBolzmannStep(self, elmts=None, particles=None, fetch_forces=True, components=None):
         """`elmts`, `particles` as the reference passes them to LB::latticeBolzmannStep; they only matter when no
         coupling step was requested this cycle (demSolve = 0: the flags of the initialisation stay, the direct forcing
-        of LB::computeHydroForces still acts on them) -- `components` = the flattened elmts[].components then
-        (default: every element's particles in index order, as DEM::initializeParticle numbers them)."""
+        of LB::computeHydroForces still acts on them) -- `components` = the flattened elmts[].components then (they
+        include the periodic ghost particles, DEM.cpp:1658, so there is no default; the ones of the last coupling
+        step are reused when there was one)."""
         fs = int(self._fs_requested and self.freeSurface)
         if self._couple is not None:
             rescan, parts, els, comps = self._couple
@@ -122,7 +123,9 @@ class LB:
         elif particles is not None and len(particles) and elmts is not None and len(elmts):
             parts, els = np.ascontiguousarray(particles), np.ascontiguousarray(elmts)
             if components is None:
-                components = self._last[2] if len(self._last[2]) else np.arange(len(parts), dtype=np.uint32)
+                if not len(self._last[2]):
+                    raise ValueError("latticeBolzmannStep: particles without a coupling step need `components`")
+                components = self._last[2]
             comps = np.ascontiguousarray(components, dtype=np.uint32)
             self._last = (parts, els, comps)
             abi.check(self.lib.lbGpuStep(self.h, fs, 0, 0, abi.ptr(parts), len(parts), abi.ptr(els), len(els),

@@ -150,7 +150,7 @@ class Oracle:
         self.L.lbo_coupling_step(self.h, int(bool(newNeighborList)), _ptr(parts), len(parts), _ptr(elmts), len(elmts),
                                  _ptr(components))
 
-    def latticeBolzmannStep(self, elmts=None, parts=None):
+    def latticeBolzmannStep(self, elmts=None, parts=None, components=None):
         nE = 0 if elmts is None else len(elmts)
         nP = 0 if parts is None else len(parts)
         F = np.zeros((nE, 3)); M = np.zeros((nE, 3)); V = np.zeros(nE); Wf = np.zeros((self.nWalls, 3))

@@ -91,4 +91,4 @@ def replay(g: Golden, engine, get_state, dem_solve=None, on_step=None):
             engine.latticeBoltzmannFreeSurfaceStep()
         if dem_solve:
             engine.latticeBoltzmannCouplingStep(flag, elmts, parts, comps)
-        yield (s,) + tuple(engine.latticeBolzmannStep(elmts, parts))
+        yield (s,) + tuple(engine.latticeBolzmannStep(elmts, parts, components=comps))

@@ -28,12 +28,27 @@ def _types(lb):
     return lb.fetch(("type_flags",))["type_flags"]
 
 
+def _record(g, rep):
+    """Worst errors per dump step, appended to gpurun_out/parity_report.jsonl (copied to profiles/ by hand)."""
+    import json
+    import os
+    out = os.environ.get("LBGPU_PARITY_REPORT", os.path.join(common.ROOT, "gpurun_out", "parity_report.jsonl"))
+    try:
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        with open(out, "a") as fh:
+            fh.write(json.dumps(dict(fixture=g.name, case=g.case_name, lattice=g.params["size"], steps=g.steps,
+                                     type_maps_checked=sorted(g.type_sha), report={str(k): v for k, v in rep.items()})) + "\n")
+    except OSError:
+        pass
+
+
 @pytest.mark.parametrize("name", gfu.names("long"))
 def test_gpu_free_surface_minis_for_1000_steps(name):
     g = gfu.GoldenFull(name)
     lb = _gpu(g)
     rep = gfu.check_run(g, lb, _types, common.gpu_state)
     lb.close()
+    _record(g, rep)
     assert g.steps == 1000 and 1000 in rep
 
 
@@ -43,4 +58,5 @@ def test_gpu_full_size_configuration_for_1000_steps(name):
     lb = _gpu(g)
     rep = gfu.check_run(g, lb, _types, common.gpu_state)
     lb.close()
+    _record(g, rep)
     assert g.steps == 1000 and 1000 in rep
