@@ -34,7 +34,7 @@ class LbGpuParams(C.Structure):
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuInitBox", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuCountsLocal", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
-           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo")
+           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo", "lbGpuFluidSummary", "lbGpuWriteVti")
 
 _lib = None
 
@@ -104,6 +104,10 @@ def load_library(build_if_missing=True):
     L.lbGpuCommInit.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     L.lbGpuCommInfo.restype = C.c_int
     L.lbGpuCommInfo.argtypes = [C.POINTER(C.c_int32)] * 3
+    L.lbGpuFluidSummary.restype = C.c_int
+    L.lbGpuFluidSummary.argtypes = [vp, C.POINTER(C.c_double * 4)]
+    L.lbGpuWriteVti.restype = C.c_int
+    L.lbGpuWriteVti.argtypes = [vp, C.c_char_p, C.c_int]
     L.lbGpuPeerHalo.restype = C.c_int
     L.lbGpuPeerHalo.argtypes = [vp, C.POINTER(C.c_int32)]
     L.lbGpuCommFinalize.restype = C.c_int

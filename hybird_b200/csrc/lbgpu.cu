@@ -18,7 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <chrono>
 #include <string>
@@ -81,19 +83,61 @@ int copy_threads() {
     }
     return n;
 }
+// a small pool of copy threads, created on first use and kept for the life of the process (spawning threads per 16 MB
+// chunk cost as much as the copy itself)
+struct CopyPool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cvWork, cvDone;
+    uint64_t generation = 0;
+    int pending = 0;
+    char* dst = nullptr; const char* src = nullptr; size_t bytes = 0, per = 0;
+    bool stop = false;
+    void start(int n) {
+        for (int k = 0; k < n; ++k)
+            workers.emplace_back([this, k] {
+                uint64_t seen = 0;
+                for (;;) {
+                    std::unique_lock<std::mutex> lk(m);
+                    cvWork.wait(lk, [&] { return stop || generation != seen; });
+                    if (stop) return;
+                    seen = generation;
+                    char* d = dst; const char* s = src; const size_t n = bytes, p = per;
+                    lk.unlock();
+                    const size_t off = (size_t)(k + 1) * p;
+                    if (off < n) memcpy(d + off, s + off, n - off < p ? n - off : p);
+                    lk.lock();
+                    if (--pending == 0) cvDone.notify_one();
+                }
+            });
+    }
+    void copy(void* d, const void* s, size_t n) {
+        const int T = (int)workers.size() + 1;
+        std::unique_lock<std::mutex> lk(m);
+        dst = (char*)d; src = (const char*)s; bytes = n;
+        per = ((n + T - 1) / T + 4095) / 4096 * 4096;
+        pending = (int)workers.size();
+        ++generation;
+        lk.unlock();
+        cvWork.notify_all();
+        memcpy(d, s, per < n ? per : n);
+        lk.lock();
+        cvDone.wait(lk, [&] { return pending == 0; });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cvWork.notify_all();
+        for (auto& t : workers) t.join();
+    }
+};
 void par_memcpy(void* dst, const void* src, size_t bytes) {
     const int T = copy_threads();
     if (T <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
-    const size_t per = ((bytes + T - 1) / T + 4095) / 4096 * 4096;
-    std::vector<std::thread> th;
-    for (int k = 1; k < T; ++k) {
-        const size_t off = (size_t)k * per;
-        if (off >= bytes) break;
-        const size_t len = bytes - off < per ? bytes - off : per;
-        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
-    }
-    memcpy(dst, src, per < bytes ? per : bytes);
-    for (auto& t : th) t.join();
+    static CopyPool* pool = nullptr;  // never destroyed: worker threads must not be joined from a static destructor at exit
+    static std::mutex poolMutex;
+    std::lock_guard<std::mutex> lk(poolMutex);
+    if (!pool) { pool = new CopyPool(); pool->start(T - 1); }
+    pool->copy(dst, src, bytes);
 }
 
 lb::FastDiv make_div(uint32_t d) {
@@ -153,7 +197,7 @@ struct Slab {
     uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
-    DevBuf<double> partial, sums, scal, elemOut, elemPartial;
+    DevBuf<double> partial, sums, scal, elemOut, elemPartial, summary;
     DevBuf<uint32_t> elemDone;
     DevBuf<unsigned long long> counters;  // [0] nInterface [1..3] k_count scratch
     DevBuf<uint32_t> status;              // [0] type error, [1] flood-fill counter
@@ -1372,6 +1416,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     {
         const bool gx = d.ghost[0], gy = d.ghost[2], gzLocal = perZ && !s->remoteLo;
         std::vector<uint32_t> gd, gs, gp;
+        int cx[Q], cy[Q], cz[Q];  // (cvec() rebuilds its table on every run-time call)
+        for (int j = 0; j < Q; ++j) { cx[j] = CXh(j); cy[j] = CYh(j); cz[j] = CZh(j); }
         auto idx = [&](int x, int y, int z) { return (uint32_t)x + (uint32_t)X * ((uint32_t)y + (uint32_t)Y * (uint32_t)z); };
         for (int z = 0; z < Zl; ++z) {
             const bool zs = (z == 0 || z == Zl - 1);
@@ -1393,7 +1439,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
                     uint32_t pm = 0;
                     for (int j = 1; j < Q; ++j) {
                         // population j is pulled out of this ghost by the cell at ghost + c_j, if that is an interior cell
-                        const int tx = x + CXh(j), ty = y + CYh(j), tz = z + CZh(j);
+                        const int tx = x + cx[j], ty = y + cy[j], tz = z + cz[j];
                         // (across a slab cut the pulling cell is the neighbour slab's: its copy of this plane is taken from here)
                         if (tx >= 1 && tx <= X - 2 && ty >= 1 && ty <= Y - 2 && tz >= (s->remoteLo ? 0 : 1) && tz <= (s->remoteHi ? Zl - 1 : Zl - 2))
                             pm |= 1u << j;
@@ -1963,6 +2009,149 @@ int lbGpuParticleForces(LbGpuHandle* h, double* FHydro, double* MHydro, double* 
     return LBGPU_OK;
 }
 
+}  // extern "C"
+namespace {
+// n and the shifted u of the last step, recomputed from the previous population buffer when the step kernel did not
+// store them (lattices whose streaming never reads them)
+int ensure_macro(LbGpuHandle* h) {
+    if (h->macroValid) return 0;
+    cudaStream_t st = h->stream;
+    for (auto& sp : h->slabs) {
+        Dev dm = dev_for(h, sp.get());
+        set_src(dm, sp.get(), h->cur ^ 1, !h->lastStepFirst);
+        const bool force = h->force || h->lastStepCoupled, couple = h->lastStepCoupled;
+        const uint32_t B = own_blocks(sp.get());
+        if (couple) k_macro<true, true><<<B, BLOCK, 0, st>>>(dm);
+        else if (force) k_macro<true, false><<<B, BLOCK, 0, st>>>(dm);
+        else k_macro<false, false><<<B, BLOCK, 0, st>>>(dm);
+        ++h->launches;
+    }
+    h->macroValid = true;
+    CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int lbGpuFluidSummary(LbGpuHandle* h, double out[4]) {
+    if (!h || !out) return fail(LBGPU_EINVAL, "lbGpuFluidSummary: null argument");
+    CU(cudaSetDevice(h->device));
+    if (int rc = check_status(h)) return rc;
+    if (int rc = ensure_macro(h)) return rc;
+    cudaStream_t st = h->stream;
+    double tot[4] = { 0.0, 0.0, 0.0, 0.0 };
+    for (auto& sp : h->slabs) {
+        Slab* s = sp.get();
+        const uint32_t B = own_blocks(s);
+        if (s->summary.n < (size_t)4 * B + 4) CU(s->summary.alloc((size_t)4 * B + 4));
+        k_summary<<<B, BLOCK, 0, st>>>(dev_for(h, s), s->summary.p + 4, B);
+        k_summary_final<<<1, 1024, 0, st>>>(s->summary.p + 4, B, B, s->summary.p);
+        h->launches += 2;
+        double r[4];
+        CU(cudaMemcpyAsync(r, s->summary.p, sizeof r, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        tot[0] = r[0] > tot[0] ? r[0] : tot[0];
+        for (int k = 1; k < 4; ++k) tot[k] += r[k];
+    }
+    if (lbcomm::active()) {
+        // maximum and sums over the ranks
+        Slab* s0 = h->slabs[0].get();
+        CU(cudaMemcpyAsync(s0->summary.p, tot, sizeof tot, cudaMemcpyHostToDevice, st));
+        NC(lbcomm::api().AllReduce(s0->summary.p, s0->summary.p, 1, lbcomm::ncclFloat64, lbcomm::ncclMax, lbcomm::comm().comm, st));
+        NC(lbcomm::api().AllReduce(s0->summary.p + 1, s0->summary.p + 1, 3, lbcomm::ncclFloat64, lbcomm::ncclSum, lbcomm::comm().comm, st));
+        CU(cudaMemcpyAsync(tot, s0->summary.p, sizeof tot, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    for (int k = 0; k < 4; ++k) out[k] = tot[k];
+    return LBGPU_OK;
+}
+
+// IO::exportParaviewFluidOld (IO.cpp:698-831): the same ImageData file -- extents, origin, spacing, array names, types,
+// order and values -- with the data as raw appended binary instead of 17 M formatted numbers per array.  One field at
+// a time passes through lbGpuFetchFields (which reproduces what the reference holds in dead shell cells), so the
+// host never holds more than the largest array.
+int lbGpuWriteVti(LbGpuHandle* h, const char* path, int withSolidIndex) {
+    if (!h || !path) return fail(LBGPU_EINVAL, "lbGpuWriteVti: null argument");
+    if (lbcomm::active()) return fail(LBGPU_EUNSUPPORTED, "lbGpuWriteVti: one process only (a rank holds its own planes)");
+    const LbGpuParams& prm = h->prm;
+    const size_t N = (size_t)prm.size[0] * prm.size[1] * prm.size[2];
+    if (N * 24 >= (1ull << 32)) return fail(LBGPU_EUNSUPPORTED, "lbGpuWriteVti: arrays of more than 4 GB need 64-bit block headers");
+    const double L = prm.unitLength, T = prm.unitTime, D = prm.unitDensity;
+    const double uSpeed = L / T, uPressure = D * L * L / T / T, uDynVisc = D * L * L / T, uDensity = D;  // node.cpp:476-488
+    struct Arr { const char* name; const char* type; int comps; size_t bytes; };
+    std::vector<Arr> arrs;
+    arrs.push_back({ "type", "Int8", 1, N });
+    arrs.push_back({ "v", "Float64", 3, N * 24 });
+    arrs.push_back({ "pressure", "Float64", 1, N * 8 });
+    if (prm.nonNewtonian) arrs.push_back({ "dynVisc", "Float64", 1, N * 8 });
+    if (prm.freeSurface) arrs.push_back({ "AAAmass", "Float64", 1, N * 8 });
+    if (withSolidIndex) arrs.push_back({ "solidIndex", "Int16", 1, N * 2 });
+    FILE* fp = fopen(path, "wb");
+    if (!fp) return fail(LBGPU_EINVAL, "lbGpuWriteVti: cannot open %s", path);
+    int rc = LBGPU_OK;
+    auto body = [&]() -> int {
+        fprintf(fp, "<VTKFile type=\"ImageData\" version=\"0.1\" byte_order=\"LittleEndian\">\n");
+        fprintf(fp, " <ImageData WholeExtent=\"0 %d 0 %d 0 %d\" Origin=\"0.0 0.0 0.0\" Spacing=\"%g %g %g\">\n", prm.size[0] - 1,
+                prm.size[1] - 1, prm.size[2] - 1, L, L, L);
+        fprintf(fp, "  <Piece Extent=\"0 %d 0 %d 0 %d\">\n   <PointData>\n", prm.size[0] - 1, prm.size[1] - 1, prm.size[2] - 1);
+        size_t off = 0;
+        for (const Arr& a : arrs) {
+            if (a.comps > 1) fprintf(fp, "    <DataArray type=\"%s\" Name=\"%s\" NumberOfComponents=\"%d\" format=\"appended\" offset=\"%zu\"/>\n", a.type, a.name, a.comps, off);
+            else fprintf(fp, "    <DataArray type=\"%s\" Name=\"%s\" format=\"appended\" offset=\"%zu\"/>\n", a.type, a.name, off);
+            off += 4 + a.bytes;
+        }
+        fprintf(fp, "   </PointData>\n   <CellData>\n   </CellData>\n  </Piece>\n </ImageData>\n <AppendedData encoding=\"raw\">\n_");
+        std::vector<uint8_t> tf(N);
+        std::vector<double> buf;
+        auto block = [&](const void* data, size_t bytes) -> int {
+            const uint32_t nb = (uint32_t)bytes;
+            if (fwrite(&nb, 4, 1, fp) != 1 || fwrite(data, 1, bytes, fp) != bytes) return fail(LBGPU_EINVAL, "lbGpuWriteVti: write to %s failed", path);
+            return 0;
+        };
+        int r;
+        // type: nodeType::getType, 1 inside particles (IO.cpp:726-733)
+        if ((r = lbGpuFetchFields(h, tf.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))) return r;
+        {
+            std::vector<int8_t> t8(N);
+            for (size_t i = 0; i < N; ++i) t8[i] = (tf[i] & LBGPU_P_BIT) ? (int8_t)1 : (int8_t)(tf[i] & LBGPU_TYPE_MASK);
+            if ((r = block(t8.data(), N))) return r;
+        }
+        // v = u * unit.Speed where a node exists (IO.cpp:746-754): lbGpuFetchFields returns zeros elsewhere
+        buf.resize(3 * N);
+        if ((r = lbGpuFetchFields(h, nullptr, nullptr, nullptr, buf.data(), nullptr, nullptr, nullptr, nullptr, nullptr))) return r;
+        for (size_t k = 0; k < 3 * N; ++k) buf[k] *= uSpeed;
+        if ((r = block(buf.data(), N * 24))) return r;
+        // pressure = 0.3333333 (n - 1) unit.Pressure where a node exists and n != 0 (IO.cpp:768-781)
+        buf.resize(N);
+        if ((r = lbGpuFetchFields(h, nullptr, nullptr, buf.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))) return r;
+        for (size_t i = 0; i < N; ++i)
+            if ((tf[i] & LBGPU_NODE_BIT) && buf[i] != 0.0) buf[i] = 0.3333333 * (buf[i] - 1.0) * uPressure;
+        if ((r = block(buf.data(), N * 8))) return r;
+        if (prm.nonNewtonian) {
+            if ((r = lbGpuFetchFields(h, nullptr, nullptr, nullptr, nullptr, nullptr, buf.data(), nullptr, nullptr, nullptr))) return r;
+            for (size_t i = 0; i < N; ++i) buf[i] *= uDynVisc;
+            if ((r = block(buf.data(), N * 8))) return r;
+        }
+        if (prm.freeSurface) {
+            if ((r = lbGpuFetchFields(h, nullptr, nullptr, nullptr, nullptr, buf.data(), nullptr, nullptr, nullptr, nullptr))) return r;
+            for (size_t i = 0; i < N; ++i) buf[i] *= uDensity;
+            if ((r = block(buf.data(), N * 8))) return r;
+        }
+        if (withSolidIndex) {
+            std::vector<uint32_t> si(N);
+            if ((r = lbGpuFetchFields(h, nullptr, si.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr))) return r;
+            std::vector<int16_t> s16(N);
+            for (size_t i = 0; i < N; ++i) s16[i] = (int16_t)si[i];
+            if ((r = block(s16.data(), N * 2))) return r;
+        }
+        fprintf(fp, "\n </AppendedData>\n</VTKFile>\n");
+        return 0;
+    };
+    rc = body();
+    if (fclose(fp) != 0 && rc == 0) rc = fail(LBGPU_EINVAL, "lbGpuWriteVti: closing %s failed", path);
+    return rc;
+}
+
 int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, double* n, double* u, double* mass,
                      double* visc, double* shearRate, double* hydroForce, double* f) {
     if (!h) return fail(LBGPU_EINVAL, "null handle");
@@ -1971,20 +2160,7 @@ int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, 
     Trace tr("lbGpuFetchFields");
     cudaStream_t st = h->stream;
     const int zLoHost = h->slabs[0]->zBegin - 1;
-    if (!h->macroValid && (n || u)) {
-        // n and the shifted u of the last step, recomputed from the previous population buffer
-        for (auto& sp : h->slabs) {
-            Dev dm = dev_for(h, sp.get());
-            set_src(dm, sp.get(), h->cur ^ 1, !h->lastStepFirst);
-            const bool force = h->force || h->lastStepCoupled, couple = h->lastStepCoupled;
-            const uint32_t B = own_blocks(sp.get());
-            if (couple) k_macro<true, true><<<B, BLOCK, 0, st>>>(dm);
-            else if (force) k_macro<true, false><<<B, BLOCK, 0, st>>>(dm);
-            else k_macro<false, false><<<B, BLOCK, 0, st>>>(dm);
-            ++h->launches;
-        }
-        h->macroValid = true;
-    }
+    if (n || u) { if (int rc = ensure_macro(h)) return rc; }
     for (auto& sp : h->slabs) {
         Slab* s = sp.get();
         const uint32_t B = s->blocks;

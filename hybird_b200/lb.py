@@ -206,6 +206,18 @@ class LB:
         abi.check(self.lib.lbGpuFetchFields(self.h, *[abi.ptr(out.get(k)) for k in order]))
         return out
 
+    # -- IO's screen export and fluid file without a full-field fetch (IO.cpp:698-895, 969-999) ------------
+    def summary(self):
+        """max |u| (lattice units), total fluid mass outside particles, active cells, per cent plastic."""
+        o = (C.c_double * 4)()
+        abi.check(self.lib.lbGpuFluidSummary(self.h, C.byref(o)))
+        act = float(o[2])
+        return dict(max_speed=float(o[0]) ** 0.5, mass=float(o[1]), active=int(act),
+                    plastic_pct=100.0 * float(o[3]) / act if act else float("nan"))
+
+    def write_vti(self, path, dem_solve=True):
+        abi.check(self.lib.lbGpuWriteVti(self.h, str(path).encode(), int(bool(dem_solve))))
+
     # -- checkpoint / restart (no counterpart in the reference) --------------------------------------
     def save_state(self) -> np.ndarray:
         n = C.c_uint64()

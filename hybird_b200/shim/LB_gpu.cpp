@@ -10,10 +10,24 @@
 //   LB::latticeBoltzmannFreeSurfaceStep  records the request                       (LB.cpp:235-245)
 //   LB::latticeBoltzmannCouplingStep   packs particles/elements, resets the flag   (LB.cpp:247-280)
 //   LB::latticeBolzmannStep            lbGpuStep + lbGpuParticleForces -> elmts[].FHydro/MHydro/fluidVolume,
-//                                      walls[].FHydro; refreshes the host mirrors IO reads when an export is due
+//                                      walls[].FHydro
 //
-// LBGPU_VERIFY=1 additionally runs the reference's own step on the host state every cycle and compares the fields
-// (integration check; the forces handed to DEM are always the device's).
+// The output path.  IO reads the fluid through lb.types / lb.nodes; the four members that walk
+// the whole lattice are made weak in IO.o (objcopy --weaken-symbol, see Makefile) and defined here on top of the device:
+//
+//   IO::exportMaxSpeedFluid, IO::exportTotalMass, IO::exportPlasticity   lbGpuFluidSummary (one device reduction; same
+//                                      text on cout / export.dat / maxFluidSpeed.dat / plasticity.dat)   IO.cpp:835-895
+//   IO::exportParaviewFluidOld         lbGpuWriteVti: the same .vti (names, types, order, values) with raw appended data
+//                                      instead of formatted text                                          IO.cpp:698-831
+//
+// so an export costs a reduction (screen) or one selective field fetch per array (fluid file) instead of a fetch of
+// every field plus a rebuild of the host node lists.  Only the problem-specific screen exports that read the fluid
+// themselves (DRUM: exportDrum, SHEARCELL: exportShearCell) still get refreshed host mirrors.
+//
+// Built twice (Makefile): hybird_gpu -- the product: no reference LB step is linked (unreferenced reference functions are
+// dropped by --gc-sections); hybird_gpu_verify -- compiled with LBGPU_SHIM_VERIFY: LBGPU_VERIFY=1 additionally runs the
+// reference's own step on the host state every cycle and compares the fields (integration check; the forces handed
+// to DEM are always the device's).
 // Built with -fno-access-control like the oracle harness: LB's members are "public: //private" (LB.h:36) but
 // nodeType's are private.
 #include "../../include/lbgpu.h"
@@ -26,13 +40,16 @@
 #include <vector>
 
 #include "LB.h"
+#include "IO.h"
 
 extern "C" {
 void LB_ref_latticeBoltzmannGet(LB*, GetPot&, GetPot&);
 void LB_ref_latticeBolzmannInit(LB*, cylinderList&, wallList&, particleList&, objectList&);
+#ifdef LBGPU_SHIM_VERIFY
 void LB_ref_latticeBolzmannStep(LB*, elmtList&, particleList&, wallList&);
 void LB_ref_latticeBoltzmannCouplingStep(LB*, bool&, elmtList&, particleList&);
 void LB_ref_latticeBoltzmannFreeSurfaceStep(LB*);
+#endif
 }
 
 namespace {
@@ -45,7 +62,7 @@ struct GpuState {
     std::vector<uint32_t> comps;
     double screenExpTime = 0.0, fluidExpTime = 0.0;
     unsigned int lastScreenExp = 0, lastFluidExp = 0;
-    unsigned long long steps = 0, fetches = 0;
+    unsigned long long steps = 0, fetches = 0, summaries = 0, vtis = 0;
     double worst = 0.0;
     // fetch buffers
     std::vector<uint8_t> tf;
@@ -141,6 +158,7 @@ bool export_due(LB* lb, GpuState& st) {
     return due;
 }
 
+#ifdef LBGPU_SHIM_VERIFY
 double rel_diff(double a, double b) {
     const double s = fmax(fabs(a), fabs(b));
     return s > 0 ? fabs(a - b) / s : 0.0;
@@ -174,6 +192,12 @@ void verify_against_host(LB* lb, GpuState& st, const std::vector<tVect>& refF, e
          << ", max rel FHydro diff " << fWorst << endl;
     if (typeDiff != 0 || worst > 1e-9 || fWorst > 1e-9) { cout << "lbgpu verify: FAILED" << endl; exit(2); }
 }
+#endif
+
+// the screen exports of these problems read lb.nodes themselves (IO::exportDrum, IO::exportShearCell)
+bool needs_host_mirrors() { return problemName == DRUM || problemName == SHEARCELL; }
+
+GpuState& state_of(const LB& lb) { return states()[const_cast<LB*>(&lb)]; }
 
 }  // namespace
 
@@ -185,8 +209,13 @@ void LB::latticeBoltzmannGet(GetPot& lbmCfgFile, GetPot& command_line) {
     if (command_line.search("-screenExpTime")) st.screenExpTime = command_line.next(st.screenExpTime);
     st.fluidExpTime = lbmCfgFile("fluidExpTime", 0.0);
     if (command_line.search("-fluidExpTime")) st.fluidExpTime = command_line.next(st.fluidExpTime);
+#ifdef LBGPU_SHIM_VERIFY
     const char* v = getenv("LBGPU_VERIFY");
     st.verify = v && v[0] == '1';
+#else
+    if (const char* v = getenv("LBGPU_VERIFY"))
+        if (v[0] == '1') { cout << "lbgpu shim: LBGPU_VERIFY needs the hybird_gpu_verify binary (this one links no reference LB step)" << endl; exit(1); }
+#endif
 }
 
 void LB::latticeBolzmannInit(cylinderList& cylinders, wallList& walls, particleList& particles, objectList& objects) {
@@ -238,12 +267,16 @@ void LB::latticeBolzmannInit(cylinderList& cylinders, wallList& walls, particleL
 void LB::latticeBoltzmannFreeSurfaceStep() {
     GpuState& st = states()[this];
     st.fsRequested = true;
+#ifdef LBGPU_SHIM_VERIFY
     if (st.verify) LB_ref_latticeBoltzmannFreeSurfaceStep(this);
+#endif
 }
 
 void LB::latticeBoltzmannCouplingStep(bool& newNeighborList, elmtList& elmts, particleList& particles) {
     GpuState& st = states()[this];
+#ifdef LBGPU_SHIM_VERIFY
     if (st.verify) { bool flag = newNeighborList; LB_ref_latticeBoltzmannCouplingStep(this, flag, elmts, particles); }
+#endif
     if (st.couplePending) {
         // the previous cycle coupled without stepping the fluid (demTime <= demInitialRepeat, hybird.cpp:60-64)
         if (lbGpuCouple(st.h, st.rescan, st.parts.data(), (uint32_t)st.parts.size(), st.elmts.data(), (uint32_t)st.elmts.size(),
@@ -258,6 +291,7 @@ void LB::latticeBoltzmannCouplingStep(bool& newNeighborList, elmtList& elmts, pa
 
 void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList& walls) {
     GpuState& st = states()[this];
+#ifdef LBGPU_SHIM_VERIFY
     std::vector<tVect> refF;
     if (st.verify) {
         elmtList refElmts(elmts);  // elmt has const members: copy-construct, never assign
@@ -265,6 +299,7 @@ void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList&
         LB_ref_latticeBolzmannStep(this, refElmts, particles, refWalls);
         for (size_t e = 0; e < refElmts.size(); ++e) refF.push_back(refElmts[e].FHydro);
     }
+#endif
     if (!st.couplePending) pack(st, elmts, particles);  // computeHydroForces reads the lists it is given (LB.cpp:1851)
     if (lbGpuStep(st.h, st.fsRequested ? 1 : 0, st.couplePending ? 1 : 0, st.rescan ? 1 : 0, st.parts.data(), (uint32_t)st.parts.size(),
                   st.elmts.data(), (uint32_t)st.elmts.size(), st.comps.data(), (uint32_t)st.comps.size()))
@@ -280,6 +315,56 @@ void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList&
         elmts[e].fluidVolume = V[e];
     }
     for (size_t w = 0; w < nW; ++w) walls[w].FHydro = tVect(W[3 * w], W[3 * w + 1], W[3 * w + 2]);
-    if (st.verify) verify_against_host(this, st, refF, elmts);
-    else if (export_due(this, st)) refresh_mirrors(this, st);
+#ifdef LBGPU_SHIM_VERIFY
+    if (st.verify) { verify_against_host(this, st, refF, elmts); return; }
+#endif
+    if (needs_host_mirrors() && export_due(this, st)) refresh_mirrors(this, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// IO's whole-lattice walks, served by the device (weak in IO.o, see the header comment)
+// ---------------------------------------------------------------------------------------------
+namespace {
+void summary_of(const LB& lb, double out[4]) {
+    GpuState& st = state_of(lb);
+    if (!st.h) { out[0] = out[1] = out[2] = out[3] = 0.0; return; }
+    if (lbGpuFluidSummary(st.h, out)) die("lbGpuFluidSummary");
+    ++st.summaries;
+}
+}  // namespace
+
+void IO::exportMaxSpeedFluid(const LB& lb) {  // IO.cpp:835-851
+    double s[4];
+    summary_of(lb, s);
+    const double maxFluidSpeed = sqrt(s[0]);
+    cout << "MaxFSpeed= " << maxFluidSpeed * lb.unit.Speed << "(" << int(lbmDt * lbmDt * maxFluidSpeed * 100.0 / 0.01) << "%)\t";
+    exportFile << "MaxFSpeed= " << maxFluidSpeed * lb.unit.Speed << "(" << int(lbmDt * lbmDt * maxFluidSpeed * 100.0 / 0.01) << "%)\t";
+    maxSpeedFile.open(maxSpeedFileName.c_str(), ios::app);
+    maxSpeedFile << realTime << " " << maxFluidSpeed * lb.unit.Speed << "\n";
+    maxSpeedFile.close();
+}
+
+void IO::exportTotalMass(const LB& lb) {  // IO.cpp:878-883, 987-999
+    double s[4] = { 0.0, 0.0, 0.0, 0.0 };
+    if (lbmSolve) summary_of(lb, s);
+    const double massTot = s[1];
+    cout << "Volume=" << massTot * lb.unit.Volume << "; Mass = " << massTot * lb.unit.Mass << "\t";
+    exportFile << "Volume=" << massTot * lb.unit.Volume << "; Mass = " << massTot * lb.unit.Mass << "\t";
+}
+
+void IO::exportPlasticity(const LB& lb) {  // IO.cpp:885-895, 969-985
+    double s[4];
+    summary_of(lb, s);
+    const double percPlastic = 100.0 * double((unsigned int)s[3]) / double((unsigned int)s[2]);
+    cout << "Plastic =" << int(percPlastic) << "%;\t";
+    exportFile << "Plastic =" << int(percPlastic) << "%;\t";
+    plasticityFile.open(plasticityFileName.c_str(), ios::app);
+    plasticityFile << realTime << " " << percPlastic << "\n";
+    plasticityFile.close();
+}
+
+void IO::exportParaviewFluidOld(const LB& lb, const string& fluidFile) {  // IO.cpp:698-831
+    GpuState& st = state_of(lb);
+    if (lbGpuWriteVti(st.h, fluidFile.c_str(), demSolve ? 1 : 0)) die("lbGpuWriteVti");
+    ++st.vtis;
 }

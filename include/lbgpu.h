@@ -165,6 +165,18 @@ int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHy
 int lbGpuFetchFields(LbGpuHandle* h, uint8_t* type_flags, uint32_t* solidIndex, double* n, double* u, double* mass,
                      double* visc, double* shearRate, double* hydroForce, double* f);
 
+/* Output path.
+ * lbGpuFluidSummary: what IO's screen export derives from the whole lattice, as one device reduction instead of a
+ * full-field fetch: out[0] = max |u|^2 over the active cells (IO::exportMaxSpeedFluid, IO.cpp:835-851; lattice units,
+ * the caller takes the root), out[1] = sum of mass over the active cells outside particles (IO::totFluidMass,
+ * IO.cpp:987-999), out[2] = active cells, out[3] = active cells with visc > 0.95 maxVisc (IO::totPlastic,
+ * IO.cpp:969-985).  Over all ranks of the communicator.
+ * lbGpuWriteVti: the file of IO::exportParaviewFluidOld (IO.cpp:698-831) -- same extents, spacing, array names
+ * (type, v, pressure, dynVisc, AAAmass, solidIndex), types, order and values in physical units -- with the data as raw
+ * appended binary instead of formatted text.  withSolidIndex = IO::demSolve.  One process. */
+int lbGpuFluidSummary(LbGpuHandle* h, double out[4]);
+int lbGpuWriteVti(LbGpuHandle* h, const char* path, int withSolidIndex);
+
 /* Checkpoint / restart of the fluid state (the reference has none: SURVEY.md 5; DEM's recycle file covers the particles,
  * IO.cpp:486-535).  The blob holds the dynamic device state (populations, types, macroscopic fields, masses, resident
  * particle lists, step counter); it is loaded into a handle created by lbGpuInit with the SAME parameters and wall

@@ -68,3 +68,22 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(root, f)).read()
                 assert "lbo" not in re.findall(r"^\s*(?:import|from)\s+(\w+)", txt, flags=re.M), f
                 assert "liblboracle" not in txt and "lb_oracle" not in txt, f
+
+
+def test_product_shim_links_no_reference_lb_step():
+    """hybird_gpu (the drop-in driver) must not carry the reference's own LB time step: only its set-up
+    (latticeBoltzmannGet / latticeBolzmannInit and what they call) stays linked; the verify binary has both."""
+    shim = os.path.join(common.ROOT, "hybird_b200", "shim", "_build")
+    prod, ver = os.path.join(shim, "hybird_gpu"), os.path.join(shim, "hybird_gpu_verify")
+    if not (os.path.exists(prod) and os.path.exists(ver)):
+        pytest.skip("shim binaries not built (needs the reference sources)")
+    step = re.compile(r" [Tt] (LB::(streaming|collision|reconstruction|computeHydroForces|updateMass|updateInterface|"
+                      r"findInterfaceMutants|smoothenInterface|removeIsolated|findNewActive|findNewSolid)\(|LB_ref_latticeBolzmannStep|"
+                      r"LB_ref_latticeBoltzmannCouplingStep|LB_ref_latticeBoltzmannFreeSurfaceStep)")
+    def syms(p):
+        return subprocess.run(["nm", "-C", p], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert not step.findall(syms(prod)), "the product binary links the reference's LB step"
+    assert step.findall(syms(ver)), "the verify binary should step the reference alongside"
+    # IO's whole-lattice walks bind to the shim's device-backed versions in both
+    for p in (prod, ver):
+        assert "lbGpuFluidSummary" in syms(p) and "lbGpuWriteVti" in syms(p)

@@ -4,9 +4,12 @@ reference is.  Both binaries are built in the build container (make -C hybird_b2
 travel to the GPU box; nothing here reads /root/reference.
 
 (1) the shipped configuration's physics (cfg1: demChute free surface + Smagorinsky) run through both
-    drivers gives the same console/export.dat lines and the same ParaView fluid files;
-(2) LBGPU_VERIFY=1 makes the shim step the reference's own LB on the host next to the device every cycle, with the
-    reference's DEM in the loop, and compare cell types, fields and particle forces (exit code 2 on a mismatch)."""
+    drivers gives the same console/export.dat lines and the same ParaView fluid files -- the shim serves IO's
+    whole-lattice walks from the device (lbGpuFluidSummary, lbGpuWriteVti: raw appended data instead of text), so the
+    files are compared array by array;
+(2) hybird_gpu_verify with LBGPU_VERIFY=1 steps the reference's own LB on the host next to the device every cycle,
+    with the reference's DEM in the loop, and compares cell types, fields and particle forces (exit code 2 on a
+    mismatch).  The product binary hybird_gpu links no reference LB step at all (tests/test_abi.py)."""
 import os
 import re
 import subprocess
@@ -21,11 +24,12 @@ import cases
 pytestmark = pytest.mark.gpu
 BUILD = os.path.join(common.ROOT, "hybird_b200", "shim", "_build")
 GPU_BIN, REF_BIN = os.path.join(BUILD, "hybird_gpu"), os.path.join(BUILD, "hybird_ref")
+VERIFY_BIN = os.path.join(BUILD, "hybird_gpu_verify")
 NUM = re.compile(r"[-+]?(?:\d+\.?\d*|\.\d+)(?:[eE][-+]?\d+)?")
 
 
 def _need_binaries():
-    if not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN)):
+    if not (os.path.exists(GPU_BIN) and os.path.exists(REF_BIN) and os.path.exists(VERIFY_BIN)):
         pytest.skip("shim binaries not built (make -C hybird_b200/shim needs the reference sources)")
 
 
@@ -40,6 +44,31 @@ def _run(binary, cfg, outdir, env=None, threads=None):
 
 def _numbers(text):
     return np.array([float(x) for x in NUM.findall(text)])
+
+
+VTK_DTYPES = {"Int8": np.int8, "Int16": np.int16, "Float64": np.float64}
+
+
+def read_vti(path):
+    """{name: array} + header attributes of an ImageData file with ascii (the reference's) or raw appended (lbGpuWriteVti)
+    DataArrays."""
+    raw = open(path, "rb").read()
+    head_end = raw.find(b"<AppendedData")
+    xml = raw[:head_end if head_end >= 0 else len(raw)].decode()
+    meta = dict(extent=re.search(r'WholeExtent="([^"]*)"', xml).group(1), spacing=[float(v) for v in re.search(r'Spacing="([^"]*)"', xml).group(1).split()])
+    out, order = {}, []
+    base = raw.find(b"_", head_end) + 1 if head_end >= 0 else None
+    for m in re.finditer(r'<DataArray ([^>]*?)(/>|>(.*?)</DataArray>)', xml, flags=re.S):
+        attrs = dict(re.findall(r'(\w+)="([^"]*)"', m.group(1)))
+        dt = VTK_DTYPES[attrs["type"]]
+        order.append((attrs["Name"], attrs["type"], int(attrs.get("NumberOfComponents", 1))))
+        if attrs.get("format") == "appended":
+            off = base + int(attrs["offset"])
+            nb = int(np.frombuffer(raw, "<u4", 1, off)[0])
+            out[attrs["Name"]] = np.frombuffer(raw, dt, nb // np.dtype(dt).itemsize, off + 4).astype(np.float64)
+        else:
+            out[attrs["Name"]] = np.array(m.group(3).split(), dtype=np.float64)
+    return meta, order, out
 
 
 def test_shipped_config_through_both_drivers(tmp_path):
@@ -64,12 +93,17 @@ def test_shipped_config_through_both_drivers(tmp_path):
     fg = sorted(os.listdir(tmp_path / "gpu" / "run" / "fluidData"))
     assert fr == fg and len(fr) >= 2
     for name in fr:
-        tr = open(tmp_path / "ref" / "run" / "fluidData" / name).read()
-        tg = open(tmp_path / "gpu" / "run" / "fluidData" / name).read()
-        a, b = _numbers(tr), _numbers(tg)
-        assert a.shape == b.shape, name
-        # printed with 6 digits: a last-digit flip of a rounded value is the most that can differ
-        assert np.allclose(a, b, rtol=2e-5, atol=1e-12), (name, np.abs(a - b).max())
+        mr, orr, ar = read_vti(tmp_path / "ref" / "run" / "fluidData" / name)
+        mg, org, ag = read_vti(tmp_path / "gpu" / "run" / "fluidData" / name)
+        assert mr["extent"] == mg["extent"] and np.allclose(mr["spacing"], mg["spacing"], rtol=1e-6)
+        assert orr == org, (orr, org)  # same arrays, types, components, order
+        for k in ar:
+            a, b = ar[k], ag[k]
+            assert a.shape == b.shape, (name, k)
+            # the reference prints 6 digits: a last-digit flip of a rounded value is the most that can differ
+            assert np.allclose(a, b, rtol=2e-5, atol=1e-12), (name, k, np.abs(a - b).max())
+    # no export step fetched the whole state: the screen lines came from device reductions
+    assert os.path.getsize(tmp_path / "gpu" / "run" / "maxVel.dat") > 0
 
 
 @pytest.mark.parametrize("name,steps", [("cfg3_mini", 60), ("cluster_dem", 40), ("cfg1_mini", 60), ("drum_mini", 150)])
@@ -78,7 +112,7 @@ def test_verify_mode_reference_steps_alongside(name, steps, tmp_path):
     case = dict(cases.catalogue()[name])
     case.update(maximumTimeSteps=steps)
     cfg = cases.write_case_files(case, str(tmp_path))
-    rc, out = _run(GPU_BIN, cfg, str(tmp_path / "gpu"), env={"LBGPU_VERIFY": "1"}, threads=1)
+    rc, out = _run(VERIFY_BIN, cfg, str(tmp_path / "gpu"), env={"LBGPU_VERIFY": "1"}, threads=1)
     assert rc == 0, out[-3000:]
     lines = [l for l in out.splitlines() if l.startswith("lbgpu verify: step")]
     assert len(lines) == steps, out[-2000:]
