@@ -192,7 +192,7 @@ struct Slab {
     // free surface: the interface-cell list and the list of tiles the step kernel visits (lb_kernels.cuh, k_list_*);
     // listCounts = {interface cells, tiles, interface cells before clamping to the capacity}
     DevBuf<uint8_t> tileFlags;
-    DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset, candList, candOwned, candBlockCount;
+    DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset, candList, candBlockCount;
     uint32_t candCap = 0;
     uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
@@ -860,10 +860,12 @@ int build_lists(LbGpuHandle* h) {
         {   // candidates of the update: owners decided on the (identical) pre-update copy of the types
             Dev d = dev_for(h, s);
             d.typeOld = s->tbuf(1);
-            k_cand_count<<<s->listGrid, BLOCK, 0, st>>>(d, s->candOwned.p, s->candBlockCount.p);
-            k_cand_offsets<<<1, 1024, 0, st>>>(d, s->candBlockCount.p, s->listCounts.p, s->candCap);
-            k_cand_write<<<s->listGrid, BLOCK, 0, st>>>(d, s->candOwned.p, s->candBlockCount.p, s->candList.p, s->candCap, s->tileFlags.p);
-            h->launches += 3;
+            const uint32_t groups = (s->N + 15u) / 16u, gb = (groups + BLOCK - 1) / BLOCK;
+            k_cand_mark<<<s->listGrid, BLOCK, 0, st>>>(d, s->mark.p, s->tileFlags.p);
+            k_plist_count<<<gb, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, nullptr, MARK_CAND);
+            k_list_offsets<<<1, 1024, 0, st>>>(s->candBlockCount.p, gb, s->listCounts.p, 3, s->candCap);
+            k_plist_write<<<gb, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, s->candList.p, s->candCap, nullptr, MARK_CAND);
+            h->launches += 4;
         }
         k_tile_count<<<tb, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p);
         k_list_offsets<<<1, 1024, 0, st>>>(s->listTileOffset.p, tb, s->listCounts.p, 1, nT);
@@ -881,7 +883,7 @@ int free_surface_step(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     int rc;
     if ((rc = build_lists(h))) return rc;
-    // candidate ownership (lb_kernels.cuh, candidate_cell) is decided on the types of before this update: tbuf(1)
+    // the kernels of the update see the types of before it in typeOld: tbuf(1)
     auto fsdev = [&](Slab* s) {
         Dev d = dev_for(h, s);
         d.typeOld = s->tbuf(1);
@@ -1014,10 +1016,10 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             const uint32_t* gate = gateSlot >= 0 ? s->status.p + gateSlot : nullptr;
-            k_plist_count<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, gate);
+            k_plist_count<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, gate, P_BIT);
             if (gateSlot < 0) k_list_offsets<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap);
             else k_list_offsets_gated<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap, gate);
-            k_plist_write<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, s->pList.p, s->pCap, gate);
+            k_plist_write<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, s->pList.p, s->pCap, gate, P_BIT);
             h->launches += 3;
         }
         return 0;
@@ -1358,8 +1360,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
         // capacities: the interface is a sheet; a lattice where more than 1 cell in 8 is an interface cell is refused
         s->cellCap = N / 8 + 1024;
         s->candCap = 4 * s->cellCap;
-        CU(s->candList.alloc(s->candCap)); CU(s->candOwned.alloc((size_t)Q * s->cellCap));
-        CU(s->candBlockCount.alloc(((size_t)Q * s->cellCap + BLOCK - 1) / BLOCK + 1));
+        CU(s->candList.alloc(s->candCap));
+        CU(s->candBlockCount.alloc((((size_t)N + 15) / 16 + BLOCK - 1) / BLOCK + 1));
         CU(s->tileFlags.alloc((size_t)s->listBlocks * LIST_TILES * TILES_PER_BLOCK + 16)); CU(s->tileList.alloc((size_t)s->blocks * TILES_PER_BLOCK)); CU(s->cellList.alloc(s->cellCap));
         CU(s->listCounts.alloc(8)); CU(s->listBlockCount.alloc(s->listBlocks)); CU(s->listTileOffset.alloc(((size_t)s->blocks * TILES_PER_BLOCK + BLOCK - 1) / BLOCK + 1));
         CU(cudaMemsetAsync(s->listCounts.p, 0, 8 * sizeof(uint32_t), st));
