@@ -223,7 +223,7 @@ struct Slab {
 // proxy thread, no rendezvous: the sender knows the destination is free because it has itself received the
 // neighbour's flag of the previous step, which the neighbour raises after its last read of that ghost plane.
 // ---------------------------------------------------------------------------------------------
-enum PeerBuf { PB_FA, PB_FB, PB_N, PB_UX, PB_UY, PB_UZ, PB_VISC, PB_HFX, PB_HFY, PB_HFZ, PB_FLAGS, PB_COUNT };
+enum PeerBuf { PB_FA, PB_FB, PB_N, PB_UX, PB_UY, PB_UZ, PB_VISC, PB_HFX, PB_HFY, PB_HFZ, PB_TYPE, PB_MARK, PB_SOLID, PB_MASS, PB_FLAGS, PB_COUNT };
 struct PeerExport {  // what a rank tells the others about one of its edge slabs (side 0: first slab, 1: last slab)
     cudaIpcMemHandle_t handle[PB_COUNT];
     unsigned long long offset[PB_COUNT];
@@ -240,6 +240,9 @@ struct PutPlan {  // one launch of k_put_halo: plane copies into peer memory + t
     uint32_t* flagDst[2];
     uint32_t* counter;
     uint32_t chunk;
+    // in-cycle exchanges (k_xput): the receiver must have reached the exchange before its ghost planes are overwritten
+    uint32_t* readyDst[2];          // where we tell each neighbour "my stream is here" ...
+    const uint32_t* readyLocal[2];  // ... and where they tell us
 };
 struct PeerHalo {
     bool on = false;
@@ -247,10 +250,15 @@ struct PeerHalo {
     char* nb[2][PB_COUNT] = {};          // [0] neighbour below (its LAST slab), [1] neighbour above (its FIRST slab)
     PeerExport nbInfo[2];
     std::vector<std::pair<cudaIpcMemHandle_t, void*>> opened;
-    DevBuf<uint32_t> flags;              // [0] raised by the rank below, [1] by the rank above, [8] block counter of the put kernel
-    uint32_t seq = 0;
+    // flag words: [0] step halo landed from the rank below, [1] from the rank above; in-cycle exchanges: [2]/[3] the rank
+    // below / above has reached exchange number x ("ready"), [4]/[5] its planes of exchange x have landed ("done");
+    // [8], [9] block counters of the two put kernels
+    DevBuf<uint32_t> flags;
+    uint32_t seq = 0, xseq = 0;
     PutPlan plan[2];
     uint32_t planWhat[2] = { 0, 0 };
+    std::vector<std::pair<uint64_t, PutPlan>> xplans;  // in-cycle exchanges, by (fields, population buffer)
+    bool inCycle = true;                 // in-cycle exchanges through peer memory too (LBGPU_PEER_CYCLE=0: NCCL)
 };
 
 __global__ void __launch_bounds__(128) k_put_halo(const __grid_constant__ PutPlan pl, uint32_t seq) {
@@ -297,6 +305,58 @@ __global__ void k_wait_halo(volatile uint32_t* flags, uint32_t seq, int needDown
         if (t1 - t0 > 20000000000ull) { atomicExch(&status[3], 1u + (uint32_t)k); return; }  // 20 s: the neighbour is gone
     }
     __threadfence_system();
+}
+
+// In-cycle exchange through peer memory (type / mark / mass / ... planes between the passes of the free-surface update
+// and of the particle-flag flood fill; the same planes ncclSend/ncclRecv would carry, in one launch).  Unlike the step
+// halo these arrays are not double-buffered, so the receiver's earlier kernels may still be reading the ghost planes:
+// block 0 first tells both neighbours that this rank's stream has reached exchange `seq` (every earlier kernel of the
+// stream has completed), every block then waits until the neighbours have said the same, copies its chunk, and the
+// last block raises the neighbours' "done" words; k_wait_halo on the done words completes the exchange.
+__global__ void __launch_bounds__(128) k_xput(const __grid_constant__ PutPlan pl, uint32_t seq, uint32_t* status) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2 && pl.readyDst[threadIdx.x]) {
+        *(volatile uint32_t*)pl.readyDst[threadIdx.x] = seq;
+        __threadfence_system();
+    }
+    if (threadIdx.x < 2 && pl.readyLocal[threadIdx.x]) {
+        const volatile uint32_t* f = pl.readyLocal[threadIdx.x];
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(*f - seq) < 0) {
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) { atomicExch(&status[3], 3u); break; }
+        }
+    }
+    __syncthreads();
+    const int e = blockIdx.y;
+    const size_t begin = (size_t)blockIdx.x * pl.chunk;
+    const uint32_t bytes = pl.bytes[e];
+    if (begin < bytes) {
+        const size_t len = bytes - begin < pl.chunk ? bytes - begin : pl.chunk;
+        const char* s = pl.src[e] + begin;
+        char* d = pl.dst[e] + begin;
+        if ((((uintptr_t)s | (uintptr_t)d | len) & 15) == 0) {
+            const uint4* s4 = (const uint4*)s; uint4* d4 = (uint4*)d;
+            for (size_t k = threadIdx.x; k < len / 16; k += blockDim.x) d4[k] = s4[k];
+        } else if ((((uintptr_t)s | (uintptr_t)d | len) & 3) == 0) {
+            const uint32_t* s1 = (const uint32_t*)s; uint32_t* d1 = (uint32_t*)d;
+            for (size_t k = threadIdx.x; k < len / 4; k += blockDim.x) d1[k] = s1[k];
+        } else {
+            for (size_t k = threadIdx.x; k < len; k += blockDim.x) d[k] = s[k];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t total = gridDim.x * gridDim.y;
+        if (atomicAdd(pl.counter, 1u) == total - 1) {
+            *pl.counter = 0;
+            __threadfence_system();
+            for (int k = 0; k < 2; ++k)
+                if (pl.flagDst[k]) *(volatile uint32_t*)pl.flagDst[k] = seq;
+        }
+    }
 }
 
 }  // namespace
@@ -612,6 +672,7 @@ void* peer_buf_ptr(Slab* s, int b, LbGpuHandle* h) {
         case PB_FA: return s->fA.p; case PB_FB: return s->fB.p; case PB_N: return s->n.p;
         case PB_UX: return s->ux.p; case PB_UY: return s->uy.p; case PB_UZ: return s->uz.p;
         case PB_VISC: return s->visc.p; case PB_HFX: return s->hfx.p; case PB_HFY: return s->hfy.p; case PB_HFZ: return s->hfz.p;
+        case PB_TYPE: return s->type0.p; case PB_MARK: return s->mark.p; case PB_SOLID: return s->solidIndex.p; case PB_MASS: return s->mass.p;
         case PB_FLAGS: return h->peer.flags.p;
     }
     return nullptr;
@@ -698,8 +759,10 @@ int peer_setup(LbGpuHandle* h) {
         return 0;
     }
     P.on = true;
-    P.seq = 0;
+    P.seq = 0; P.xseq = 0;
     P.planWhat[0] = P.planWhat[1] = 0;
+    P.xplans.clear();
+    if (const char* e = getenv("LBGPU_PEER_CYCLE")) P.inCycle = atoi(e) != 0;
     if (getenv("LBGPU_VERBOSE")) fprintf(stderr, "[lbgpu rank %d] peer halo on (neighbours %d / %d mapped)\n", c.rank, down, up);
     return 0;
 }
@@ -765,6 +828,72 @@ int peer_put(LbGpuHandle* h, uint32_t what, cudaStream_t st) {
     return 0;
 }
 
+// in-cycle exchange of the face planes of `what` through peer memory, on the handle's stream (see k_xput)
+int peer_exchange(LbGpuHandle* h, uint32_t what) {
+    PeerHalo& P = h->peer;
+    cudaStream_t st = h->stream;
+    int down, up;
+    neighbour_ranks(h, &down, &up);
+    const uint64_t key = ((uint64_t)what << 1) | (uint64_t)(h->cur & 1);
+    PutPlan* pl = nullptr;
+    for (auto& kv : P.xplans) if (kv.first == key) pl = &kv.second;
+    if (!pl) {
+        P.xplans.emplace_back(key, PutPlan());
+        pl = &P.xplans.back().second;
+        memset(pl, 0, sizeof *pl);
+        auto add = [&](const void* src, char* dst, size_t bytes) {
+            if (pl->n >= PUT_MAX) return;
+            pl->src[pl->n] = (const char*)src; pl->dst[pl->n] = dst; pl->bytes[pl->n] = (uint32_t)bytes; ++pl->n;
+        };
+        for (int dir = 0; dir < 2; ++dir) {
+            const int nb = dir == 0 ? down : up;
+            if (nb < 0) continue;
+            const bool isUp = dir == 1;
+            Slab* s = isUp ? h->slabs.back().get() : h->slabs.front().get();
+            const PeerExport& r = P.nbInfo[dir];
+            const size_t XY = s->XY;
+            const size_t sp = isUp ? (size_t)s->dev.Z - 2 : 1, dp = isUp ? 0 : (size_t)r.Z - 1;
+            auto pops = [&](int buf, bool all) {
+                const double* f = s->fbuf(buf);
+                double* nf = (double*)P.nb[dir][buf == 0 ? PB_FA : PB_FB] + r.pad;
+                auto pop = [&](int k) { add(f + (size_t)k * s->stride + sp * XY, (char*)(nf + (size_t)k * r.stride + dp * XY), XY * 8); };
+                if (all) { for (int k = 0; k < Q; ++k) pop(k); }
+                else { const int* ks = isUp ? POPS_UP : POPS_DOWN; for (int q = 0; q < 5; ++q) pop(ks[q]); }
+            };
+            if (what & G_POPS) pops(h->cur ^ 1, h->slip);
+            if (what & G_POPS_SRC) pops(h->cur, true);
+            auto field = [&](const void* mineP, int b, size_t elem) {
+                if (mineP && P.nb[dir][b]) add((const char*)mineP + sp * XY * elem, P.nb[dir][b] + dp * XY * elem, XY * elem);
+            };
+            if (what & G_TYPE) field(s->tbuf(0), PB_TYPE, 1);
+            if (what & G_SOLID) field(s->solidIndex.p, PB_SOLID, 4);
+            if (what & G_MASS) field(s->mass.p, PB_MASS, 8);
+            if (what & G_MACRO) { field(s->n.p, PB_N, 8); field(s->ux.p, PB_UX, 8); field(s->uy.p, PB_UY, 8); field(s->uz.p, PB_UZ, 8); }
+            if (what & G_VISC) field(s->visc.p, PB_VISC, 8);
+            if (what & G_HF) { field(s->hfx.p, PB_HFX, 8); field(s->hfy.p, PB_HFY, 8); field(s->hfz.p, PB_HFZ, 8); }
+            if ((what & G_MARK) && s->mark.p) field(s->mark.p, PB_MARK, 1);
+            uint32_t* nbFlags = (uint32_t*)P.nb[dir][PB_FLAGS];
+            // we are the neighbour ABOVE for the rank below us (its slots [3], [5]) and the neighbour BELOW for the rank above ([2], [4])
+            pl->readyDst[dir] = nbFlags + (isUp ? 2 : 3);
+            pl->flagDst[dir] = nbFlags + (isUp ? 4 : 5);
+            pl->readyLocal[dir] = P.flags.p + (isUp ? 3 : 2);
+        }
+        pl->counter = P.flags.p + 9;
+        pl->chunk = 32768;
+    }
+    ++P.xseq;
+    if (pl->n > 0) {
+        uint32_t maxBytes = 0;
+        for (int k = 0; k < pl->n; ++k) maxBytes = pl->bytes[k] > maxBytes ? pl->bytes[k] : maxBytes;
+        dim3 grid((maxBytes + pl->chunk - 1) / pl->chunk, (unsigned)pl->n);
+        k_xput<<<grid, 128, 0, st>>>(*pl, P.xseq, h->slabs[0]->status.p);
+        k_wait_halo<<<1, 32, 0, st>>>(P.flags.p + 4, P.xseq, down >= 0, up >= 0, h->slabs[0]->status.p);
+        h->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
 // in-place sum over the ranks of a small device array (no-op in a single-process run)
 int allreduce_sum(LbGpuHandle* h, void* buf, size_t count, int dtype) {
     if (!lbcomm::active() || count == 0) return 0;
@@ -800,7 +929,10 @@ int exchange(LbGpuHandle* h, uint32_t what, bool popsPushed = false, bool remote
             if ((rc = copy_face(h, b, 1, a, (uint32_t)a->dev.Z - 1, what, false))) return rc;
         }
     }
-    if (multiProc && remote) { if (int rc = exchange_remote(h, what, st)) return rc; }
+    if (multiProc && remote) {
+        if (h->peer.on && h->peer.inCycle) { if (int rc = peer_exchange(h, what)) return rc; }
+        else if (int rc = exchange_remote(h, what, st)) return rc;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -926,8 +1058,10 @@ int free_surface_step(LbGpuHandle* h) {
         k_add_counters<<<1, 32, 0, st>>>(s0->counters.p, h->slabs[k]->counters.p, 1);
         h->launches += 2;
     }
+    if (lbcomm::active()) NC(lbcomm::api().GroupStart());  // one launch for both sums
     if ((rc = allreduce_sum(h, s0->sums.p, 3, lbcomm::ncclFloat64))) return rc;
     if ((rc = allreduce_sum(h, s0->counters.p, 1, lbcomm::ncclUint64))) return rc;
+    if (lbcomm::active()) NC(lbcomm::api().GroupEnd());
     k_fs_finalize<<<1, 1, 0, st>>>(s0->sums.p, s0->counters.p, s0->scal.p);
     ++h->launches;
     for (auto& sp : h->slabs) {
@@ -1043,7 +1177,9 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
     // Flood fill, one generation per round.  The count of cells a generation flagged lives in status[1 + (gen & 1)] of
     // every slab (the global sum); the next generation's launches are gated on it, so the first SPEC generations are
     // issued without waiting for the host -- only then is the count read back, once per further generation.
-    constexpr int SPEC = 3, MAX_GEN = 4096;
+    // (particles move a fraction of a cell per step: the cells they newly cover touch flagged cells, so generation 0 flags
+    // them and generation 1 only confirms that nothing is left)
+    constexpr int SPEC = 2, MAX_GEN = 4096;
     bool converged = false;
     for (int gen = 0; gen < MAX_GEN; ++gen) {
         const int cur = 1 + (gen & 1), prev = 1 + ((gen + 1) & 1);

@@ -8,7 +8,7 @@ echo "pytest rc=$?" >> gpurun_out/r2d/pytest.log
 grep -E "passed|failed|FAILED|rc=" gpurun_out/r2d/pytest.log | tail -30
 for mode in peer nccl; do
   if [ $mode = nccl ]; then export LBGPU_PEER_HALO=0; else unset LBGPU_PEER_HALO; fi
-  LBGPU_VERBOSE=1 LBGPU_PREFETCH=740 timeout 600 python bench.py --gpus 2 --steps 300 --warmup 5 --no-extra > gpurun_out/r2d/bench_n2_$mode.json 2> gpurun_out/r2d/bench_n2_$mode.err
+  LBGPU_TRACE=1 LBGPU_VERBOSE=1 timeout 900 python bench.py --gpus 2 --steps 300 --warmup 5 > gpurun_out/r2d/bench_n2_$mode.json 2> gpurun_out/r2d/bench_n2_$mode.err
   python - <<PY
 import json
 try:
@@ -19,7 +19,7 @@ except Exception as e:
 PY
 done
 unset LBGPU_PEER_HALO
-LBGPU_PREFETCH=740 timeout 300 python bench.py --gpus 1 --steps 300 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2d/bench_n1.json 2> gpurun_out/r2d/bench_n1.err
+LBGPU_TRACE=1 timeout 300 python bench.py --gpus 1 --steps 300 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2d/bench_n1.json 2> gpurun_out/r2d/bench_n1.err
 python - <<PY
 import json
 d = json.loads(open("gpurun_out/r2d/bench_n1.json").read().strip().splitlines()[-1])
