@@ -984,8 +984,29 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
 
 // interface-cell list and visited-tile list of every slab from the current types: count - scan - write for the cells
 // (k_list_*), then for the tiles (k_tile_*)
+// The interface-cell and candidate lists grow AHEAD of need: the counts of the last list build that has reached the host
+// (they trail by a step at most, and an interface moves one cell per step) are compared with half the capacity, so a
+// list is never found too small by the kernels that consume it.  Returns true when a list was re-allocated.
+int grow_lists(LbGpuHandle* h, bool* grown) {
+    *grown = false;
+    for (size_t q = 0; q < h->slabs.size(); ++q) {
+        Slab* s = h->slabs[q].get();
+        const uint32_t cells = h->pinnedCounts[8 * q + 2], cand = h->pinnedCounts[8 * q + 4];
+        if (cells <= s->cellCap / 2 && cand <= s->candCap / 2) continue;
+        CU(cudaStreamSynchronize(h->stream));
+        auto target = [&](uint32_t seen, uint32_t cap) {
+            unsigned long long t = 2ull * (seen > cap ? seen : cap) + 1024ull;
+            return (uint32_t)(t < (unsigned long long)s->N + 16ull ? t : (unsigned long long)s->N + 16ull);
+        };
+        if (cells > s->cellCap / 2 && s->cellCap < s->N + 16u) { s->cellCap = target(cells, s->cellCap); CU(s->cellList.alloc(s->cellCap)); *grown = true; }
+        if (cand > s->candCap / 2 && s->candCap < s->N + 16u) { s->candCap = target(cand, s->candCap); CU(s->candList.alloc(s->candCap)); *grown = true; }
+    }
+    return 0;
+}
+
 int build_lists(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
+    { bool grown; if (int rc = grow_lists(h, &grown)) return rc; }
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
         const uint32_t nT = s->blocks * TILES_PER_BLOCK, tb = (nT + BLOCK - 1) / BLOCK;  // tiles of 32 cells
@@ -1228,8 +1249,8 @@ int build_static(LbGpuHandle* h, Slab* s) {
     s->dev.bulk = s->bulk.p;
     DevBuf<uint32_t> bc;
     CU(bc.alloc(s->blocks));
-    if (!s->staticCount.p) CU(s->staticCount.alloc(4));
-    CU(cudaMemsetAsync(s->staticCount.p, 0, 4 * sizeof(uint32_t), st));
+    if (!s->staticCount.p) CU(s->staticCount.alloc(8));  // [1] static cells, [3] wall-push cells (+ [4]: k_list_offsets mirrors slot 3 unclamped)
+    CU(cudaMemsetAsync(s->staticCount.p, 0, 8 * sizeof(uint32_t), st));
     if (h->fs) k_static_count<true><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
     else k_static_count<false><<<s->blocks, BLOCK, 0, st>>>(dev_all(h, s), s->bulk.p, bc.p);
     k_list_offsets<<<1, 1024, 0, st>>>(bc.p, s->blocks, s->staticCount.p, 1, s->N);
@@ -1496,8 +1517,9 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     if (h->fs) {
         CU(s->type1.alloc(NT)); CU(s->mark.alloc(NT)); CU(s->newMass.alloc(N)); CU(cudaMemsetAsync(s->mark.p, 0, NT, st));
         s->listBlocks = (s->blocks + LIST_TILES - 1) / LIST_TILES;
-        // capacities: the interface is a sheet; a lattice where more than 1 cell in 8 is an interface cell is refused
+        // first capacities: the interface is a sheet (1 cell in 8 at most); the lists grow ahead of need (grow_lists)
         s->cellCap = N / 8 + 1024;
+        if (const char* e = getenv("LBGPU_LIST_CAP")) s->cellCap = (uint32_t)atoi(e) > 16u ? (uint32_t)atoi(e) : 16u;  // tests: exercise the growth
         s->candCap = 4 * s->cellCap;
         CU(s->candList.alloc(s->candCap));
         CU(s->candBlockCount.alloc((((size_t)N + 15) / 16 + BLOCK - 1) / BLOCK + 1));
@@ -1941,7 +1963,18 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
             k_count<<<own_blocks(s), BLOCK, 0, st>>>(dev_for(h, s), s->counters.p + 1);
             ++h->launches;
         }
-        if (h->fs) { if (int r = build_lists(h)) return r; }  // valid until the first free-surface step rebuilds them
+        if (h->fs) {  // valid until the first free-surface step rebuilds them
+            if (int r = build_lists(h)) return r;
+            // the initial interface decides the first capacities (a lattice that is mostly interface band is legal)
+            for (int pass = 0; pass < 4; ++pass) {
+                CU(cudaStreamSynchronize(st));
+                bool grown = false;
+                if (int r = grow_lists(h, &grown)) return r;
+                if (!grown) break;
+                for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->mark.p, 0, sp->mark.n, st));  // marks of the overflowed build
+                if (int r = build_lists(h)) return r;
+            }
+        }
         Slab* s0 = h->slabs[0].get();
         for (size_t k = 1; k < h->slabs.size(); ++k) { k_add_counters<<<1, 32, 0, st>>>(s0->counters.p + 1, h->slabs[k]->counters.p + 1, 3); ++h->launches; }
         if (int r = allreduce_sum(h, s0->counters.p + 1, 3, lbcomm::ncclUint64)) return r;

@@ -4,7 +4,7 @@ import common, golden_util as gu
 name = sys.argv[1]; steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 g = gu.Golden(name)
 from hybird_b200 import LB
-lb = LB(dict(g.params)); lb.latticeBolzmannInit(*g.init_arrays())
+lb = LB(dict(g.params)); lb.latticeBolzmannInit(*g.init_arrays()); g.configure(lb)
 k = 0
 for s, F, M, V, W in gu.replay(g, lb, None):
     k += 1

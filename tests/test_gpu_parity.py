@@ -163,3 +163,23 @@ def test_type_error_reported():
         lb.synchronize()
     assert ei.value.code == -5
     lb.close()
+
+
+@pytest.mark.parametrize("cap", [24, 400])
+def test_interface_lists_grow_ahead_of_need(cap, monkeypatch):
+    """The interface-cell / candidate lists start small (LBGPU_LIST_CAP) and are re-allocated before they are too small:
+    at initialisation (cap 24: far below the initial interface) and while the dam-break front spreads (cap 400: above
+    twice the initial interface, below the later one).  Type maps must stay the reference's for all 100 steps."""
+    monkeypatch.setenv("LBGPU_LIST_CAP", str(cap))
+    g = gu.Golden("dam_newtonian")
+    lb = _gpu(g)
+    monkeypatch.delenv("LBGPU_LIST_CAP")
+    n_iface = []
+    for s, *_ in gu.replay(g, lb, None):
+        t = lb.fetch(("type_flags",))["type_flags"]
+        assert np.array_equal(t & 0x1F, g.types[s]), "type map differs from the reference after step %d" % s
+        n_iface.append(int(np.count_nonzero((t & 15) == 3)))
+    lb.synchronize()
+    lb.close()
+    if cap == 400:
+        assert n_iface[0] < cap // 2 < max(n_iface), (n_iface[0], max(n_iface))  # the case really crosses the threshold
