@@ -30,11 +30,23 @@ class LbGpuParams(C.Structure):
                 ("nLocalSlabs", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
+class LbGpuDemParams(C.Structure):
+    _fields_ = [("contactModel", C.c_int32), ("multiStep", C.c_int32), ("knConst", C.c_double), ("ksConst", C.c_double),
+                ("dampCoeff", C.c_double), ("viscTang", C.c_double), ("linearStiff", C.c_double), ("frictionCoefPart", C.c_double),
+                ("frictionCoefWall", C.c_double), ("numVisc", C.c_double), ("demF", C.c_double * 3), ("deltat", C.c_double),
+                ("nebrRange", C.c_double), ("maxDisp", C.c_double)]
+
+
+DEM_ELEMENT_DTYPE = np.dtype([("x0", "<f8", 3), ("x1", "<f8", 3), ("w0", "<f8", 3), ("radius", "<f8"), ("m", "<f8"), ("I", "<f8", 3)])
+DEM_WALL_DTYPE = np.dtype([("n", "<f8", 3), ("p", "<f8", 3), ("vel", "<f8", 3), ("omega", "<f8", 3), ("rotCenter", "<f8", 3),
+                           ("moving", "<i4"), ("pad", "<i4")])
+
 # every symbol include/lbgpu.h declares
 EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRange", "lbGpuInit", "lbGpuInitBox", "lbGpuSetCurves", "lbGpuSetMassTarget", "lbGpuStep", "lbGpuCouple", "lbGpuRun",
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuCountsLocal", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
-           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo", "lbGpuFluidSummary", "lbGpuWriteVti")
+           "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo", "lbGpuFluidSummary", "lbGpuWriteVti",
+           "lbGpuDemInit", "lbGpuDemStep", "lbGpuRunDem", "lbGpuDemState")
 
 _lib = None
 
@@ -108,6 +120,14 @@ def load_library(build_if_missing=True):
     L.lbGpuFluidSummary.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.lbGpuWriteVti.restype = C.c_int
     L.lbGpuWriteVti.argtypes = [vp, C.c_char_p, C.c_int]
+    L.lbGpuDemInit.restype = C.c_int
+    L.lbGpuDemInit.argtypes = [vp, C.POINTER(LbGpuDemParams), vp, C.c_uint32, vp, C.c_uint32]
+    L.lbGpuDemStep.restype = C.c_int
+    L.lbGpuDemStep.argtypes = [vp, vp]
+    L.lbGpuRunDem.restype = C.c_int
+    L.lbGpuRunDem.argtypes = [vp, C.c_int, C.c_uint32]
+    L.lbGpuDemState.restype = C.c_int
+    L.lbGpuDemState.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_double * 3)]
     L.lbGpuPeerHalo.restype = C.c_int
     L.lbGpuPeerHalo.argtypes = [vp, C.POINTER(C.c_int32)]
     L.lbGpuCommFinalize.restype = C.c_int

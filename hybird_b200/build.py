@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.environ.get("LBGPU_LIB") or os.path.join(HERE, "liblbgpu.so")  # LBGPU_LIB: A/B experiments with alternative builds
 SOURCES = [os.path.join(HERE, "csrc", "lbgpu.cu")]
-DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("lb_kernels.cuh", "lb_d3q19.cuh", "lbgpu_comm.h")] + \
+DEPS = SOURCES + [os.path.join(HERE, "csrc", f) for f in ("lb_kernels.cuh", "lb_d3q19.cuh", "lb_dem.cuh", "lbgpu_comm.h")] + \
     [os.path.join(ROOT, "include", "lbgpu.h")]
 
 # -fmad=false: the reference is built for x86-64 without FMA contraction; fusing a*b+c on the

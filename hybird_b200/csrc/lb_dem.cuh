@@ -1,0 +1,267 @@
+// lb_dem.cuh -- the DEM sub-steps of a coupled cycle on the device, for single-sphere elements.
+//
+// What DEM::discreteElementStep (DEM.cpp:331-376) does between two LB steps, restated per element:
+//   k_dem_trigger          DEM::evalMaxDisp + the neighbour-table trigger (DEM.cpp:1314-1324, 340-346)
+//   k_dem_neighbours       when triggered: DEM::evalNeighborTable (DEM.cpp:1377-1494) as one partner list per element -- every
+//                          element whose centre is closer than nebrRange NOW, in ascending index order
+//   k_dem_predict          DEM::evalNearWallTable when triggered (DEM.cpp:1496-1513: the FIRST wall within nebrRange, at the
+//                          corrected position), elmt::predict (elmt.cpp:139-177), particle::updatePredicted
+//   k_dem_forces_correct   particle-particle and wall-particle contacts (DEM.cpp:1668-1717, 1801-1982) with the LINEAR /
+//                          HERTZIAN laws (DEM.cpp:2138-2224), Newton's equations (DEM.cpp:1150-1181), elmt::correct
+//                          (elmt.cpp:179-254), particle::updateCorrected
+//   k_dem_export           the particle / element lists LB::latticeBoltzmannCouplingStep and LB::computeHydroForces read
+// The hydrodynamic force and torque come straight from the LB step's per-element reduction (physical units), the
+// positions and velocities go straight into the coupling step: a coupled cycle has no host round trip for the particles.
+// The contact laws are memoryless (no tangential spring), and a pair's force is bit-identical whichever of the two is
+// "I" (both threads of a pair evaluate it with the lower index as I), so every element sums the contacts with its
+// partners in ascending index order: deterministic, no atomics.  Broad phase: the reference searches its table with
+// linked cells (DEM.cpp:1326-1375) whose width is at least nebrRange wherever the domain is wider than six radii, so its
+// table IS the set of pairs within nebrRange at rebuild time; here a rebuild compares all pairs through shared-memory
+// tiles (4e8 distance tests for 20 000 spheres, once every few LB steps) and the sub-steps in between only walk the
+// partner lists.  No periodic boundaries (ghost particles), cylinders, objects, clusters.
+// Compiled with -fmad=false like the LB kernels: the reference's operation order is kept.
+#pragma once
+#include <stdint.h>
+
+namespace lbdem {
+
+struct Params {
+    int contactModel, multiStep;
+    double knConst, ksConst, dampCoeff, viscTang, linearStiff, frictionCoefPart, frictionCoefWall, numVisc;
+    double demF[3], deltat, nebrRange;
+    double c[5], coeff1[6], coeff2[6];  // DEM::predictor / DEM::corrector constants (DEM.cpp:1067-1112), computed on the host
+};
+struct Wall { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int moving, pad; };
+struct Elmt {
+    double x[6][3], xp[6][3], w[6][3], wp[6][3];
+    double radius, m, I[3];
+    int nearWall, pad;
+};
+struct V3 { double x, y, z; };
+__device__ __forceinline__ V3 v3(const double* a) { return { a[0], a[1], a[2] }; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ V3 operator-(V3 a) { return { -a.x, -a.y, -a.z }; }
+__device__ __forceinline__ V3 operator*(V3 a, double s) { return { a.x * s, a.y * s, a.z * s }; }
+__device__ __forceinline__ V3 operator*(double s, V3 a) { return { s * a.x, s * a.y, s * a.z }; }
+__device__ __forceinline__ V3 operator/(V3 a, double s) { return { a.x / s, a.y / s, a.z / s }; }
+__device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double norm2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+__device__ __forceinline__ void put(double* d, V3 a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; }
+
+// scal[0] = maxDisp, flag[0] = rebuild the tables in this sub-step, flag[2] = rebuilds so far
+__global__ void __launch_bounds__(1024) k_dem_trigger(const Elmt* __restrict__ e, uint32_t n, double deltat, double nebrRange,
+                                                      double* __restrict__ scal, uint32_t* __restrict__ flag) {
+    __shared__ double sm[32];
+    double mx = 0.0;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) mx = fmax(mx, norm2(v3(e[k].x[1])));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < 32; ++k) mx = fmax(mx, sm[k]);
+        double md = scal[0] + sqrt(mx) * deltat;
+        const bool rebuild = md > 0.25 * nebrRange;
+        if (rebuild) md = 0.0;
+        scal[0] = md;
+        flag[0] = rebuild ? 1u : 0u;
+        if (rebuild) flag[2] += 1u;
+    }
+}
+
+// partner lists: nbr[k * MAX_NBR + q], q < nNbr[k], ascending.  status[0] = largest list length seen (> MAX_NBR: error)
+constexpr int MAX_NBR = 48;
+__global__ void __launch_bounds__(128) k_dem_neighbours(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+                                                        uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr, uint32_t* __restrict__ status) {
+    if (!*flag) return;
+    __shared__ double sx[128], sy[128], sz[128];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = k < n;
+    const V3 xk = live ? v3(e[k].x[0]) : V3{ 0, 0, 0 };
+    const double r2 = nebrRange * nebrRange;
+    uint32_t cnt = 0;
+    for (uint32_t base = 0; base < n; base += 128) {
+        const uint32_t j = base + threadIdx.x;
+        __syncthreads();
+        if (j < n) { sx[threadIdx.x] = e[j].x[0][0]; sy[threadIdx.x] = e[j].x[0][1]; sz[threadIdx.x] = e[j].x[0][2]; }
+        __syncthreads();
+        const uint32_t m = n - base < 128u ? n - base : 128u;
+        if (live)
+            for (uint32_t q = 0; q < m; ++q) {
+                const V3 d = { sx[q] - xk.x, sy[q] - xk.y, sz[q] - xk.z };
+                if (base + q != k && norm2(d) < r2) {
+                    if (cnt < (uint32_t)MAX_NBR) nbr[(size_t)k * MAX_NBR + cnt] = base + q;
+                    ++cnt;
+                }
+            }
+    }
+    if (live) {
+        nNbr[k] = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
+        if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_dem_predict(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p,
+                                                     const Wall* __restrict__ walls, uint32_t nWalls, const uint32_t* __restrict__ flag) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Elmt& el = e[k];
+    if (*flag) {
+        int nw = -1;
+        const V3 x0 = v3(el.x[0]);
+        for (uint32_t w = 0; w < nWalls; ++w)
+            if (dot(v3(walls[w].n), x0 - v3(walls[w].p)) < p.nebrRange) { nw = (int)w; break; }
+        el.nearWall = nw;
+    }
+    const double* c = p.c;
+    V3 x[6], w[6];
+    for (int q = 0; q < 6; ++q) { x[q] = v3(el.x[q]); w[q] = v3(el.w[q]); }
+    put(el.xp[0], x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4]);
+    put(el.xp[1], x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3]);
+    put(el.xp[2], x[2] + x[3] * c[0] + x[4] * c[1] + x[5] * c[2]);
+    put(el.xp[3], x[3] + x[4] * c[0] + x[5] * c[1]);
+    put(el.xp[4], x[4] + x[5] * c[0]);
+    put(el.xp[5], x[5]);
+    put(el.wp[0], w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4]);
+    put(el.wp[1], w[1] + w[2] * c[0] + w[3] * c[1] + w[4] * c[2] + w[5] * c[3]);
+    put(el.wp[2], w[2] + w[3] * c[0] + w[4] * c[1] + w[5] * c[2]);
+    put(el.wp[3], w[3] + w[4] * c[0] + w[5] * c[1]);
+    put(el.wp[4], w[4] + w[5] * c[0]);
+    put(el.wp[5], w[5]);
+}
+
+__device__ __forceinline__ double normal_contact(const Params& p, double overlap, double vreln, double effRad, double effMass) {
+    if (p.contactModel == 1) {
+        const double kn = p.knConst * sqrt(effRad) * sqrt(overlap);
+        const double gamman = 2.0 * p.dampCoeff * sqrt(kn * effMass);
+        return fmax(kn * overlap + (-gamman * vreln), 0.0);
+    }
+    const double gamman = 2.0 * p.dampCoeff * sqrt(p.linearStiff * effMass);
+    return fmax(p.linearStiff * overlap + (-gamman * vreln), 0.0);
+}
+__device__ __forceinline__ double tangential_contact(const Params& p, double vrelt, double fn, double effRad, double effMass, double friction) {
+    const double ks = p.contactModel == 1 ? p.ksConst * sqrt(effRad) * pow(fabs(fn), 1.0 / 3.0) : p.linearStiff;
+    const double fsMax = friction * fn;
+    const double gammas = 2.0 * p.viscTang * sqrt(effMass * ks);
+    return fmin(gammas * vrelt, fsMax);
+}
+
+// hydro: per element {FHydro(3), MHydro(3), fluidVolume} in physical units, as the LB step's reduction left them
+__global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p,
+                                                            const Wall* __restrict__ walls, const double* __restrict__ hydro,
+                                                            const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ nNbr) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Elmt& el = e[k];
+    const V3 xk = v3(el.xp[0]), vk = v3(el.xp[1]), wk = v3(el.wp[0]);
+    const double rk = el.radius, mk = el.m;
+    V3 FP = { 0, 0, 0 }, FW = { 0, 0, 0 }, MP = { 0, 0, 0 }, MW = { 0, 0, 0 };
+    const uint32_t nn = nNbr[k];
+    for (uint32_t q = 0; q < nn; ++q) {
+        const uint32_t j = nbr[(size_t)k * MAX_NBR + q];
+        const Elmt& o = e[j];
+        const V3 xo = v3(o.xp[0]);
+        const bool iAmI = k < j;  // the pair's force is evaluated in the role assignment (lower index = I); see the header
+        const V3 d = iAmI ? xo - xk : xk - xo;  // partJ->x0 - partI->x0
+        const double rI = iAmI ? rk : o.radius, rJ = iAmI ? o.radius : rk;
+        const double sig = rI + rJ;
+        if (!(norm2(d) < sig * sig)) continue;
+        const double mI = iAmI ? mk : o.m, mJ = iAmI ? o.m : mk;
+        const V3 vI = iAmI ? vk : v3(o.xp[1]), vJ = iAmI ? v3(o.xp[1]) : vk;
+        const V3 wI = iAmI ? wk : v3(o.wp[0]), wJ = iAmI ? v3(o.wp[0]) : wk;
+        const double dist = sqrt(norm2(d));
+        const double overlap = rI + rJ - dist;
+        const V3 relVel = vJ - vI;
+        const V3 en = d / dist;
+        const double vn = dot(relVel, en);
+        const V3 normalRelVel = en * vn;
+        const double effMass = mI * mJ / (mI + mJ);
+        const double effRad = rI * rJ / (rI + rJ);
+        const double fn = normal_contact(p, overlap, vn, effRad, effMass);
+        const V3 nf = en * fn;
+        const V3 vecRadI = rI * en, vecRadJ = -rJ * en;
+        FP = iAmI ? FP - nf : FP + nf;
+        const V3 relC = relVel - cross(wI, vecRadI) + cross(wJ, vecRadJ);
+        const V3 tang = relC - normalRelVel;
+        const double nt = sqrt(norm2(tang));
+        if (nt != 0.0) {
+            const double ft = tangential_contact(p, nt, fn, effRad, effMass, p.frictionCoefPart);
+            const V3 et = tang / nt;
+            const V3 tf = ft * et;
+            if (iAmI) { MP = MP + cross(vecRadI, tf); FP = FP + tf; }
+            else { MP = MP - cross(vecRadJ, tf); FP = FP - tf; }
+        }
+    }
+    if (el.nearWall >= 0) {
+        const Wall wl = walls[el.nearWall];
+        const V3 en = v3(wl.n);
+        const double dist = dot(en, xk - v3(wl.p));
+        const double overlap = rk - dist;
+        if (overlap > 0.0) {
+            V3 cpv = { 0.0, 0.0, 0.0 };
+            if (wl.moving) {
+                const V3 dc = xk - v3(wl.rotCenter);
+                cpv = v3(wl.vel) + cross(v3(wl.omega), dc - dot(dc, en) * en);
+            }
+            const V3 relVel = vk - cpv;
+            const double vn = dot(relVel, en);
+            const V3 normalRelVel = en * vn;
+            const double fn = normal_contact(p, 2.0 * overlap, vn, rk, mk);
+            const V3 nf = en * fn;
+            const V3 vecRadJ = -rk * en;
+            FW = FW + nf;
+            const V3 relC = relVel + cross(wk, vecRadJ);
+            const V3 tang = relC - normalRelVel;
+            const double nt = sqrt(norm2(tang));
+            if (nt != 0.0) {
+                const double ft = tangential_contact(p, nt, fn, rk, mk, p.frictionCoefWall);
+                const V3 et = tang / sqrt(norm2(tang));
+                const V3 tf = ft * et;
+                MW = MW - cross(vecRadJ, tf);
+                FW = FW - tf;
+            }
+        }
+    }
+    // Newton's equations (DEM.cpp:1150-1181); a sphere's body frame stays the global one (header)
+    const V3 FH = hydro ? v3(hydro + (size_t)7 * k) : V3{ 0, 0, 0 }, MH = hydro ? v3(hydro + (size_t)7 * k + 3) : V3{ 0, 0, 0 };
+    const V3 FVisc = -6.0 * M_PI * p.numVisc * rk * vk;
+    const V3 MVisc = -8.0 * M_PI * p.numVisc * rk * rk * rk * wk;
+    const V3 x2 = (FVisc + FH + FP + FW) / mk + v3(p.demF);
+    const V3 mom = MVisc + MH + MP + MW;
+    const double* I = el.I;
+    const V3 w1 = { (mom.x + (I[1] - I[2]) * wk.y * wk.z) / I[0], (mom.y + (I[2] - I[0]) * wk.z * wk.x) / I[1],
+                    (mom.z + (I[0] - I[1]) * wk.x * wk.y) / I[2] };
+    // elmt::correct
+    const double* c2 = p.coeff2; const double* c1 = p.coeff1;
+    V3 xp[6], wp[6];
+    for (int q = 0; q < 6; ++q) { xp[q] = v3(el.xp[q]); wp[q] = v3(el.wp[q]); }
+    const V3 x2c = x2 - xp[2];
+    V3 x[6];
+    x[0] = xp[0] + x2c * c2[0]; x[1] = xp[1] + x2c * c2[1]; x[2] = x2;
+    x[3] = xp[3] + x2c * c2[3]; x[4] = xp[4] + x2c * c2[4]; x[5] = xp[5] + x2c * c2[5];
+    const V3 w1c = w1 - wp[1];
+    V3 w[6];
+    w[0] = wp[0] + w1c * c1[0]; w[1] = w1;
+    w[2] = wp[2] + w1c * c1[2]; w[3] = wp[3] + w1c * c1[3]; w[4] = wp[4] + w1c * c1[4]; w[5] = wp[5] + w1c * c1[5];
+    // every element reads the others' PREDICTED state (xp, wp) above and writes only its own corrected state (x, w);
+    // xp := x / wp := w (the tail of elmt::correct) happens at the top of the next predict, which overwrites them anyway
+    for (int q = 0; q < 6; ++q) { put(el.x[q], x[q]); put(el.w[q], w[q]); }
+}
+
+// the lists the LB side reads (layout of LbGpuParticle / LbGpuElement, physical units): particle::updateCorrected for a
+// one-sphere element is x0 = elmt::x0 (the prototype offset is zero), r = radius; elmt::wGlobal = w0 (wSolver, elmt.cpp:232-235)
+struct OutParticle { double x0[3], r, radiusVec[3]; uint32_t clusterIndex, particleIndex; };
+struct OutElement { double x1[3], wGlobal[3]; uint32_t compBegin, compEnd; };
+__global__ void __launch_bounds__(128) k_dem_export(const Elmt* __restrict__ e, uint32_t n, OutParticle* __restrict__ parts, OutElement* __restrict__ elmts,
+                                                    uint32_t* __restrict__ comps) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    OutParticle op; OutElement oe;
+    for (int c = 0; c < 3; ++c) { op.x0[c] = e[k].x[0][c]; op.radiusVec[c] = 0.0; oe.x1[c] = e[k].x[1][c]; oe.wGlobal[c] = e[k].w[0][c]; }
+    op.r = e[k].radius; op.clusterIndex = k; op.particleIndex = k;
+    oe.compBegin = k; oe.compEnd = k + 1;
+    parts[k] = op; elmts[k] = oe; comps[k] = k;
+}
+
+}  // namespace lbdem

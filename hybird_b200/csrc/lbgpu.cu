@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "lb_kernels.cuh"
+#include "lb_dem.cuh"
 #include "lbgpu_comm.h"
 
 namespace {
@@ -409,6 +410,16 @@ struct LbGpuHandle {
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
     int numSMs = 148;
+    // DEM sub-steps on the device (lb_dem.cuh): the elements' Gear state, partner lists, wall table
+    struct Dem {
+        bool on = false;
+        lbdem::Params prm;
+        uint32_t n = 0, nWalls = 0;
+        DevBuf<lbdem::Elmt> e;
+        DevBuf<lbdem::Wall> walls;
+        DevBuf<uint32_t> nbr, nNbr, flag;  // flag[0] = rebuild in this sub-step, [1] = longest partner list, [2] = rebuilds so far
+        DevBuf<double> scal, hydro;         // scal[0] = DEM::maxDisp; hydro: forces handed in from the host (lbGpuDemStep)
+    } dem;
 };
 
 namespace {
@@ -951,9 +962,7 @@ __global__ void k_add_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict
     if (i < n) dst[i] += src[i];
 }
 
-int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
-                     uint32_t nElmts, const uint32_t* comps, uint32_t nComps) {
-    static_assert(sizeof(LbGpuParticle) == sizeof(RawParticle) && sizeof(LbGpuElement) == sizeof(RawElement), "ABI layout");
+int particle_capacity(LbGpuHandle* h, uint32_t nParts, uint32_t nElmts, uint32_t nComps) {
     if (nParts > h->rawParts.n) { CU(h->rawParts.alloc(nParts + nParts / 2 + 16)); CU(h->parts.alloc(h->rawParts.n)); }
     if (nElmts > h->rawElmts.n) {
         CU(h->rawElmts.alloc(nElmts + nElmts / 2 + 16));
@@ -961,6 +970,13 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
         for (auto& s : h->slabs) CU(s->elemOut.alloc(h->rawElmts.n * 7));
     }
     if (nComps > h->comps.n) CU(h->comps.alloc(nComps + nComps / 2 + 16));
+    return 0;
+}
+
+int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
+                     uint32_t nElmts, const uint32_t* comps, uint32_t nComps) {
+    static_assert(sizeof(LbGpuParticle) == sizeof(RawParticle) && sizeof(LbGpuElement) == sizeof(RawElement), "ABI layout");
+    if (int rc = particle_capacity(h, nParts, nElmts, nComps)) return rc;
     const size_t bP = sizeof(RawParticle) * nParts, bE = sizeof(RawElement) * nElmts, bC = sizeof(uint32_t) * nComps;
     if (int rc = ensure_pinned(h, bP + bE + bC)) return rc;
     // the previous step's async copies out of the staging buffer must have completed
@@ -1452,6 +1468,12 @@ int lb_step(LbGpuHandle* h) {
 }
 
 int check_status(LbGpuHandle* h) {
+    if (h->dem.on) {
+        CU(cudaMemcpyAsync(h->pinnedStatus, h->dem.flag.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*h->pinnedStatus > (uint32_t)lbdem::MAX_NBR)
+            return fail(LBGPU_EUNSUPPORTED, "DEM: an element has %u partners within nebrRange, the partner lists hold %d", *h->pinnedStatus, lbdem::MAX_NBR);
+    }
     if (h->peer.on) {
         CU(cudaMemcpyAsync(h->pinnedStatus, h->slabs[0]->status.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
@@ -2117,6 +2139,137 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     return LBGPU_OK;
 }
 
+}  // extern "C"
+namespace {
+// DEM::discreteElementStep (DEM.cpp:331-376) on the device, then the lists the LB side reads.  hydro: 7 doubles per
+// element on the device, or nullptr = no hydrodynamic force yet (before the first LB step)
+int dem_step(LbGpuHandle* h, const double* hydro) {
+    static_assert(sizeof(lbdem::OutParticle) == sizeof(RawParticle) && sizeof(lbdem::OutElement) == sizeof(RawElement), "list layout");
+    auto& D = h->dem;
+    cudaStream_t st = h->stream;
+    const uint32_t n = D.n, nb = (n + 127) / 128;
+    for (int sub = 0; sub < D.prm.multiStep; ++sub) {
+        lbdem::k_dem_trigger<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.deltat, D.prm.nebrRange, D.scal.p, D.flag.p);
+        lbdem::k_dem_neighbours<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
+        lbdem::k_dem_predict<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, D.nWalls, D.flag.p);
+        lbdem::k_dem_forces_correct<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, hydro, D.nbr.p, D.nNbr.p);
+        h->launches += 4;
+    }
+    lbdem::k_dem_export<<<nb, 128, 0, st>>>(D.e.p, n, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
+    k_prepare_particles<<<nb, 128, 0, st>>>(h->rawParts.p, n, h->rawElmts.p, n, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElement* elmts, uint32_t nElmts, const LbGpuDemWall* walls,
+                 uint32_t nWalls) {
+    if (!h || !prm || !elmts || nElmts == 0) return fail(LBGPU_EINVAL, "lbGpuDemInit: null argument or no elements");
+    if (nWalls && !walls) return fail(LBGPU_EINVAL, "lbGpuDemInit: wall array missing");
+    if (prm->multiStep < 1 || !(prm->deltat > 0.0) || !(prm->nebrRange > 0.0)) return fail(LBGPU_EINVAL, "lbGpuDemInit: multiStep, deltat and nebrRange must be positive");
+    static_assert(sizeof(LbGpuDemWall) == sizeof(lbdem::Wall), "ABI layout");
+    CU(cudaSetDevice(h->device));
+    auto& D = h->dem;
+    lbdem::Params& P = D.prm;
+    P.contactModel = prm->contactModel; P.multiStep = prm->multiStep;
+    P.knConst = prm->knConst; P.ksConst = prm->ksConst; P.dampCoeff = prm->dampCoeff; P.viscTang = prm->viscTang;
+    P.linearStiff = prm->linearStiff; P.frictionCoefPart = prm->frictionCoefPart; P.frictionCoefWall = prm->frictionCoefWall;
+    P.numVisc = prm->numVisc; P.deltat = prm->deltat; P.nebrRange = prm->nebrRange;
+    for (int k = 0; k < 3; ++k) P.demF[k] = prm->demF[k];
+    // DEM::predictor / DEM::corrector constants (DEM.cpp:1067-1112), in the reference's expressions
+    const double dt = prm->deltat;
+    const double c[5] = { dt, dt * dt / 2.0, dt * dt * dt / 6.0, dt * dt * dt * dt / 24.0, dt * dt * dt * dt * dt / 120.0 };
+    const double g1[6] = { 95.0 / 288.0, 1.0, 25.0 / 24.0, 35.0 / 72.0, 5.0 / 48.0, 1.0 / 120.0 };
+    const double g2[6] = { 3.0 / 16.0, 251.0 / 360.0, 1.0, 11.0 / 18.0, 1.0 / 6.0, 1.0 / 60.0 };
+    for (int k = 0; k < 5; ++k) P.c[k] = c[k];
+    P.coeff1[0] = g1[0] * c[0]; P.coeff2[0] = g2[0] * c[1];
+    for (int k = 1; k < 6; ++k) { P.coeff1[k] = g1[k] * c[0] / c[k - 1]; P.coeff2[k] = g2[k] * c[1] / c[k - 1]; }
+    std::vector<lbdem::Elmt> E(nElmts);
+    memset(E.data(), 0, sizeof(lbdem::Elmt) * nElmts);
+    for (uint32_t k = 0; k < nElmts; ++k) {
+        for (int q = 0; q < 3; ++q) {
+            E[k].x[0][q] = E[k].xp[0][q] = elmts[k].x0[q];
+            E[k].x[1][q] = E[k].xp[1][q] = elmts[k].x1[q];
+            E[k].w[0][q] = elmts[k].w0[q];
+            E[k].I[q] = elmts[k].I[q];
+        }
+        E[k].radius = elmts[k].radius; E[k].m = elmts[k].m; E[k].nearWall = -1;
+        if (!(E[k].radius > 0.0) || !(E[k].m > 0.0)) return fail(LBGPU_EINVAL, "lbGpuDemInit: element %u has no radius or mass", k);
+    }
+    CU(D.e.alloc(nElmts)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)nElmts * lbdem::MAX_NBR)); CU(D.nNbr.alloc(nElmts));
+    CU(D.flag.alloc(4)); CU(D.scal.alloc(2)); CU(D.hydro.alloc((size_t)7 * nElmts));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(D.e.p, E.data(), sizeof(lbdem::Elmt) * nElmts, cudaMemcpyHostToDevice));
+    if (nWalls) CU(cudaMemcpy(D.walls.p, walls, sizeof(lbdem::Wall) * nWalls, cudaMemcpyHostToDevice));
+    CU(cudaMemset(D.nNbr.p, 0, sizeof(uint32_t) * nElmts));
+    CU(cudaMemset(D.flag.p, 0, sizeof(uint32_t) * 4));
+    const double sc[2] = { prm->maxDisp, 0.0 };
+    CU(cudaMemcpy(D.scal.p, sc, sizeof sc, cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());  // the copies ran on the legacy stream (see lbGpuSetCurves)
+    D.n = nElmts; D.nWalls = nWalls; D.on = true;
+    // the resident lists of the coupling step: one particle per element
+    if (int rc = particle_capacity(h, nElmts, nElmts, nElmts)) return rc;
+    h->nParts = h->nElmts = h->nComps = nElmts;
+    const uint32_t nb = (nElmts + 127) / 128;
+    lbdem::k_dem_export<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
+    k_prepare_particles<<<nb, 128, 0, h->stream>>>(h->rawParts.p, nElmts, h->rawElmts.p, nElmts, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return LBGPU_OK;
+}
+
+int lbGpuDemStep(LbGpuHandle* h, const double* hydro) {
+    if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuDemStep: no device-side DEM on this handle (lbGpuDemInit)");
+    CU(cudaSetDevice(h->device));
+    const double* src = h->lastStepCoupled ? h->slabs[0]->elemOut.p : nullptr;
+    if (hydro) {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(h->dem.hydro.p, hydro, sizeof(double) * 7 * h->dem.n, cudaMemcpyHostToDevice));
+        CU(cudaDeviceSynchronize());
+        src = h->dem.hydro.p;
+    }
+    return dem_step(h, src);
+}
+
+int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
+    if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuRunDem: no device-side DEM on this handle (lbGpuDemInit)");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->evA, h->stream));
+    h->kevCount = 0;
+    for (uint32_t k = 0; k < count; ++k) {
+        int rc;
+        if ((rc = dem_step(h, h->lastStepCoupled ? h->slabs[0]->elemOut.p : nullptr))) return rc;
+        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
+        if ((rc = coupling_step(h, false))) return rc;  // dem.newNeighborList is only raised with periodic DEM boundaries (DEM.cpp:1414)
+        if ((rc = lb_step(h))) return rc;
+    }
+    CU(cudaEventRecord(h->evB, h->stream));
+    return LBGPU_OK;
+}
+
+int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double info[3]) {
+    if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuDemState: no device-side DEM on this handle (lbGpuDemInit)");
+    CU(cudaSetDevice(h->device));
+    if (int rc = check_status(h)) return rc;
+    auto& D = h->dem;
+    std::vector<lbdem::Elmt> E(D.n);
+    uint32_t f[3]; double sc[2];
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(E.data(), D.e.p, sizeof(lbdem::Elmt) * D.n, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(f, D.flag.p, sizeof f, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(sc, D.scal.p, sizeof sc, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < D.n; ++k)
+        for (int q = 0; q < 3; ++q) {
+            if (x0) x0[3 * k + q] = E[k].x[0][q];
+            if (x1) x1[3 * k + q] = E[k].x[1][q];
+            if (w0) w0[3 * k + q] = E[k].w[0][q];
+        }
+    if (info) { info[0] = sc[0]; info[1] = (double)f[2]; info[2] = (double)f[1]; }
+    return LBGPU_OK;
+}
+
 int lbGpuSynchronize(LbGpuHandle* h) {
     if (!h) return fail(LBGPU_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
@@ -2555,6 +2708,13 @@ int visit_state(LbGpuHandle* h, F&& fn) {
     if (h->nParts && (rc = fn((void*)h->parts.p, sizeof(lb::Particle) * h->nParts))) return rc;
     if (h->nElmts && (rc = fn((void*)h->elmts.p, sizeof(lb::Element) * h->nElmts))) return rc;
     if (h->nComps && (rc = fn((void*)h->comps.p, sizeof(uint32_t) * h->nComps))) return rc;
+    if (h->dem.on) {  // the elements' Gear state and tables (the handle the blob is loaded into went through lbGpuDemInit)
+        auto& D = h->dem;
+        if ((rc = fn((void*)D.e.p, sizeof(lbdem::Elmt) * D.n)) || (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) ||
+            (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.n)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
+            (rc = fn((void*)D.scal.p, sizeof(double) * 2)))
+            return rc;
+    }
     return 0;
 }
 }  // namespace
@@ -2585,6 +2745,7 @@ int lbGpuSaveState(LbGpuHandle* h, void* buffer, uint64_t bytes) {
     for (auto& sp : h->slabs) hd.cellsTotal += sp->N;
     hd.steps = h->steps; hd.cur = (uint32_t)h->cur; hd.macroValid = h->macroValid; hd.lastStepFirst = h->lastStepFirst;
     hd.lastStepCoupled = h->lastStepCoupled; hd.nParts = h->nParts; hd.nElmts = h->nElmts; hd.nComps = h->nComps;
+    hd.pad = h->dem.on ? h->dem.n : 0;  // elements of the device-side DEM
     char* out = (char*)buffer;
     memcpy(out, &hd, sizeof hd);
     size_t off = sizeof hd;
@@ -2605,6 +2766,8 @@ int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes) {
     if (hd.nSlabs != h->slabs.size() || hd.cellsTotal != cells || hd.size[0] != h->prm.size[0] || hd.size[1] != h->prm.size[1] ||
         hd.size[2] != h->prm.size[2] || (hd.fs != 0) != h->fs)
         return fail(LBGPU_EINVAL, "lbGpuLoadState: the state was saved from a different lattice (size / slabs / free surface)");
+    if (hd.pad != (h->dem.on ? h->dem.n : 0u))
+        return fail(LBGPU_EINVAL, "lbGpuLoadState: the state holds %u device-side DEM elements, this handle %u (lbGpuDemInit first)", hd.pad, h->dem.on ? h->dem.n : 0u);
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     // room for the particle lists of the saved state (as upload_particles provides it)

@@ -153,6 +153,54 @@ class LB:
         abi.check(self.lib.lbGpuRun(self.h, int(fs), int(steps)))
         self.time += int(steps)
 
+    # -- DEM::discreteElementStep on the device (lbGpuDem*): single-sphere elements, plane walls ---------------
+    def demInit(self, dem: dict):
+        """`dem`: dict(params=..., elmts=[...], walls=[...]) with the reference's DEM member names (what
+        DEM::discreteElementInit left: sphereMat constants, deltat, multiStep, nebrRange, maxDisp; per element x0, x1, w0,
+        radius, m, I; per wall n, p, vel, omega, rotCenter, moving) -- physical units."""
+        p = dem["params"]
+        P = abi.LbGpuDemParams()
+        P.contactModel = int(p["contactModel"]); P.multiStep = int(p["multiStep"])
+        for k in ("knConst", "ksConst", "dampCoeff", "viscTang", "linearStiff", "frictionCoefPart", "frictionCoefWall", "numVisc",
+                  "deltat", "nebrRange", "maxDisp"):
+            setattr(P, k, float(p[k]))
+        P.demF[:] = [float(v) for v in p["demF"]]
+        E = np.zeros(len(dem["elmts"]), dtype=abi.DEM_ELEMENT_DTYPE)
+        for k, e in enumerate(dem["elmts"]):
+            if int(e.get("size", 1)) != 1:
+                raise ValueError("demInit: the device-side DEM covers single-sphere elements only (element %d has size %d)" % (k, e["size"]))
+            for f in ("x0", "x1", "w0", "I"):
+                E[k][f] = e[f]
+            E[k]["radius"] = e["radius"]; E[k]["m"] = e["m"]
+        W = np.zeros(len(dem["walls"]), dtype=abi.DEM_WALL_DTYPE)
+        for k, w in enumerate(dem["walls"]):
+            for f in ("n", "p", "vel", "omega", "rotCenter"):
+                W[k][f] = w[f]
+            W[k]["moving"] = int(w["moving"])
+        abi.check(self.lib.lbGpuDemInit(self.h, C.byref(P), abi.ptr(E), len(E), abi.ptr(W) if len(W) else None, len(W)))
+        self._dem_n = len(E)
+        self._last = (np.zeros(len(E), abi_particle_dtype()), np.zeros(len(E), abi_element_dtype()), np.arange(len(E), dtype=np.uint32))
+        return self
+
+    def demStep(self, hydro=None):
+        """dem.discreteElementStep(); `hydro` (nElmts x 7: FHydro, MHydro, -) replaces the device's own forces (tests)."""
+        hy = None if hydro is None else np.ascontiguousarray(hydro, dtype=np.float64)
+        if hy is not None and hy.size != 7 * self._dem_n:
+            raise ValueError("demStep: hydro must hold 7 values per element")
+        abi.check(self.lib.lbGpuDemStep(self.h, abi.ptr(hy)))
+
+    def runDem(self, steps, free_surface=None):
+        """`steps` goCycles on the device: DEM step, free-surface step, coupling step, LB step (lbGpuRunDem)."""
+        fs = self.freeSurface if free_surface is None else free_surface
+        abi.check(self.lib.lbGpuRunDem(self.h, int(fs), int(steps)))
+        self.time += int(steps)
+
+    def demState(self):
+        n = self._dem_n
+        x0 = np.zeros((n, 3)); x1 = np.zeros((n, 3)); w0 = np.zeros((n, 3)); info = (C.c_double * 3)()
+        abi.check(self.lib.lbGpuDemState(self.h, abi.ptr(x0), abi.ptr(x1), abi.ptr(w0), C.byref(info)))
+        return dict(x0=x0, x1=x1, w0=w0, maxDisp=float(info[0]), rebuilds=int(info[1]), longest_list=int(info[2]))
+
     def synchronize(self):
         abi.check(self.lib.lbGpuSynchronize(self.h))
 

@@ -130,6 +130,25 @@ def catalogue():
         elements=[dict(size=2, radius=2.6, x0=[11.0, 10.5, 17.0], x1=[0.0, 0.0, 0.0], w=[0.01, 0.02, 0.0]),
                   dict(size=3, radius=2.2, x0=[12.5, 11.0, 8.5], x1=[0.0, 0.0, 0.0], w=[0.0, 0.0, 0.02])],
         motion="dem")
+    # DEM in the loop with contacts: sphere-sphere and sphere-wall collisions, three DEM sub-steps per LB step; sphere 3
+    # drifts into a corner (DEM::evalNearWallTable lists ONE wall per particle).  LINEAR and HERTZIAN contact models.
+    dem_spheres = [dict(size=1, radius=3.2, x0=[10.6, 12.0, 15.0], x1=[0.09, 0.0, 0.0], w=[0.0, 0.0, 0.01]),
+                   dict(size=1, radius=3.0, x0=[17.6, 12.6, 15.4], x1=[-0.08, 0.0, 0.0], w=[0.0, 0.02, 0.0]),
+                   dict(size=1, radius=3.4, x0=[14.0, 13.0, 4.5], x1=[0.0, 0.01, -0.07], w=[0.0, 0.0, 0.0]),
+                   dict(size=1, radius=3.0, x0=[3.9, 3.8, 23.0], x1=[-0.06, -0.05, 0.01], w=[0.01, 0.0, 0.0])]
+    C["spheres_dem"] = make_case("spheres_dem", lbSizeX=30, lbSizeY=26, lbSizeZ=30, lbFZ=-2e-5, initVisc=0.1, multiStep=3,
+                                 elements=copy.deepcopy(dem_spheres), motion="dem")
+    C["spheres_hertz"] = make_case("spheres_hertz", lbSizeX=30, lbSizeY=26, lbSizeZ=30, lbFZ=-2e-5, initVisc=0.1, multiStep=2,
+                                   contactModel="HERTZIAN", youngMod=4.0, poisson=0.3, restitution=0.8, viscTang=0.3,
+                                   elements=copy.deepcopy(dem_spheres), motion="dem")
+    # a loose bed: twelve heavy spheres with random velocities in a box wider than nebrRange -- several rebuilds of the
+    # neighbour table, pairs that enter and leave it, wall contacts on every side
+    bed = _sphere_bed(12, (1.0, 1.0, 1.0), (39.0, 35.0, 39.0), 2.2, 3.0, 777)
+    for k, e in enumerate(bed):
+        e["x1"] = [0.12 * (((k * 7) % 5) - 2) / 2.0, 0.1 * (((k * 3) % 7) - 3) / 3.0, 0.11 * (((k * 5) % 3) - 1)]
+        e["w"] = [0.01 * ((k % 3) - 1), 0.0, 0.02 * ((k % 2) - 0.5)]
+    C["bed_dem"] = make_case("bed_dem", lbSizeX=40, lbSizeY=36, lbSizeZ=40, lbFZ=-4e-5, initVisc=0.04, multiStep=2, density=8.0,
+                             elements=bed, motion="dem")
     # --- cfg 4: free-surface dam break, Bingham --------------------------------------
     C["cfg4"] = make_case("cfg4", lbSizeX=512, lbSizeY=128, lbSizeZ=256, freeSurfaceSolve=1, nonNewtonianSolve=1,
                           lbFZ=-1e-4, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,

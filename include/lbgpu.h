@@ -156,6 +156,35 @@ int lbGpuCouple(LbGpuHandle* h, int rescanParticles, const LbGpuParticle* parts,
  * and the hydrodynamic force reduction run every cycle as in goCycle (hybird.cpp:49-57). */
 int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
 
+/* DEM sub-steps on the device: DEM::discreteElementStep (DEM.cpp:331-376) for single-sphere elements
+ * bounded by plane walls -- neighbour table + wall table on the displacement trigger (DEM.cpp:1314-1324, 1377-1513),
+ * 5th-order Gear predictor / corrector (elmt.cpp:139-254), LINEAR / HERTZIAN particle-particle and particle-wall contacts
+ * (DEM.cpp:1668-1717, 1801-1982, 2138-2224), Newton's equations with the hydrodynamic force and torque of the last LB step
+ * (DEM.cpp:1150-1181).  The particle / element lists of the coupling step and of LB::computeHydroForces are refreshed on
+ * the device, so a coupled cycle has no host round trip.  Not covered: clusters (size > 1), periodic DEM boundaries
+ * (ghost particles), cylinders, objects -- those keep the host DEM and lbGpuStep.  All values in physical units, as the
+ * reference's DEM holds them.  With a communicator every rank advances the same (replicated) elements.
+ *   contactModel  0 LINEAR, 1 HERTZIAN (material::contactModel, DEM.cpp:150-158)
+ *   deltat, multiStep, nebrRange, maxDisp: DEM::deltat / multiStep / nebrRange / maxDisp after DEM::discreteElementInit */
+typedef struct {
+    int32_t contactModel, multiStep;
+    double knConst, ksConst, dampCoeff, viscTang, linearStiff, frictionCoefPart, frictionCoefWall, numVisc;
+    double demF[3], deltat, nebrRange, maxDisp;
+} LbGpuDemParams;
+typedef struct { double x0[3], x1[3], w0[3], radius, m, I[3]; } LbGpuDemElement;   /* elmt::x0, x1, w0, radius, m, I (elmt.h:60-110) */
+typedef struct { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int32_t moving, pad; } LbGpuDemWall; /* wall.h */
+int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* params, const LbGpuDemElement* elmts, uint32_t nElmts,
+                 const LbGpuDemWall* walls, uint32_t nWalls);
+/* One DEM::discreteElementStep (multiStep sub-steps).  hydro = NULL: FHydro / MHydro of the last LB step as they lie on the
+ * device; otherwise 7 doubles per element {FHydro, MHydro, -} from the host (tests). */
+int lbGpuDemStep(LbGpuHandle* h, const double* hydro);
+/* `count` goCycles (hybird.cpp:35-66) back to back on the device: DEM step, free-surface step (if doFreeSurface), coupling
+ * step, LB step. */
+int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count);
+/* elmt::x0, x1, w0 (3*nElmts each; any may be NULL); info[0] = DEM::maxDisp, info[1] = neighbour-table rebuilds so far,
+ * info[2] = longest partner list.  Synchronises. */
+int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double info[3]);
+
 /* Results of the last step in physical units; any pointer may be NULL. Synchronises. */
 int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHydro /*3*nElmts*/,
                         double* fluidVolume /*nElmts*/, double* wallFHydro /*3*nWalls*/);

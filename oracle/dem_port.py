@@ -1,0 +1,224 @@
+"""Plain-Python restatement of the reference's DEM sub-step for single-sphere elements -- TEST INFRASTRUCTURE (the checker
+of the device-side DEM, pinned against the particle traces the unmodified reference records; never imported by the
+product).  Follows DEM::discreteElementStep (DEM.cpp:331-376): evalMaxDisp + the neighbour-table trigger (DEM.cpp:1314-1324,
+340-346), elmt::predict (elmt.cpp:139-177), particle-particle and wall-particle contacts (DEM.cpp:1668-1717, 1801-1982) with
+the LINEAR / HERTZIAN laws (DEM.cpp:2138-2224), Newton's equations (DEM.cpp:1150-1181), elmt::correct (elmt.cpp:179-254).
+Quirks kept: contacts are only looked for among the pairs DEM::evalNeighborTable listed at the last rebuild (centres
+closer than nebrRange THEN, DEM.cpp:1326-1494; the linked cells only bound the search and are not restated: every cell is
+wider than nebrRange, so the table is exactly the set of pairs within range); DEM::evalNearWallTable lists only the FIRST
+wall within nebrRange of a particle, at table-rebuild time (DEM.cpp:1496-1513); spheres never rotate their frame (q2 is only integrated for size > 1), so the body frame is the
+global one.  No periodic boundaries, cylinders, objects or clusters."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def read_dem_file(path):
+    """PREFIX_dem.txt written by oracle/ref_harness.cpp -> dict(params, elmts, walls)."""
+    return parse_dem_text(open(path).read())
+
+
+def parse_dem_text(text):
+    prm, elmts, walls, counts = {}, [], [], {}
+    for ln in str(text).splitlines():
+        t = ln.split()
+        if not t:
+            continue
+        if t[0] == "contactModel":
+            i = 0
+            while i < len(t):
+                k = t[i]
+                if k == "demF":
+                    prm[k] = [float(v) for v in t[i + 1:i + 4]]; i += 4
+                else:
+                    prm[k] = float(t[i + 1]); i += 2
+        elif t[0] == "elmt":
+            elmts.append(dict(size=int(t[3]), radius=float(t[5]), m=float(t[7]), I=[float(v) for v in t[9:12]],
+                              x0=[float(v) for v in t[13:16]], x1=[float(v) for v in t[17:20]], w0=[float(v) for v in t[21:24]]))
+        elif t[0] == "wall":
+            walls.append(dict(n=[float(v) for v in t[3:6]], p=[float(v) for v in t[7:10]], vel=[float(v) for v in t[11:14]],
+                              omega=[float(v) for v in t[15:18]], rotCenter=[float(v) for v in t[19:22]], moving=int(t[23])))
+        elif t[0] == "pbcs":
+            counts = {t[i]: int(t[i + 1]) for i in range(0, len(t), 2)}
+    prm["contactModel"] = int(prm["contactModel"]); prm["multiStep"] = int(prm["multiStep"])
+    return dict(params=prm, elmts=elmts, walls=walls, counts=counts)
+
+
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]])
+
+
+def _norm2(a):
+    return a[0] * a[0] + a[1] * a[1] + a[2] * a[2]
+
+
+class DemPort:
+    def __init__(self, dem):
+        p = dem["params"]
+        self.p = p
+        self.n = len(dem["elmts"])
+        E = dem["elmts"]
+        assert all(e["size"] == 1 for e in E), "single-sphere elements only"
+        z = lambda: np.zeros((self.n, 3))
+        self.x = [np.array([e["x0"] for e in E], dtype=float).reshape(-1, 3), np.array([e["x1"] for e in E], dtype=float).reshape(-1, 3), z(), z(), z(), z()]
+        self.xp = [self.x[0].copy(), self.x[1].copy(), z(), z(), z(), z()]
+        self.w = [np.array([e["w0"] for e in E], dtype=float).reshape(-1, 3), z(), z(), z(), z(), z()]
+        self.wp = [z(), z(), z(), z(), z(), z()]
+        self.radius = np.array([e["radius"] for e in E]); self.m = np.array([e["m"] for e in E])
+        self.I = np.array([e["I"] for e in E]).reshape(-1, 3)
+        self.walls = dem["walls"]
+        self.maxDisp = p["maxDisp"]; self.nebrRange = p["nebrRange"]
+        self.nearWall = [-1] * self.n
+        self.pairs = []  # DEM::neighborTable as (i, j), i < j
+        dt = p["deltat"]
+        self.c = [dt, dt * dt / 2.0, dt * dt * dt / 6.0, dt * dt * dt * dt / 24.0, dt * dt * dt * dt * dt / 120.0]
+        g1 = [95.0 / 288.0, 1.0, 25.0 / 24.0, 35.0 / 72.0, 5.0 / 48.0, 1.0 / 120.0]
+        g2 = [3.0 / 16.0, 251.0 / 360.0, 1.0, 11.0 / 18.0, 1.0 / 6.0, 1.0 / 60.0]
+        c = self.c
+        self.coeff1 = [g1[0] * c[0], g1[1] * c[0] / c[0], g1[2] * c[0] / c[1], g1[3] * c[0] / c[2], g1[4] * c[0] / c[3], g1[5] * c[0] / c[4]]
+        self.coeff2 = [g2[0] * c[1], g2[1] * c[1] / c[0], g2[2] * c[1] / c[1], g2[3] * c[1] / c[2], g2[4] * c[1] / c[3], g2[5] * c[1] / c[4]]
+        self.FHydro = z(); self.MHydro = z()
+        self.rebuilds = 0
+
+    # -- contact laws (DEM.cpp:2138-2224) ---------------------------------------------------------------
+    def normal(self, overlap, vreln, effRad, effMass):
+        p = self.p
+        if p["contactModel"] == 1:
+            kn = p["knConst"] * math.sqrt(effRad) * math.sqrt(overlap)
+            gamman = 2.0 * p["dampCoeff"] * math.sqrt(kn * effMass)
+            return max(kn * overlap + (-gamman * vreln), 0.0)
+        gamman = 2.0 * p["dampCoeff"] * math.sqrt(p["linearStiff"] * effMass)
+        return max(p["linearStiff"] * overlap + (-gamman * vreln), 0.0)
+
+    def tangential(self, vrelt, fn, effRad, effMass, friction):
+        p = self.p
+        if p["contactModel"] == 1:
+            ks = p["ksConst"] * math.sqrt(effRad) * math.pow(abs(fn), 1.0 / 3.0)
+        else:
+            ks = p["linearStiff"]
+        fsMax = friction * fn
+        gammas = 2.0 * p["viscTang"] * math.sqrt(effMass * ks)
+        return min(gammas * vrelt, fsMax)
+
+    def substep(self):
+        p, n, c = self.p, self.n, self.c
+        x, xp, w, wp = self.x, self.xp, self.w, self.wp
+        # evalMaxDisp + trigger
+        maxVel = 0.0
+        for k in range(n):
+            v2 = _norm2(x[1][k])
+            if v2 > maxVel:
+                maxVel = v2
+        self.maxDisp += math.sqrt(maxVel) * p["deltat"]
+        if self.maxDisp > 0.25 * self.nebrRange:
+            self.maxDisp = 0.0
+            self.rebuilds += 1
+            r2 = self.nebrRange * self.nebrRange
+            self.pairs = [(i, j) for i in range(n) for j in range(i + 1, n) if _norm2(x[0][j] - x[0][i]) < r2]
+            for k in range(n):  # evalNearWallTable: the first wall within range, at the corrected position
+                self.nearWall[k] = -1
+                for wi, wl in enumerate(self.walls):
+                    if float(np.dot(np.array(wl["n"]), x[0][k] - np.array(wl["p"]))) < self.nebrRange:
+                        self.nearWall[k] = wi
+                        break
+        # predictor
+        xp[0] = x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4]
+        xp[1] = x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3]
+        xp[2] = x[2] + x[3] * c[0] + x[4] * c[1] + x[5] * c[2]
+        xp[3] = x[3] + x[4] * c[0] + x[5] * c[1]
+        xp[4] = x[4] + x[5] * c[0]
+        xp[5] = x[5].copy()
+        wp[0] = w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4]
+        wp[1] = w[1] + w[2] * c[0] + w[3] * c[1] + w[4] * c[2] + w[5] * c[3]
+        wp[2] = w[2] + w[3] * c[0] + w[4] * c[1] + w[5] * c[2]
+        wp[3] = w[3] + w[4] * c[0] + w[5] * c[1]
+        wp[4] = w[4] + w[5] * c[0]
+        wp[5] = w[5].copy()
+        FP, FW, MP, MW = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        # particle-particle contacts at the predicted positions
+        for i, j in self.pairs:
+            if True:
+                d = xp[0][j] - xp[0][i]
+                sig = self.radius[i] + self.radius[j]
+                if _norm2(d) < sig * sig:
+                    dist = math.sqrt(_norm2(d))
+                    overlap = self.radius[i] + self.radius[j] - dist
+                    relVel = xp[1][j] - xp[1][i]
+                    en = d / dist
+                    vn = float(np.dot(relVel, en))
+                    normalRelVel = en * vn
+                    effMass = self.m[i] * self.m[j] / (self.m[i] + self.m[j])
+                    effRad = self.radius[i] * self.radius[j] / (self.radius[i] + self.radius[j])
+                    fn = self.normal(overlap, vn, effRad, effMass)
+                    nf = en * fn
+                    vecRadI, vecRadJ = self.radius[i] * en, -self.radius[j] * en
+                    FP[i] = FP[i] - nf; FP[j] = FP[j] + nf
+                    relC = relVel - _cross(wp[0][i], vecRadI) + _cross(wp[0][j], vecRadJ)
+                    tang = relC - normalRelVel
+                    nt = math.sqrt(_norm2(tang))
+                    if nt != 0.0:
+                        ft = self.tangential(nt, fn, effRad, effMass, p["frictionCoefPart"])
+                        et = tang / nt
+                        tf = ft * et
+                        MP[i] = MP[i] + _cross(vecRadI, tf); FP[i] = FP[i] + tf
+                        MP[j] = MP[j] - _cross(vecRadJ, tf); FP[j] = FP[j] - tf
+        # wall contacts (one listed wall per particle)
+        for k in range(n):
+            wi = self.nearWall[k]
+            if wi < 0:
+                continue
+            wl = self.walls[wi]
+            en = np.array(wl["n"])
+            dist = float(np.dot(en, xp[0][k] - np.array(wl["p"])))
+            overlap = self.radius[k] - dist
+            if overlap > 0.0:
+                cpv = np.zeros(3)
+                if wl["moving"]:
+                    dc = xp[0][k] - np.array(wl["rotCenter"])
+                    cpv = np.array(wl["vel"]) + _cross(np.array(wl["omega"]), dc - float(np.dot(dc, en)) * en)
+                relVel = xp[1][k] - cpv
+                vn = float(np.dot(relVel, en))
+                normalRelVel = en * vn
+                fn = self.normal(2.0 * overlap, vn, self.radius[k], self.m[k])
+                nf = en * fn
+                vecRadJ = -self.radius[k] * en
+                FW[k] = FW[k] + nf
+                relC = relVel + _cross(wp[0][k], vecRadJ)
+                tang = relC - normalRelVel
+                nt = math.sqrt(_norm2(tang))
+                if nt != 0.0:
+                    ft = self.tangential(nt, fn, self.radius[k], self.m[k], p["frictionCoefWall"])
+                    et = tang / math.sqrt(_norm2(tang))
+                    tf = ft * et
+                    MW[k] = MW[k] - _cross(vecRadJ, tf)
+                    FW[k] = FW[k] - tf
+        # Newton (DEM.cpp:1150-1181) + corrector
+        demF = np.array(p["demF"])
+        for k in range(n):
+            FVisc = -6.0 * math.pi * p["numVisc"] * self.radius[k] * xp[1][k]
+            MVisc = -8.0 * math.pi * p["numVisc"] * self.radius[k] * self.radius[k] * self.radius[k] * wp[0][k]
+            x[2][k] = (FVisc + self.FHydro[k] + FP[k] + FW[k]) / self.m[k] + demF
+            mom = MVisc + self.MHydro[k] + MP[k] + MW[k]
+            I, wl_ = self.I[k], wp[0][k]
+            w[1][k] = np.array([(mom[0] + (I[1] - I[2]) * wl_[1] * wl_[2]) / I[0], (mom[1] + (I[2] - I[0]) * wl_[2] * wl_[0]) / I[1],
+                                (mom[2] + (I[0] - I[1]) * wl_[0] * wl_[1]) / I[2]])
+        c2, c1 = self.coeff2, self.coeff1
+        x2c = x[2] - xp[2]
+        x[0] = xp[0] + x2c * c2[0]; x[1] = xp[1] + x2c * c2[1]
+        x[3] = xp[3] + x2c * c2[3]; x[4] = xp[4] + x2c * c2[4]; x[5] = xp[5] + x2c * c2[5]
+        for k in range(6):
+            xp[k] = x[k].copy()
+        w1c = w[1] - wp[1]
+        w[0] = wp[0] + w1c * c1[0]
+        w[2] = wp[2] + w1c * c1[2]; w[3] = wp[3] + w1c * c1[3]; w[4] = wp[4] + w1c * c1[4]; w[5] = wp[5] + w1c * c1[5]
+        for k in range(6):
+            wp[k] = w[k].copy()
+
+    def step(self, FHydro, MHydro):
+        """One DEM::discreteElementStep with the hydrodynamic forces of the last LB step (physical units)."""
+        self.FHydro = np.asarray(FHydro, dtype=float).reshape(-1, 3); self.MHydro = np.asarray(MHydro, dtype=float).reshape(-1, 3)
+        for _ in range(self.p["multiStep"]):
+            self.substep()
+        return self.x[0].copy(), self.x[1].copy(), self.w[0].copy()

@@ -325,6 +325,23 @@ int main(int argc, char** argv) {
                 lb.boundary[3], lb.boundary[4], lb.boundary[5], (int)lb.freeSurface, (int)lb.forceField,
                 (int)lb.nonNewtonian, (int)lb.turbulenceOn);
         fprintf(logFp, "# totalMass %.17g enforceMass %d\n", lb.totalMass, (int)(problemName == DRUM));
+        // what a device-side DEM needs to restate DEM::discreteElementStep for single-sphere elements (tests only)
+        if (FILE* df = fopen((a.out + "_dem.txt").c_str(), "w")) {
+            fprintf(df, "contactModel %d knConst %.17g ksConst %.17g dampCoeff %.17g viscTang %.17g linearStiff %.17g frictionCoefPart %.17g "
+                        "frictionCoefWall %.17g numVisc %.17g demF %.17g %.17g %.17g deltat %.17g multiStep %u nebrRange %.17g maxDisp %.17g\n",
+                    (int)(dem.sphereMat.contactModel == HERTZIAN ? 1 : 0), dem.sphereMat.knConst, dem.sphereMat.ksConst, dem.sphereMat.dampCoeff,
+                    dem.sphereMat.viscTang, dem.sphereMat.linearStiff, dem.sphereMat.frictionCoefPart, dem.sphereMat.frictionCoefWall, dem.numVisc,
+                    dem.demF.x, dem.demF.y, dem.demF.z, dem.deltat, dem.multiStep, dem.nebrRange, dem.maxDisp);
+            for (const elmt& e : dem.elmts)
+                fprintf(df, "elmt %u size %u radius %.17g m %.17g I %.17g %.17g %.17g x0 %.17g %.17g %.17g x1 %.17g %.17g %.17g w0 %.17g %.17g %.17g\n",
+                        e.index, e.size, e.radius, e.m, e.I.x, e.I.y, e.I.z, e.x0.x, e.x0.y, e.x0.z, e.x1.x, e.x1.y, e.x1.z, e.w0.x, e.w0.y, e.w0.z);
+            for (const wall& w : dem.walls)
+                fprintf(df, "wall %u n %.17g %.17g %.17g p %.17g %.17g %.17g vel %.17g %.17g %.17g omega %.17g %.17g %.17g rotCenter %.17g %.17g %.17g moving %d\n",
+                        w.index, w.n.x, w.n.y, w.n.z, w.p.x, w.p.y, w.p.z, w.vel.x, w.vel.y, w.vel.z, w.omega.x, w.omega.y, w.omega.z,
+                        w.rotCenter.x, w.rotCenter.y, w.rotCenter.z, (int)w.moving);
+            fprintf(df, "pbcs %zu cylinders %zu objects %zu ghosts %zu\n", dem.pbcs.size(), dem.cylinders.size(), dem.objects.size(), dem.ghosts.size());
+            fclose(df);
+        }
         if (a.dumps.count(0)) dumpState(lb, dem, a.out + "_state000000.bin", 0, a.dumpNeighbors, a.lite);
     }
     auto writeTypes = [&]() {

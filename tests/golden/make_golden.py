@@ -14,6 +14,7 @@ One `<case>.npz` per case:
   types          (steps+1, N) uint8: nodeType::t | p<<4 after init and after every step
   sha_<field>_<step>   sha256 of the field's bytes over the active cells after `step` in CHECK_STEPS
   final_n / final_mass / final_u  full arrays after the last step (for diagnosing a hash mismatch)
+  dem            (cases with the DEM in the loop) text: material constants, time step, tables' range, elements, walls
 """
 from __future__ import annotations
 
@@ -42,6 +43,8 @@ STEPS = {
     "cfg4_mini": 100, "dam_newtonian": 100, "droplet": 100, "bubble_periodic": 100,
     "cfg1_mini": 100, "cfg5_mini": 100,
     "drum_mini": 300, "drum_bingham": 200,
+    # DEM in the loop (contacts, table rebuilds): the fixtures also carry what DEM::discreteElementInit left (`dem`)
+    "spheres_dem": 120, "spheres_hertz": 120, "bed_dem": 200,
 }
 
 
@@ -79,6 +82,8 @@ def generate(name, workdir="/tmp/hb_golden"):
         forces=np.fromfile(out + "_forces.bin", dtype="<f8"),
         types=np.fromfile(out + "_types.bin", dtype=np.uint8).reshape(-1, N),
     )
+    if case.get("motion") == "dem" and os.path.exists(out + "_dem.txt"):
+        d["dem"] = open(out + "_dem.txt").read()  # parameters, elements and walls of the reference's DEM after its init
     if len(st0.get("curve_cells", ())):
         d["curve_cells"] = st0["curve_cells"]; d["curve_delta"] = st0["curve_delta"]
     d["sha_init_f"] = sha(st0["f"][np.isin(st0["type"], (0, 3))] + 0.0)

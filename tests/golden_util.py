@@ -53,6 +53,11 @@ class Golden:
         finally:
             os.unlink(fpath)
 
+    def dem(self):
+        """What the reference's DEM held after its initialisation (cases with the DEM in the loop), as dem_port parses it."""
+        import dem_port
+        return dem_port.parse_dem_text(str(self.z["dem"])) if "dem" in self.z.files else None
+
     def init_arrays(self):
         z = self.z
         return (z["init_type_flags"], z["init_solidIndex"], z["init_n"], z["init_u"], z["init_mass"], z["init_visc"])

@@ -1,0 +1,106 @@
+"""GPU (B200): DEM::discreteElementStep on the device (lbGpuDem*) against the unmodified reference.
+
+(1) the DEM sub-steps alone, fed with the reference's recorded hydrodynamic forces: positions, velocities and spins of every
+    element after every LB step within 1e-12 of the reference's trace (and of the Python restatement);
+(2) the whole coupled cycle on the device (DEM step -> coupling step -> LB step, no host round trip for the particles):
+    identical cell-type / particle-flag maps at every step, forces within 1e-9, trajectories within 1e-9;
+(3) lbGpuRunDem(count) == count x lbGpuRunDem(1); checkpoint / restart carries the elements."""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem")
+TOL_DEM = 1e-12
+TOL_COUPLED = 1e-9
+
+
+def _gpu(g):
+    from hybird_b200 import LB
+    lb = LB(dict(g.params))
+    lb.latticeBolzmannInit(*g.init_arrays())
+    return lb.demInit(g.dem())
+
+
+@pytest.mark.parametrize("name", DEM_CASES)
+def test_device_dem_follows_reference_trace(name):
+    import dem_port
+    g = gu.Golden(name)
+    lb = _gpu(g)
+    P = dem_port.DemPort(g.dem())
+    n = len(g.dem()["elmts"])
+    hydro = np.zeros((n, 7))
+    worst = worst_port = 0.0
+    for s in range(g.steps):
+        parts, elmts, comps, flag = g.trace[s]
+        lb.demStep(hydro)
+        st = lb.demState()
+        px0, px1, pw = P.step(hydro[:, 0:3], hydro[:, 3:6])
+        worst = max(worst, np.abs(st["x0"] - parts["x0"]).max(), np.abs(st["x1"] - elmts["x1"]).max(), np.abs(st["w0"] - elmts["wGlobal"]).max())
+        worst_port = max(worst_port, np.abs(st["x0"] - px0).max(), np.abs(st["x1"] - px1).max(), np.abs(st["w0"] - pw).max())
+        hydro[:, 0:3], hydro[:, 3:6] = g.forces[s][0], g.forces[s][1]
+    assert st["rebuilds"] == P.rebuilds
+    assert worst <= TOL_DEM and worst_port <= TOL_DEM, (worst, worst_port)
+    lb.close()
+
+
+@pytest.mark.parametrize("name", DEM_CASES)
+def test_coupled_cycle_on_device_matches_reference(name):
+    g = gu.Golden(name)
+    lb = _gpu(g)
+    worst_x = worst_f = 0.0
+    for s in range(1, g.steps + 1):
+        parts, elmts, comps, flag = g.trace[s - 1]
+        lb.runDem(1)
+        st = lb.demState()
+        worst_x = max(worst_x, np.abs(st["x0"] - parts["x0"]).max(), np.abs(st["x1"] - elmts["x1"]).max(), np.abs(st["w0"] - elmts["wGlobal"]).max())
+        t = lb.fetch(("type_flags",))["type_flags"]
+        assert np.array_equal(t & 0x1F, g.types[s]), "type / particle-flag map differs from the reference after step %d" % s
+        F, M, V, W = lb.forces()
+        rF, rM, rV, rW = g.forces[s - 1]
+        arm = float(parts["r"].max()); fmax = float(np.abs(rF).max())
+        for a, b, floor in ((F, rF, 0.0), (M, rM, fmax * arm), (V, rV, 0.0)):
+            worst_f = max(worst_f, np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-300))
+    assert worst_x <= TOL_COUPLED and worst_f <= TOL_COUPLED, (worst_x, worst_f)
+    # the fields at the end, against the reference's hashes where the path is order-deterministic (no free surface here)
+    mine = lb.fetch()
+    h = gu.state_hashes(mine)
+    ref = g.hashes(g.steps)
+    print("%s: trajectories %.2e, forces %.2e, bit-identical fields: %s" % (name, worst_x, worst_f, [k for k in gu.FIELDS if h[k] == ref[k]]))
+    lb.close()
+
+
+def test_run_dem_equals_single_cycles_and_restart():
+    g = gu.Golden("bed_dem")
+    a, b, c = _gpu(g), _gpu(g), _gpu(g)
+    a.runDem(60)
+    for _ in range(60):
+        b.runDem(1)
+    c.runDem(25)
+    blob = c.save_state()
+    c.close()
+    c = _gpu(g).load_state(blob)
+    c.runDem(35)
+    sa, sb, sc = a.demState(), b.demState(), c.demState()
+    for k in ("x0", "x1", "w0"):
+        assert np.array_equal(sa[k], sb[k]) and np.array_equal(sa[k], sc[k]), k
+    fa, fb, fc = a.fetch(), b.fetch(), c.fetch()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]) and np.array_equal(fa[k], fc[k]), k
+    for lb in (a, b, c):
+        lb.close()
+
+
+def test_partner_list_overflow_is_an_error():
+    from hybird_b200 import LB
+    from hybird_b200.abi import LbGpuError
+    g = gu.Golden("spheres_dem")
+    dem = g.dem()
+    e0 = dem["elmts"][0]
+    dem["elmts"] = [dict(e0, x0=[10.0 + 0.01 * k, 12.0, 15.0]) for k in range(60)]  # 59 partners each, the lists hold 48
+    lb = LB(dict(g.params)).latticeBolzmannInit(*g.init_arrays()).demInit(dem)
+    with pytest.raises(LbGpuError):
+        lb.demStep()
+        lb.synchronize()
+    lb.close()
