@@ -109,7 +109,8 @@ def workload_label(name, n_slabs=1):
     if name == "cfg2":
         return "cfg2: D3Q19 periodic channel 256x256x%d, BGK Newtonian tau=1, body force, no particles" % (
             256 if n_slabs == 1 else 254 * n_slabs + 2)
-    return {"cfg3": "cfg3: single sphere r=8 in a 128x128x256 no-slip box, particle coupling + force reduction",
+    return {"cfg1": "cfg1: the shipped lbmConfigDevisFluid.cfg case, 100x150x30, free surface + Smagorinsky, periodic in x",
+            "cfg3": "cfg3: single sphere r=8 in a 128x128x256 no-slip box, particle coupling + force reduction",
             "cfg4": "cfg4: free-surface dam break 512x128x256, Bingham rheology",
             "cfg5": "cfg5: debris flow, 20000 spheres in a 1024x256x256 free-surface fluid (long axis stored as z), "
                     "%d z-slab(s)" % n_slabs}.get(name, name)
@@ -412,7 +413,7 @@ def main_ours(args, rank, world, local_rank):
     # ---- the other configurations, device-resident, so that they are measured by the same driver run ----
     extra = {}
     if args.workload == "cfg2" and not args.no_extra:
-        for nm in (("cfg3", "cfg4", "cfg5") if world == 1 else ("cfg5",)):
+        for nm in (("cfg1", "cfg3", "cfg4", "cfg5") if world == 1 else ("cfg5",)):
             try:
                 Kx = min(K, 100)
                 lbx, infx, rx = resident_run(nm, args, rank, world, local_rank, dist, Kx, W, False)

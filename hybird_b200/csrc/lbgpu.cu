@@ -410,6 +410,16 @@ struct LbGpuHandle {
     std::vector<cudaEvent_t> kev0, kev1;
     uint32_t kevCount = 0;
     int numSMs = 148;
+    // CUDA graph of two consecutive cycles of a free-surface lattice without particles (lbGpuRun): ~20 launches per cycle
+    // replayed as one graph launch.  Two cycles, because the population buffers alternate.  LBGPU_GRAPH=0 turns it off.
+    struct CycleGraph {
+        cudaGraphExec_t exec = nullptr;
+        std::vector<uint32_t> tiles;   // visited tiles per slab the step kernels' grids were sized for
+        uint64_t launches = 0;         // kernels per replay
+        int cur = -1;
+        uint64_t replays = 0, captures = 0;
+    } graph;
+    bool graphAllowed = true, capturing = false;
     // DEM sub-steps on the device (lb_dem.cuh): the elements' Gear state, partner lists, wall table
     struct Dem {
         bool on = false;
@@ -1003,8 +1013,17 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
 // The interface-cell and candidate lists grow AHEAD of need: the counts of the last list build that has reached the host
 // (they trail by a step at most, and an interface moves one cell per step) are compared with half the capacity, so a
 // list is never found too small by the kernels that consume it.  Returns true when a list was re-allocated.
+bool lists_need_growth(const LbGpuHandle* h) {
+    for (size_t q = 0; q < h->slabs.size(); ++q) {
+        const Slab* s = h->slabs[q].get();
+        if ((h->pinnedCounts[8 * q + 2] > s->cellCap / 2 && s->cellCap < s->N + 16u) || (h->pinnedCounts[8 * q + 4] > s->candCap / 2 && s->candCap < s->N + 16u)) return true;
+    }
+    return false;
+}
+
 int grow_lists(LbGpuHandle* h, bool* grown) {
     *grown = false;
+    if (h->capturing) return 0;  // lbGpuRun looks at the counts before it captures or replays a graph
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
         const uint32_t cells = h->pinnedCounts[8 * q + 2], cand = h->pinnedCounts[8 * q + 4];
@@ -1020,29 +1039,35 @@ int grow_lists(LbGpuHandle* h, bool* grown) {
     return 0;
 }
 
+// coarse blocks of a list build (lb_kernels.cuh, SCAN_MAX_BLOCKS): `chunks` 128-thread chunks on `grid` blocks of `per` chunks
+struct Coarse { uint32_t grid, per; };
+Coarse coarse_blocks(uint32_t chunks) {
+    const uint32_t per = chunks > SCAN_MAX_BLOCKS ? (chunks + SCAN_MAX_BLOCKS - 1) / SCAN_MAX_BLOCKS : 1u;
+    return { chunks ? (chunks + per - 1) / per : 1u, per };
+}
+
 int build_lists(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     { bool grown; if (int rc = grow_lists(h, &grown)) return rc; }
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
         const uint32_t nT = s->blocks * TILES_PER_BLOCK, tb = (nT + BLOCK - 1) / BLOCK;  // tiles of 32 cells
-        k_list_count<<<s->listBlocks, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p);
-        k_list_offsets<<<1, 1024, 0, st>>>(s->listBlockCount.p, s->listBlocks, s->listCounts.p, 0, s->cellCap);
-        k_list_write<<<s->listBlocks, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p, s->listBlockCount.p, s->cellList.p, s->cellCap);
+        const Coarse cl = coarse_blocks(s->listBlocks), ct = coarse_blocks(tb);
+        k_list_count<<<cl.grid, BLOCK, 0, st>>>(s->tbuf(0), nT, s->tileFlags.p, s->listBlockCount.p, cl.per);
+        k_list_write<<<cl.grid, BLOCK, 0, st>>>(dev_all(h, s), nT, s->tileFlags.p, s->listBlockCount.p, s->cellList.p, s->cellCap, cl.per, s->listCounts.p);
         {   // candidates of the update: owners decided on the (identical) pre-update copy of the types
             Dev d = dev_for(h, s);
             d.typeOld = s->tbuf(1);
             const uint32_t groups = (s->N + 15u) / 16u, gb = (groups + BLOCK - 1) / BLOCK;
+            const Coarse cc = coarse_blocks(gb);
             k_cand_mark<<<s->listGrid, BLOCK, 0, st>>>(d, s->mark.p, s->tileFlags.p);
-            k_plist_count<<<gb, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, nullptr, MARK_CAND);
-            k_list_offsets<<<1, 1024, 0, st>>>(s->candBlockCount.p, gb, s->listCounts.p, 3, s->candCap);
-            k_plist_write<<<gb, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, s->candList.p, s->candCap, nullptr, MARK_CAND);
-            h->launches += 4;
+            k_plist_count<<<cc.grid, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, nullptr, MARK_CAND, cc.per);
+            k_plist_write<<<cc.grid, BLOCK, 0, st>>>(s->mark.p, groups, s->candBlockCount.p, s->candList.p, s->candCap, nullptr, MARK_CAND, cc.per, s->listCounts.p, 3);
+            h->launches += 3;
         }
-        k_tile_count<<<tb, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p);
-        k_list_offsets<<<1, 1024, 0, st>>>(s->listTileOffset.p, tb, s->listCounts.p, 1, nT);
-        k_tile_write<<<tb, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, s->tileList.p);
-        h->launches += 6;
+        k_tile_count<<<ct.grid, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, ct.per);
+        k_tile_write<<<ct.grid, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, s->tileList.p, ct.per, s->listCounts.p);
+        h->launches += 4;
         // the host only needs the tile count to size the step kernel's grid; a stale value is fine (grid-stride loop)
         CU(cudaMemcpyAsync(h->pinnedCounts + 8 * q, s->listCounts.p, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
@@ -1190,11 +1215,10 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
         for (auto& sp : h->slabs) {
             Slab* s = sp.get();
             const uint32_t* gate = gateSlot >= 0 ? s->status.p + gateSlot : nullptr;
-            k_plist_count<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, gate, P_BIT);
-            if (gateSlot < 0) k_list_offsets<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap);
-            else k_list_offsets_gated<<<1, 1024, 0, st>>>(s->pBlockCount.p, s->pScanBlocks, s->pCounts.p, 0, s->pCap, gate);
-            k_plist_write<<<s->pScanBlocks, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, s->pList.p, s->pCap, gate, P_BIT);
-            h->launches += 3;
+            const Coarse cp = coarse_blocks(s->pScanBlocks);
+            k_plist_count<<<cp.grid, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, gate, P_BIT, cp.per);
+            k_plist_write<<<cp.grid, BLOCK, 0, st>>>(s->tbuf(0), s->pGroups, s->pBlockCount.p, s->pList.p, s->pCap, gate, P_BIT, cp.per, s->pCounts.p, 0);
+            h->launches += 2;
         }
         return 0;
     };
@@ -1330,7 +1354,7 @@ int lb_step(LbGpuHandle* h) {
     const uint32_t ke = h->kevCount % LbGpuHandle::KEV;
     if (h->dynWall)
         for (auto& sp : h->slabs) CU(cudaMemsetAsync(sp->partial.p, 0, sizeof(double) * (size_t)sp->blocks * nSums, st));
-    CU(cudaEventRecord(h->kev0[ke], st));
+    if (!h->capturing) CU(cudaEventRecord(h->kev0[ke], st));
     const uint32_t what = G_POPS | (fsOn ? (G_MACRO | G_VISC | G_HF) : 0u) | (h->hasCurved ? (G_MACRO | G_VISC) : 0u);
     // Slabs of other processes: the two face planes are updated first and travel (NCCL, comm stream) while the
     // interior is updated.  Moving walls keep the plain order (their per-block partial sums are indexed by block).
@@ -1387,8 +1411,7 @@ int lb_step(LbGpuHandle* h) {
         CU(cudaEventRecord(h->evHalo, h->commStream));
     }
     for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
-    CU(cudaEventRecord(h->kev1[ke], st));
-    ++h->kevCount;
+    if (!h->capturing) { CU(cudaEventRecord(h->kev1[ke], st)); ++h->kevCount; }
     // ghostCopy: the mirrors of everything the step kernel stored are copied now (the kernel did not push them)
     const uint32_t whatLocal = what | (h->ghostCopy ? ((macro ? G_MACRO : 0u) | (h->shear ? G_VISC : 0u) | (couple ? G_HF : 0u)) : 0u);
     if ((rc = exchange(h, whatLocal, !h->ghostCopy, !overlap))) return rc;
@@ -1940,6 +1963,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         h->fs = prm->freeSurface != 0;
         if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
         if (const char* e = getenv("LBGPU_WALL_PUSH")) h->wallPushAllowed = atoi(e) != 0;
+        if (const char* e = getenv("LBGPU_GRAPH")) h->graphAllowed = atoi(e) != 0;
         if (const char* e = getenv("LBGPU_PREFETCH")) h->prefetchBlocks = (uint32_t)atoi(e);
         if (h->prefetchBlocks == 0xffffffffu) h->prefetchBlocks = (uint32_t)h->numSMs * 5u;
         if (const char* e = getenv("LBGPU_PREFETCH_TILES")) h->prefetchTiles = (uint32_t)atoi(e);
@@ -2090,6 +2114,7 @@ int lbGpuSetMassTarget(LbGpuHandle* h, double totalMass) {
     if (!h->fs) return fail(LBGPU_EINVAL, "lbGpuSetMassTarget: the lattice has no free surface");
     h->enforceMass = true;
     h->totalMass = totalMass;
+    if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }  // the captured cycle had no mass target
     return LBGPU_OK;
 }
 
@@ -2129,12 +2154,62 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->evA, h->stream));
     h->kevCount = 0;
-    for (uint32_t k = 0; k < count; ++k) {
+    auto cycle = [&]() -> int {
         int rc;
         if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
         if (h->nParts > 0) { if ((rc = coupling_step(h, false))) return rc; }  // goCycle's order, particles of the last upload
-        if ((rc = lb_step(h))) return rc;
+        return lb_step(h);
+    };
+    uint32_t k = 0;
+    // A free-surface cycle is ~20 small launches around the step kernel: on small lattices their issue cost bounds the
+    // cycle.  Without particles (the coupling step reads a count back every cycle) and in one process the cycle is a fixed
+    // sequence of stream operations, so two consecutive cycles are captured once and replayed.  The last cycles of a call
+    // run eagerly: they carry the CUDA events lbGpuLastKernelMs reads, and the list counts the host sizes grids with.
+    const bool graphable = h->graphAllowed && h->fs && doFreeSurface && h->nParts == 0 && !lbcomm::active() && !h->dem.on && !h->dynWall && count >= 8;
+    if (graphable) {
+        constexpr uint32_t TAIL = 2;
+        for (; k < count && h->steps < 2; ++k) { if (int rc = cycle()) return rc; }
+        while (count - k >= 2 + TAIL) {
+            if (lists_need_growth(h)) {  // an eager cycle re-allocates the lists; the graph holds the old pointers
+                if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }
+                if (int rc = cycle()) return rc;
+                ++k;
+                continue;
+            }
+            bool valid = h->graph.exec != nullptr && h->graph.cur == h->cur;
+            for (size_t q = 0; valid && q < h->slabs.size(); ++q) {
+                const uint32_t now = h->pinnedCounts[8 * q + 1], then = h->graph.tiles[q];
+                valid = now <= then + then / 32 && now + now / 4 + 64 >= then;  // the grids carry 1/16 of headroom
+            }
+            if (!valid) {
+                if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }
+                const uint64_t steps0 = h->steps, launches0 = h->launches;
+                h->graph.tiles.resize(h->slabs.size());
+                for (size_t q = 0; q < h->slabs.size(); ++q) h->graph.tiles[q] = h->pinnedCounts[8 * q + 1];
+                cudaGraph_t g = nullptr;
+                CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                h->capturing = true;
+                int rc = cycle();
+                if (!rc) rc = cycle();
+                h->capturing = false;
+                const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+                h->steps = steps0;  // nothing ran yet
+                h->graph.launches = h->launches - launches0;
+                h->launches = launches0;
+                if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+                if (ce != cudaSuccess) return fail(LBGPU_ECUDA, "graph capture of the free-surface cycle: %s", cudaGetErrorString(ce));
+                const cudaError_t ie = cudaGraphInstantiate(&h->graph.exec, g, 0);
+                cudaGraphDestroy(g);
+                if (ie != cudaSuccess) { h->graph.exec = nullptr; return fail(LBGPU_ECUDA, "graph instantiation: %s", cudaGetErrorString(ie)); }
+                h->graph.cur = h->cur;
+                ++h->graph.captures;
+            }
+            CU(cudaGraphLaunch(h->graph.exec, h->stream));
+            h->steps += 2; h->launches += h->graph.launches; ++h->graph.replays;
+            k += 2;
+        }
     }
+    for (; k < count; ++k) { if (int rc = cycle()) return rc; }
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
 }
@@ -2297,6 +2372,12 @@ int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches) {
         sum += ms;
     }
     *msSum = sum; *launches = n;
+    return LBGPU_OK;
+}
+
+int lbGpuGraphInfo(LbGpuHandle* h, uint64_t info[2]) {
+    if (!h || !info) return fail(LBGPU_EINVAL, "null argument");
+    info[0] = h->graph.captures; info[1] = h->graph.replays;
     return LBGPU_OK;
 }
 
@@ -2790,6 +2871,7 @@ int lbGpuLoadState(LbGpuHandle* h, const void* buffer, uint64_t bytes) {
             return 0;
         }))
         return rc;
+    if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }
     h->steps = hd.steps; h->cur = (int)hd.cur; h->macroValid = hd.macroValid != 0; h->lastStepFirst = hd.lastStepFirst != 0;
     h->lastStepCoupled = hd.lastStepCoupled != 0;
     h->typesFlipped = false; h->listsFresh = false;
@@ -2803,6 +2885,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
+    if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
     peer_teardown(h);
     h->slabs.clear();
     if (h->evA) cudaEventDestroy(h->evA);

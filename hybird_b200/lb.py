@@ -220,6 +220,12 @@ class LB:
         abi.check(self.lib.lbGpuLaunchCount(self.h, C.byref(v)))
         return int(v.value)
 
+    def graph_info(self):
+        """(captures, replays) of the CUDA graph lbGpuRun uses for free-surface cycles without particles."""
+        v = (C.c_uint64 * 2)()
+        abi.check(self.lib.lbGpuGraphInfo(self.h, C.byref(v)))
+        return int(v[0]), int(v[1])
+
     def counts(self, local=False):
         c = (C.c_uint64 * 4)()
         abi.check((self.lib.lbGpuCountsLocal if local else self.lib.lbGpuCounts)(self.h, C.byref(c)))

@@ -225,7 +225,10 @@ int lbGpuLastStepMs(LbGpuHandle* h, float* ms);
 /* device time of the fused stream-collide kernel alone: sum over the (at most 512 most recent)
  * launches of the last lbGpuStep/lbGpuRun call, CUDA events on the engine's stream. Synchronises. */
 int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches);
-/* number of kernels this handle launched so far */
+/* lbGpuRun replays two consecutive cycles of a free-surface lattice without particles as one CUDA graph (single process;
+ * LBGPU_GRAPH=0 turns it off): info[0] = captures, info[1] = replays (of two cycles each) so far */
+int lbGpuGraphInfo(LbGpuHandle* h, uint64_t info[2]);
+/* number of kernels this handle launched so far (kernels inside a replayed graph included) */
 int lbGpuLaunchCount(LbGpuHandle* h, uint64_t* launches);
 /* device self-test of the engine's shared-reciprocal fp64 division against IEEE division on `count`
  * pseudo-random operand pairs: result[0] = mismatches (must be 0), [1] = quotients compared, [2] = operand

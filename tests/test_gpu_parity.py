@@ -99,6 +99,27 @@ def test_run_equals_step_loop():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("name", ["dam_newtonian", "cfg4_mini", "bubble_periodic", "cfg1_mini"])
+def test_graph_replay_equals_eager_cycles(name, monkeypatch):
+    """lbGpuRun's CUDA graph of two free-surface cycles (captured once, replayed) == the same cycles launched one by one."""
+    g = gu.Golden(name)
+    a = _gpu(g)
+    monkeypatch.setenv("LBGPU_GRAPH", "0")
+    b = _gpu(g)
+    monkeypatch.delenv("LBGPU_GRAPH")
+    for n in (31, 8, 40):
+        l0a, l0b = a.launch_count(), b.launch_count()
+        a.run(n); b.run(n)
+        a.synchronize(); b.synchronize()
+        assert a.launch_count() - l0a == b.launch_count() - l0b
+    assert a.graph_info()[1] >= 30 and b.graph_info() == (0, 0)
+    sa, sb = a.fetch(), b.fetch()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert a.counts() == b.counts()
+    a.close(); b.close()
+
+
 def test_run_keeps_resident_particles_coupled():
     """lbGpuRun(count) with particles uploaded earlier == count x (coupling step + LB step) with the same particles."""
     g = gu.Golden("cfg5_mini")
