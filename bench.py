@@ -425,6 +425,14 @@ def main_ours(args, rank, world, local_rank):
                 rx["workload"] = workload_label(nm, world)
                 rx["roofline"]["traffic"], rx["roofline"]["traffic_source"] = traffic_of(nm)
                 rx["peer_halo"] = lbx.peer_halo() if world > 1 else None
+                # where the device time of a cycle goes (CUDA events at the phase boundaries, a separate short run: the
+                # trace launches every cycle eagerly); rank 0's view
+                lbx.phase_trace(True)
+                lbx.run(min(Kx, 32))
+                ph, ncyc = lbx.phase_ms()
+                lbx.phase_trace(False)
+                rx["phase_ms"] = {k: round(v, 4) for k, v in ph.items()}
+                rx["phase_ms"]["cycles"] = ncyc
                 if world > 1:
                     dist.barrier()
                 lbx.close()

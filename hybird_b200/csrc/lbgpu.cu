@@ -196,6 +196,8 @@ struct Slab {
     DevBuf<uint32_t> cellList, tileList, listCounts, listBlockCount, listTileOffset, candList, candBlockCount;
     uint32_t candCap = 0;
     uint32_t listGrid = 0, listBlocks = 0, cellCap = 0;  // blocks of a list-driven launch; blocks of the list passes
+    DevBuf<uint32_t> rangeCells, listRanges;  // face / interior launches of a slab between processes: cell ranges, their list positions
+    bool hasRanges = false;
     DevBuf<uint32_t> gDst, gSrc, gPop;   // local ghost list (periodic mirrors)
     uint32_t nGhost = 0;
     DevBuf<double> partial, sums, scal, elemOut, elemPartial, summary;
@@ -416,10 +418,18 @@ struct LbGpuHandle {
         cudaGraphExec_t exec = nullptr;
         std::vector<uint32_t> tiles;   // visited tiles per slab the step kernels' grids were sized for
         uint64_t launches = 0;         // kernels per replay
-        int cur = -1;
+        int cur = -1, fs = -1;
+        uint32_t nParts = 0;
         uint64_t replays = 0, captures = 0;
     } graph;
     bool graphAllowed = true, capturing = false;
+    int floodGens = 3;       // single process: flood-fill generations issued per coupling step without a host round trip (0: ask the host)
+    uint32_t eagerCycles = 0;  // cycles launched one by one since the particle lists / settings last changed (a graph needs settled buffers)
+    // phase trace (lbGpuPhaseTrace): CUDA events at the phase boundaries of a cycle, a ring of the last PH_RING cycles
+    static constexpr int PH_MARKS = 8, PH_RING = 64;
+    bool phaseOn = false;
+    std::vector<cudaEvent_t> phaseEv;  // PH_RING x PH_MARKS
+    uint64_t phaseCycles = 0;
     // DEM sub-steps on the device (lb_dem.cuh): the elements' Gear state, partner lists, wall table
     struct Dem {
         bool on = false;
@@ -435,6 +445,15 @@ struct LbGpuHandle {
 namespace {
 
 typedef void (*StepKernel)(const Dev);
+
+// phase boundaries of a cycle: 0 start, 1 after the DEM sub-steps, 2 after the list build, 3 after the free-surface update,
+// 4 after the coupling step, 5 after the step kernels + halo, 6 after wall slots / moving-wall sums, 7 after the element forces
+// and the type sync (end of the cycle)
+inline void phase_mark(LbGpuHandle* h, int m) {
+    if (!h->phaseOn || h->capturing) return;
+    cudaEventRecord(h->phaseEv[(size_t)(h->phaseCycles % LbGpuHandle::PH_RING) * LbGpuHandle::PH_MARKS + m], h->stream);
+    if (m == LbGpuHandle::PH_MARKS - 1) ++h->phaseCycles;
+}
 
 // FS / DYNWALL / PART are compile-time in k_step; only the combinations that can occur are instantiated.
 // part 0: the whole step in one launch (lean variants); parts 1 + 2: bulk cells, then the rest (lb_kernels.cuh).
@@ -986,6 +1005,7 @@ int particle_capacity(LbGpuHandle* h, uint32_t nParts, uint32_t nElmts, uint32_t
 int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts, const LbGpuElement* elmts,
                      uint32_t nElmts, const uint32_t* comps, uint32_t nComps) {
     static_assert(sizeof(LbGpuParticle) == sizeof(RawParticle) && sizeof(LbGpuElement) == sizeof(RawElement), "ABI layout");
+    if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }  // the lists may move
     if (int rc = particle_capacity(h, nParts, nElmts, nComps)) return rc;
     const size_t bP = sizeof(RawParticle) * nParts, bE = sizeof(RawElement) * nElmts, bC = sizeof(uint32_t) * nComps;
     if (int rc = ensure_pinned(h, bP + bE + bC)) return rc;
@@ -998,6 +1018,7 @@ int upload_particles(LbGpuHandle* h, const LbGpuParticle* parts, uint32_t nParts
     if (bP) CU(cudaMemcpyAsync(h->rawParts.p, st, bP, cudaMemcpyHostToDevice, h->stream));
     if (bE) CU(cudaMemcpyAsync(h->rawElmts.p, st + bP, bE, cudaMemcpyHostToDevice, h->stream));
     if (bC) CU(cudaMemcpyAsync(h->comps.p, st + bP + bE, bC, cudaMemcpyHostToDevice, h->stream));
+    if (h->nParts != nParts || h->nElmts != nElmts || h->nComps != nComps) h->eagerCycles = 0;  // buffers may be allocated by the next cycles
     h->nParts = nParts; h->nElmts = nElmts; h->nComps = nComps;
     const uint32_t m = nParts > nElmts ? nParts : nElmts;
     if (m) {
@@ -1039,6 +1060,19 @@ int grow_lists(LbGpuHandle* h, bool* grown) {
     return 0;
 }
 
+// Slabs of other processes: the face planes of an edge slab are updated by launches of their own, ahead of the interior, so
+// that they can travel while the interior is updated (lb_step).  Which faces this handle's slab q splits off:
+void face_plan(LbGpuHandle* h, size_t q, bool* loFace, bool* hiFace) {
+    *loFace = *hiFace = false;
+    if (!lbcomm::active() || h->dynWall) return;
+    int down, up;
+    neighbour_ranks(h, &down, &up);
+    // (an edge slab with fewer than three owned planes has no interior to hide the transport behind)
+    if ((down >= 0 && h->slabs.front()->dev.Z < 5) || (up >= 0 && h->slabs.back()->dev.Z < 5)) return;
+    *loFace = q == 0 && down >= 0;
+    *hiFace = q + 1 == h->slabs.size() && up >= 0;
+}
+
 // coarse blocks of a list build (lb_kernels.cuh, SCAN_MAX_BLOCKS): `chunks` 128-thread chunks on `grid` blocks of `per` chunks
 struct Coarse { uint32_t grid, per; };
 Coarse coarse_blocks(uint32_t chunks) {
@@ -1068,6 +1102,20 @@ int build_lists(LbGpuHandle* h) {
         k_tile_count<<<ct.grid, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, ct.per);
         k_tile_write<<<ct.grid, BLOCK, 0, st>>>(s->tileFlags.p, nT, s->listTileOffset.p, s->tileList.p, ct.per, s->listCounts.p);
         h->launches += 4;
+        bool loFace, hiFace;
+        face_plan(h, q, &loFace, &hiFace);
+        s->hasRanges = loFace || hiFace;
+        if (s->hasRanges) {  // where the face planes and the interior lie in the two ascending lists
+            if (!s->rangeCells.p) {
+                CU(s->rangeCells.alloc(6)); CU(s->listRanges.alloc(12));
+                const uint32_t b = s->ownBegin + (loFace ? s->XY : 0u), e = s->ownEnd - (hiFace ? s->XY : 0u);
+                const uint32_t rc6[6] = { s->ownBegin, b, b, e, e, s->ownEnd };
+                CU(cudaMemcpyAsync(s->rangeCells.p, rc6, sizeof rc6, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));  // rc6 is on the stack; once per slab
+            }
+            k_list_ranges<<<1, 32, 0, st>>>(s->tileList.p, s->candList.p, s->listCounts.p, s->rangeCells.p, 3, s->listRanges.p);
+            ++h->launches;
+        }
         // the host only needs the tile count to size the step kernel's grid; a stale value is fine (grid-stride loop)
         CU(cudaMemcpyAsync(h->pinnedCounts + 8 * q, s->listCounts.p, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     }
@@ -1080,6 +1128,7 @@ int free_surface_step(LbGpuHandle* h) {
     cudaStream_t st = h->stream;
     int rc;
     if ((rc = build_lists(h))) return rc;
+    phase_mark(h, 2);
     // the kernels of the update see the types of before it in typeOld: tbuf(1)
     auto fsdev = [&](Slab* s) {
         Dev d = dev_for(h, s);
@@ -1151,6 +1200,7 @@ int free_surface_step(LbGpuHandle* h) {
     }
     // new interface cells carry n, u, visc taken from their donors: refresh everything a neighbour may read
     if ((rc = exchange(h, G_TYPE | G_MASS | G_MACRO | G_VISC | G_HF))) return rc;
+    phase_mark(h, 3);
     h->typesFlipped = true;  // until the step kernel has run: tbuf(1) holds the types of before this update
     h->listsFresh = false;   // the interface list describes the interface of before this update
     CU(cudaGetLastError());
@@ -1240,7 +1290,12 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
     // issued without waiting for the host -- only then is the count read back, once per further generation.
     // (particles move a fraction of a cell per step: the cells they newly cover touch flagged cells, so generation 0 flags
     // them and generation 1 only confirms that nothing is left)
-    constexpr int SPEC = 2, MAX_GEN = 4096;
+    // One process: the host is not asked at all.  floodGens generations are issued (each gated on the one before, so the
+    // idle ones cost a few empty launches); should the last of them still flag cells the fill is unfinished, which
+    // check_status reports as an error (LBGPU_FLOOD_GENS raises the number, 0 restores the round trip).  A particle would
+    // have to advance more than floodGens - 1 cells in one step for that -- far beyond what the LB step itself tolerates.
+    const bool deferred = !lbcomm::active() && h->floodGens >= 2;
+    const int SPEC = deferred ? h->floodGens : 2, MAX_GEN = deferred ? h->floodGens : 4096;
     bool converged = false;
     for (int gen = 0; gen < MAX_GEN; ++gen) {
         const int cur = 1 + (gen & 1), prev = 1 + ((gen + 1) & 1);
@@ -1258,7 +1313,14 @@ int coupling_step(LbGpuHandle* h, bool rescan) {
         if ((rc = allreduce_sum(h, s0->status.p + cur, 1, lbcomm::ncclUint32))) return rc;
         for (size_t k = 1; k < h->slabs.size(); ++k)
             CU(cudaMemcpyAsync(h->slabs[k]->status.p + cur, s0->status.p + cur, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        if (gen + 1 >= SPEC) {
+        if (deferred) {
+            if (gen + 1 == SPEC) {
+                k_flood_leftover<<<1, 1, 0, st>>>(s0->status.p + cur, s0->status.p + 4);
+                ++h->launches;
+                converged = true;
+                break;
+            }
+        } else if (gen + 1 >= SPEC) {
             CU(cudaMemcpyAsync(h->pinnedStatus, s0->status.p + cur, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             for (auto& sp : h->slabs)
                 CU(cudaMemcpyAsync(h->pinnedStatus + 16 + sp->slot, sp->pCounts.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -1360,11 +1422,13 @@ int lb_step(LbGpuHandle* h) {
     // interior is updated.  Moving walls keep the plain order (their per-block partial sums are indexed by block).
     int down = -1, up = -1;
     if (lbcomm::active()) neighbour_ranks(h, &down, &up);
-    // (an edge slab with fewer than three owned planes has no interior to hide the transport behind: its face launch
-    // would be the whole slab, so such handles use the plain order too)
-    bool overlap = lbcomm::active() && !h->dynWall;
-    if (overlap && ((down >= 0 && h->slabs.front()->dev.Z < 5) || (up >= 0 && h->slabs.back()->dev.Z < 5))) overlap = false;
-    auto launch = [&](Slab* s, uint32_t begin, uint32_t end) {
+    bool overlap = false;
+    {
+        bool lo, hi;
+        for (size_t q = 0; q < h->slabs.size(); ++q) { face_plan(h, q, &lo, &hi); overlap = overlap || lo || hi; }
+    }
+    // part: 0 lower face plane, 1 interior (or the whole slab), 2 upper face plane
+    auto launch = [&](Slab* s, uint32_t begin, uint32_t end, int part) {
         if (end <= begin) return;
         Dev d = dev_for(h, s);
         // the streaming being evaluated happened under the type map of before this cycle's free-surface step
@@ -1375,9 +1439,11 @@ int lb_step(LbGpuHandle* h) {
             // one tile per block, sized with the tile count of the last list build that has reached the host (any
             // value is correct: the kernel strides over the list)
             d.list = s->tileList.p; d.nList = s->listCounts.p + 1;
+            d.range = s->hasRanges ? s->listRanges.p + 4 * part : nullptr;
             uint32_t g = (h->pinnedCounts[8 * s->slot + 1] + TILES_PER_BLOCK - 1) / TILES_PER_BLOCK;
             g = g + g / 16 + 8;
             if (g > s->blocks) g = s->blocks;
+            if (s->hasRanges && part != 1) { const uint32_t gf = (s->XY / TILE + 2 + TILES_PER_BLOCK - 1) / TILES_PER_BLOCK + 1; if (g > gf) g = gf; }  // one plane
             if (h->fsGridPerSM > 0 && g > (uint32_t)(h->fsGridPerSM * h->numSMs)) g = (uint32_t)(h->fsGridPerSM * h->numSMs);
             k<<<g, BLOCK, 0, st>>>(d);
         } else {
@@ -1386,11 +1452,13 @@ int lb_step(LbGpuHandle* h) {
         ++h->launches;
         if (k2 && s->nStatic) {  // the cells next to walls, shells and periodic faces
             d.list = s->staticList.p; d.nList = s->staticCount.p + 1;
+            d.range = nullptr;
             k2<<<(s->nStatic + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(d);
             ++h->launches;
         }
         if (k3) {  // interface cells old and new
             d.list = s->cellList.p; d.nList = s->listCounts.p;
+            d.range = s->hasRanges ? s->listRanges.p + 4 * part + 2 : nullptr;
             k3<<<s->listGrid, BLOCK, 0, st>>>(d);
             ++h->launches;
         }
@@ -1399,8 +1467,10 @@ int lb_step(LbGpuHandle* h) {
     for (size_t q = 0; q < h->slabs.size(); ++q) {
         Slab* s = h->slabs[q].get();
         uint32_t b = s->ownBegin, e = s->ownEnd;
-        if (overlap && q == 0 && down >= 0) { launch(s, b, b + s->XY); b += s->XY; }
-        if (overlap && q + 1 == h->slabs.size() && up >= 0) { launch(s, e - s->XY, e); e -= s->XY; }
+        bool lo, hi;
+        face_plan(h, q, &lo, &hi);
+        if (lo) { launch(s, b, b + s->XY, 0); b += s->XY; }
+        if (hi) { launch(s, e - s->XY, e, 2); e -= s->XY; }
         rest[q] = { b, e };
     }
     if (overlap) {
@@ -1410,7 +1480,7 @@ int lb_step(LbGpuHandle* h) {
         else if ((rc = exchange_remote(h, what, h->commStream))) return rc;
         CU(cudaEventRecord(h->evHalo, h->commStream));
     }
-    for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second);
+    for (size_t q = 0; q < h->slabs.size(); ++q) launch(h->slabs[q].get(), rest[q].first, rest[q].second, 1);
     if (!h->capturing) { CU(cudaEventRecord(h->kev1[ke], st)); ++h->kevCount; }
     // ghostCopy: the mirrors of everything the step kernel stored are copied now (the kernel did not push them)
     const uint32_t whatLocal = what | (h->ghostCopy ? ((macro ? G_MACRO : 0u) | (h->shear ? G_VISC : 0u) | (couple ? G_HF : 0u)) : 0u);
@@ -1422,6 +1492,7 @@ int lb_step(LbGpuHandle* h) {
             ++h->launches;
         }
     }
+    phase_mark(h, 5);
     Slab* s0 = h->slabs[0].get();
     if (h->hasCurved) {
         // streaming through the curved links + their extraMass, after every cell's n, u of this step are in place
@@ -1459,6 +1530,7 @@ int lb_step(LbGpuHandle* h) {
             if ((rc = exchange(h, G_MASS))) return rc;
         }
     }
+    phase_mark(h, 6);
     if (h->nElmts > 0 && couple) {
         // few elements: several blocks share one (the launch should fill the device: ~2 blocks per SM)
         uint32_t split = 1;
@@ -1481,7 +1553,9 @@ int lb_step(LbGpuHandle* h) {
     }
     if (h->typesFlipped) { if ((rc = sync_old_types(h))) return rc; }
     h->typesFlipped = false;
+    phase_mark(h, 7);
     CU(cudaGetLastError());
+    if (!h->capturing) ++h->eagerCycles;
     h->cur ^= 1;
     h->macroValid = macro;
     h->lastStepFirst = first;
@@ -1501,6 +1575,16 @@ int check_status(LbGpuHandle* h) {
         CU(cudaMemcpyAsync(h->pinnedStatus, h->slabs[0]->status.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         if (*h->pinnedStatus) return fail(LBGPU_ECOMM, "peer halo: the planes of the rank %s never arrived (20 s)", *h->pinnedStatus == 1 ? "below" : "above");
+    }
+    if (h->nParts > 0 && !lbcomm::active() && h->floodGens >= 2) {
+        CU(cudaMemcpyAsync(h->pinnedStatus, h->slabs[0]->status.p + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (*h->pinnedStatus) {
+            CU(cudaMemsetAsync(h->slabs[0]->status.p + 4, 0, sizeof(uint32_t), h->stream));
+            return fail(LBGPU_EUNSUPPORTED, "particle coupling: the flood fill of LB::findNewSolid was still flagging cells (%u) after %d generations: "
+                        "a particle moved several cells in one step (LBGPU_FLOOD_GENS raises the number of generations, 0 asks the host each generation)",
+                        *h->pinnedStatus, h->floodGens);
+        }
     }
     for (auto& sp : h->slabs) {
         if (h->fs && h->pinnedCounts[8 * sp->slot + 2] > sp->cellCap)
@@ -1581,7 +1665,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     const size_t nPartial = widest * (size_t)(3 > nSums ? 3 : nSums);
     CU(s->partial.alloc(nPartial));
     CU(s->sums.alloc(8 + 3 * 64)); CU(s->scal.alloc(8));
-    CU(s->counters.alloc(8)); CU(s->status.alloc(4));
+    CU(s->counters.alloc(8)); CU(s->status.alloc(8));  // status: [0] type error, [1],[2] flood-fill counts, [3] peer time-out, [4] unfinished flood fill
     CU(cudaMemsetAsync(s->shearRate.p, 0, sizeof(double) * N, st));
     CU(cudaMemsetAsync(s->hfx.p, 0, sizeof(double) * N, st));
     CU(cudaMemsetAsync(s->hfy.p, 0, sizeof(double) * N, st));
@@ -1589,7 +1673,7 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     CU(cudaMemsetAsync(s->sums.p, 0, sizeof(double) * s->sums.n, st));
     CU(cudaMemsetAsync(s->scal.p, 0, sizeof(double) * 8, st));
     CU(cudaMemsetAsync(s->counters.p, 0, sizeof(unsigned long long) * 8, st));
-    CU(cudaMemsetAsync(s->status.p, 0, sizeof(uint32_t) * 4, st));
+    CU(cudaMemsetAsync(s->status.p, 0, sizeof(uint32_t) * 8, st));
     CU(cudaMemsetAsync(s->partial.p, 0, sizeof(double) * nPartial, st));
 
     tr.mark("allocations + memsets issued");
@@ -1964,6 +2048,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         if (const char* e = getenv("LBGPU_FS_GRID")) h->fsGridPerSM = atoi(e);
         if (const char* e = getenv("LBGPU_WALL_PUSH")) h->wallPushAllowed = atoi(e) != 0;
         if (const char* e = getenv("LBGPU_GRAPH")) h->graphAllowed = atoi(e) != 0;
+        if (const char* e = getenv("LBGPU_FLOOD_GENS")) h->floodGens = atoi(e);
         if (const char* e = getenv("LBGPU_PREFETCH")) h->prefetchBlocks = (uint32_t)atoi(e);
         if (h->prefetchBlocks == 0xffffffffu) h->prefetchBlocks = (uint32_t)h->numSMs * 5u;
         if (const char* e = getenv("LBGPU_PREFETCH_TILES")) h->prefetchTiles = (uint32_t)atoi(e);
@@ -2126,7 +2211,8 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
     CU(cudaEventRecord(h->evA, h->stream));
     h->kevCount = 0;
     int rc;
-    if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
+    phase_mark(h, 0); phase_mark(h, 1);
+    if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
     // LB::computeHydroForces (LB.cpp:1851-1919) applies the direct forcing on every cell flagged inside a particle whether
     // or not goCycle ran the coupling step (demSolve = 0 keeps the flags of the initialisation): the particle lists
     // become resident whenever they are given, only the flag update is tied to doCoupling
@@ -2134,6 +2220,7 @@ int lbGpuStep(LbGpuHandle* h, int doFreeSurface, int doCoupling, int rescanParti
         if ((rc = upload_particles(h, parts, nParts, elmts, nElmts, components, nComponents))) return rc;
     }
     if (doCoupling) { if ((rc = coupling_step(h, rescanParticles != 0))) return rc; }
+    phase_mark(h, 4);
     if ((rc = lb_step(h))) return rc;
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
@@ -2156,19 +2243,24 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     h->kevCount = 0;
     auto cycle = [&]() -> int {
         int rc;
-        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
+        phase_mark(h, 0); phase_mark(h, 1);
+        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
         if (h->nParts > 0) { if ((rc = coupling_step(h, false))) return rc; }  // goCycle's order, particles of the last upload
+        phase_mark(h, 4);
         return lb_step(h);
     };
     uint32_t k = 0;
-    // A free-surface cycle is ~20 small launches around the step kernel: on small lattices their issue cost bounds the
-    // cycle.  Without particles (the coupling step reads a count back every cycle) and in one process the cycle is a fixed
-    // sequence of stream operations, so two consecutive cycles are captured once and replayed.  The last cycles of a call
-    // run eagerly: they carry the CUDA events lbGpuLastKernelMs reads, and the list counts the host sizes grids with.
-    const bool graphable = h->graphAllowed && h->fs && doFreeSurface && h->nParts == 0 && !lbcomm::active() && !h->dem.on && !h->dynWall && count >= 8;
+    // A free-surface or coupled cycle is 10-25 small launches around the step kernel: on small lattices their issue cost
+    // bounds the cycle.  In one process the cycle is a fixed sequence of stream operations (the flood fill of the coupling
+    // step gates its generations on the device, see coupling_step), so two consecutive cycles are captured once and
+    // replayed.  The last cycles of a call run eagerly: they carry the CUDA events lbGpuLastKernelMs reads, and the list
+    // counts the host sizes grids with.
+    const bool fsCycle = h->fs && doFreeSurface, coupled = h->nParts > 0;
+    const bool graphable = h->graphAllowed && !h->phaseOn && (fsCycle || coupled) && (!h->fs || doFreeSurface) &&
+                           (!coupled || h->floodGens >= 2) && !lbcomm::active() && !h->dem.on && !h->dynWall && count >= 8;
     if (graphable) {
         constexpr uint32_t TAIL = 2;
-        for (; k < count && h->steps < 2; ++k) { if (int rc = cycle()) return rc; }
+        for (; k < count && (h->steps < 2 || h->eagerCycles < 2); ++k) { if (int rc = cycle()) return rc; }
         while (count - k >= 2 + TAIL) {
             if (lists_need_growth(h)) {  // an eager cycle re-allocates the lists; the graph holds the old pointers
                 if (h->graph.exec) { cudaGraphExecDestroy(h->graph.exec); h->graph.exec = nullptr; }
@@ -2176,7 +2268,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
                 ++k;
                 continue;
             }
-            bool valid = h->graph.exec != nullptr && h->graph.cur == h->cur;
+            bool valid = h->graph.exec != nullptr && h->graph.cur == h->cur && h->graph.fs == (int)fsCycle && h->graph.nParts == h->nParts;
             for (size_t q = 0; valid && q < h->slabs.size(); ++q) {
                 const uint32_t now = h->pinnedCounts[8 * q + 1], then = h->graph.tiles[q];
                 valid = now <= then + then / 32 && now + now / 4 + 64 >= then;  // the grids carry 1/16 of headroom
@@ -2201,7 +2293,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
                 const cudaError_t ie = cudaGraphInstantiate(&h->graph.exec, g, 0);
                 cudaGraphDestroy(g);
                 if (ie != cudaSuccess) { h->graph.exec = nullptr; return fail(LBGPU_ECUDA, "graph instantiation: %s", cudaGetErrorString(ie)); }
-                h->graph.cur = h->cur;
+                h->graph.cur = h->cur; h->graph.fs = (int)fsCycle; h->graph.nParts = h->nParts;
                 ++h->graph.captures;
             }
             CU(cudaGraphLaunch(h->graph.exec, h->stream));
@@ -2315,9 +2407,12 @@ int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     h->kevCount = 0;
     for (uint32_t k = 0; k < count; ++k) {
         int rc;
+        phase_mark(h, 0);
         if ((rc = dem_step(h, h->lastStepCoupled ? h->slabs[0]->elemOut.p : nullptr))) return rc;
-        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; }
+        phase_mark(h, 1);
+        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
         if ((rc = coupling_step(h, false))) return rc;  // dem.newNeighborList is only raised with periodic DEM boundaries (DEM.cpp:1414)
+        phase_mark(h, 4);
         if ((rc = lb_step(h))) return rc;
     }
     CU(cudaEventRecord(h->evB, h->stream));
@@ -2372,6 +2467,35 @@ int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches) {
         sum += ms;
     }
     *msSum = sum; *launches = n;
+    return LBGPU_OK;
+}
+
+int lbGpuPhaseTrace(LbGpuHandle* h, int on) {
+    if (!h) return fail(LBGPU_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    if (on && h->phaseEv.empty()) {
+        h->phaseEv.resize((size_t)LbGpuHandle::PH_RING * LbGpuHandle::PH_MARKS);
+        for (auto& e : h->phaseEv) CU(cudaEventCreate(&e));
+    }
+    h->phaseOn = on != 0;
+    h->phaseCycles = 0;
+    return LBGPU_OK;
+}
+
+int lbGpuPhaseMs(LbGpuHandle* h, float ms[7], uint32_t* cycles) {
+    if (!h || !ms || !cycles) return fail(LBGPU_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const uint32_t n = (uint32_t)(h->phaseCycles < (uint64_t)LbGpuHandle::PH_RING ? h->phaseCycles : (uint64_t)LbGpuHandle::PH_RING);
+    for (int p = 0; p < 7; ++p) ms[p] = 0.f;
+    for (uint32_t c = 0; c < n; ++c)
+        for (int p = 0; p < 7; ++p) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, h->phaseEv[(size_t)c * LbGpuHandle::PH_MARKS + p], h->phaseEv[(size_t)c * LbGpuHandle::PH_MARKS + p + 1]));
+            ms[p] += t;
+        }
+    for (int p = 0; p < 7; ++p) ms[p] = n ? ms[p] / (float)n : 0.f;
+    *cycles = n;
     return LBGPU_OK;
 }
 
@@ -2886,6 +3010,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->commStream) cudaStreamSynchronize(h->commStream);
     if (h->graph.exec) cudaGraphExecDestroy(h->graph.exec);
+    for (cudaEvent_t e : h->phaseEv) if (e) cudaEventDestroy(e);
     peer_teardown(h);
     h->slabs.clear();
     if (h->evA) cudaEventDestroy(h->evA);

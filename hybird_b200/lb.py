@@ -220,6 +220,17 @@ class LB:
         abi.check(self.lib.lbGpuLaunchCount(self.h, C.byref(v)))
         return int(v.value)
 
+    PHASES = ("dem", "list_build", "free_surface_update", "coupling", "step_kernels_and_halo", "wall_slots_and_sums", "element_forces_and_type_sync")
+
+    def phase_trace(self, on=True):
+        abi.check(self.lib.lbGpuPhaseTrace(self.h, int(bool(on))))
+
+    def phase_ms(self):
+        """Mean device time per cycle and phase over the last (<= 64) cycles since phase_trace(True)."""
+        ms, n = (C.c_float * 7)(), C.c_uint32()
+        abi.check(self.lib.lbGpuPhaseMs(self.h, C.byref(ms), C.byref(n)))
+        return {k: float(ms[i]) for i, k in enumerate(self.PHASES)}, int(n.value)
+
     def graph_info(self):
         """(captures, replays) of the CUDA graph lbGpuRun uses for free-surface cycles without particles."""
         v = (C.c_uint64 * 2)()

@@ -225,6 +225,12 @@ int lbGpuLastStepMs(LbGpuHandle* h, float* ms);
 /* device time of the fused stream-collide kernel alone: sum over the (at most 512 most recent)
  * launches of the last lbGpuStep/lbGpuRun call, CUDA events on the engine's stream. Synchronises. */
 int lbGpuLastKernelMs(LbGpuHandle* h, float* msSum, uint32_t* launches);
+/* Where the device time of a cycle goes: with the trace on, CUDA events are recorded at the phase boundaries of every cycle
+ * (and lbGpuRun launches its cycles one by one); lbGpuPhaseMs averages over the last (at most 64) cycles:
+ * ms[0] DEM sub-steps, [1] list build of the free-surface update, [2] free-surface update, [3] coupling step,
+ * [4] step kernels + step halo, [5] wall slots / moving-wall sums, [6] element forces + type sync.  Synchronises. */
+int lbGpuPhaseTrace(LbGpuHandle* h, int on);
+int lbGpuPhaseMs(LbGpuHandle* h, float ms[7], uint32_t* cycles);
 /* lbGpuRun replays two consecutive cycles of a free-surface lattice without particles as one CUDA graph (single process;
  * LBGPU_GRAPH=0 turns it off): info[0] = captures, info[1] = replays (of two cycles each) so far */
 int lbGpuGraphInfo(LbGpuHandle* h, uint64_t info[2]);

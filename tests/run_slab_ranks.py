@@ -2,7 +2,9 @@
 a golden case cut into WORLD_SIZE z-slabs, one GPU per rank, replayed with the recorded particle inputs;
 rank 0 gathers the fields and writes them to OUT.   python run_slab_ranks.py CASE OUT [--device-init] [--nccl-halo]
 --device-init: every rank initialises its planes on the device (lbGpuInitBox) instead of uploading host arrays;
---nccl-halo: the step halo travels over NCCL send/recv instead of through peer memory (LBGPU_PEER_HALO=0)."""
+--nccl-halo: the step halo travels over NCCL send/recv instead of through peer memory (LBGPU_PEER_HALO=0);
+--dem: the DEM runs on the device too (lbGpuDemInit + lbGpuRunDem, every rank advances the same elements) instead of the
+recorded particle inputs."""
 import os
 import sys
 
@@ -40,14 +42,25 @@ else:
     lb.latticeBolzmannInit(tf[sl], si[sl], n[sl], u[sl], mass[sl], visc[sl])
 steps = min(g.steps, 30)
 Fs, Ms = [], []
-for s, F, M, V, W in gu.replay(g, lb, None):
-    Fs.append(F.copy()); Ms.append(M.copy())
-    if s == steps:
-        break
+extra = {}
+if "--dem" in sys.argv:
+    steps = min(g.steps, 60)
+    lb.demInit(g.dem())
+    for s in range(steps):
+        lb.runDem(1)
+        F, M, V, W = lb.forces()
+        Fs.append(F.copy()); Ms.append(M.copy())
+    st = lb.demState()
+    extra = dict(dem_x0=st["x0"], dem_x1=st["x1"], dem_w0=st["w0"])
+else:
+    for s, F, M, V, W in gu.replay(g, lb, None):
+        Fs.append(F.copy()); Ms.append(M.copy())
+        if s == steps:
+            break
 fields = slabs.gather_fields(lb, rank, world, dist, ("type_flags", "n", "u", "mass", "f"))
 cnt = lb.counts()
 if rank == 0:
-    np.savez(out, steps=steps, F=np.stack(Fs), M=np.stack(Ms), fluid=cnt["fluid"], **fields)
+    np.savez(out, steps=steps, F=np.stack(Fs), M=np.stack(Ms), fluid=cnt["fluid"], **fields, **extra)
 dist.barrier()  # nobody unmaps / frees arrays a neighbour may still be writing into
 lb.close()
 slabs.finalize_comm()

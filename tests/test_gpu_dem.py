@@ -92,6 +92,49 @@ def test_run_dem_equals_single_cycles_and_restart():
         lb.close()
 
 
+def _coupled(g, n_slabs, steps):
+    from hybird_b200 import LB
+    prm = dict(g.params)
+    prm["nSlabs"] = n_slabs; prm["nLocalSlabs"] = n_slabs
+    lb = LB(prm).latticeBolzmannInit(*g.init_arrays()).demInit(g.dem())
+    lb.runDem(steps)
+    out = (lb.demState(), lb.fetch(("type_flags", "f")), lb.forces())
+    lb.close()
+    return out
+
+
+def test_coupled_cycle_on_slabs_of_one_device():
+    """The element forces are summed per slab first, so trajectories agree to rounding rather than bit for bit."""
+    g = gu.Golden("bed_dem")
+    (s1, f1, F1), (s3, f3, F3) = _coupled(g, 1, 80), _coupled(g, 3, 80)
+    assert np.array_equal(f1["type_flags"], f3["type_flags"])
+    for k in ("x0", "x1", "w0"):
+        assert np.abs(s1[k] - s3[k]).max() <= TOL_COUPLED, k
+    assert np.abs(F1[0] - F3[0]).max() <= TOL_COUPLED * np.abs(F1[0]).max()
+
+
+def test_coupled_cycle_on_two_gpus(tmp_path):
+    import os, subprocess, sys
+    import torch
+    import common
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    out = tmp_path / "ranks.npz"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29900 + os.getpid() % 90), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), "bed_dem", str(out), "--dem"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    z = np.load(out)
+    g = gu.Golden("bed_dem")
+    s1, f1, F1 = _coupled(g, 1, int(z["steps"]))
+    assert np.array_equal(z["type_flags"], f1["type_flags"])
+    for k in ("x0", "x1", "w0"):
+        assert np.abs(z["dem_" + k] - s1[k]).max() <= TOL_COUPLED, k
+    # ... and both follow the reference's recorded trajectory
+    parts, elmts, comps, flag = g.trace[int(z["steps"]) - 1]
+    assert np.abs(z["dem_x0"] - parts["x0"]).max() <= TOL_COUPLED
+
+
 def test_partner_list_overflow_is_an_error():
     from hybird_b200 import LB
     from hybird_b200.abi import LbGpuError

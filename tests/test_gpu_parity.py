@@ -120,6 +120,69 @@ def test_graph_replay_equals_eager_cycles(name, monkeypatch):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("name", ["cfg3_mini", "cfg5_mini", "cluster_dem"])
+def test_graph_replay_of_coupled_cycles(name, monkeypatch):
+    """The same with resident particles (coupling step + force reduction inside the captured cycle)."""
+    g = gu.Golden(name)
+    parts, elmts, comps, _ = g.trace[0]
+
+    def start():
+        lb = _gpu(g)
+        if g.params["freeSurface"]:
+            lb.latticeBoltzmannFreeSurfaceStep()
+        lb.latticeBoltzmannCouplingStep(True, elmts, parts, comps)
+        lb.latticeBolzmannStep(elmts, parts)
+        return lb
+    a = start()
+    monkeypatch.setenv("LBGPU_GRAPH", "0")
+    b = start()
+    monkeypatch.delenv("LBGPU_GRAPH")
+    for n in (21, 30):
+        a.run(n); b.run(n)
+    assert a.graph_info()[1] >= 15 and b.graph_info() == (0, 0)
+    Fa, Fb = a.forces(), b.forces()
+    for x, y in zip(Fa, Fb):
+        assert np.array_equal(x, y)
+    sa, sb = a.fetch(), b.fetch()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["two_spheres_kin", "cfg5_mini"])
+def test_flood_fill_with_host_round_trip_is_the_same(name, monkeypatch):
+    """LBGPU_FLOOD_GENS=0: every flood-fill generation asks the host whether to go on (what several processes do)."""
+    g = gu.Golden(name)
+    a = _gpu(g)
+    monkeypatch.setenv("LBGPU_FLOOD_GENS", "0")
+    b = _gpu(g)
+    monkeypatch.delenv("LBGPU_FLOOD_GENS")
+    for (s, *ra), (_, *rb) in zip(gu.replay(g, a, None), gu.replay(g, b, None)):
+        for x, y in zip(ra, rb):
+            assert np.array_equal(x, y)
+    sa, sb = a.fetch(), b.fetch()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close(); b.close()
+
+
+def test_unfinished_flood_fill_is_an_error():
+    """A particle that jumps many cells in one step outruns the generations issued without asking the host: loud error."""
+    from hybird_b200.abi import LbGpuError
+    g = gu.Golden("sphere_kin")
+    lb = _gpu(g)
+    parts, elmts, comps, _ = g.trace[0]
+    lb.latticeBoltzmannCouplingStep(False, elmts, parts, comps)
+    lb.latticeBolzmannStep(elmts, parts)
+    far = parts.copy()
+    far["x0"][:, 2] -= 6.0 * g.params["unitLength"]
+    lb.latticeBoltzmannCouplingStep(False, elmts, far, comps)
+    with pytest.raises(LbGpuError, match="flood fill"):
+        lb.latticeBolzmannStep(elmts, far)
+        lb.synchronize()
+    lb.close()
+
+
 def test_run_keeps_resident_particles_coupled():
     """lbGpuRun(count) with particles uploaded earlier == count x (coupling step + LB step) with the same particles."""
     g = gu.Golden("cfg5_mini")
