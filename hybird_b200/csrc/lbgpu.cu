@@ -397,7 +397,7 @@ struct LbGpuHandle {
     // dense step launches: L2 prefetch distance in blocks (Dev::prefetch).  Default: one generation of resident blocks
     // (5 per SM); LBGPU_PREFETCH overrides (0 = off).  A/B on the 256^3 channel: 0 -> 0.872-0.900 of the copy peak,
     // 370 / 740 -> 0.907-0.951, 1480 -> 0.81, 2960+ -> 0.68 (the prefetched rows no longer survive in L2).
-    uint32_t prefetchBlocks = 0xffffffffu, prefetchTiles = 0;
+    uint32_t prefetchBlocks = 0xffffffffu, prefetchTiles = 0;  // (tile lists: one request per population for four consecutive full tiles)
     bool wallPushAllowed = true;  // LBGPU_WALL_PUSH=0 keeps the list-driven launch for every wall-adjacent cell (A/B)
     bool ghostCopy = false;  // with wallPush, single process: the periodic mirrors are written by k_fill_ghosts after the step
                              // instead of by the step kernel, so the cells next to periodic faces take the bulk path too
@@ -423,6 +423,7 @@ struct LbGpuHandle {
         uint64_t replays = 0, captures = 0;
     } graph;
     bool graphAllowed = true, capturing = false;
+    bool forcesPending = false, lazyForces = false;  // several processes: the element sums of the last step are still per rank / lbGpuRun defers them
     int floodGens = 3;       // single process: flood-fill generations issued per coupling step without a host round trip (0: ask the host)
     uint32_t eagerCycles = 0;  // cycles launched one by one since the particle lists / settings last changed (a graph needs settled buffers)
     // phase trace (lbGpuPhaseTrace): CUDA events at the phase boundaries of a cycle, a ring of the last PH_RING cycles
@@ -935,6 +936,14 @@ int peer_exchange(LbGpuHandle* h, uint32_t what) {
 }
 
 // in-place sum over the ranks of a small device array (no-op in a single-process run)
+int allreduce_sum(LbGpuHandle* h, void* buf, size_t count, int dtype);
+// the per-element sums of the last LB step over all ranks (collective: every rank calls it at the same point)
+int forces_reduced(LbGpuHandle* h) {
+    if (!h->forcesPending) return 0;
+    h->forcesPending = false;
+    return allreduce_sum(h, h->slabs[0]->elemOut.p, (size_t)7 * h->nElmts, lbcomm::ncclFloat64);
+}
+
 int allreduce_sum(LbGpuHandle* h, void* buf, size_t count, int dtype) {
     if (!lbcomm::active() || count == 0) return 0;
     NC(lbcomm::api().AllReduce(buf, buf, count, dtype, lbcomm::ncclSum, lbcomm::comm().comm, h->stream));
@@ -1548,8 +1557,11 @@ int lb_step(LbGpuHandle* h) {
             ++h->launches;
             if (s != s0) { k_add_arrays<<<(7 * h->nElmts + 127) / 128, 128, 0, st>>>(s0->elemOut.p, s->elemOut.p, 7 * h->nElmts); ++h->launches; }
         }
-        // every rank ends up with the forces of all elements (LB::computeHydroForces sums over the whole lattice)
-        if ((rc = allreduce_sum(h, s0->elemOut.p, (size_t)7 * h->nElmts, lbcomm::ncclFloat64))) return rc;
+        // every rank ends up with the forces of all elements (LB::computeHydroForces sums over the whole lattice) -- when
+        // somebody asks for them: the DEM step, lbGpuParticleForces, a checkpoint (forces_reduced).  lbGpuRun's cycles keep
+        // the particles fixed and read no forces, so its ranks skip 7 x nElmts doubles of all-reduce per cycle.
+        h->forcesPending = lbcomm::active();
+        if (!h->lazyForces) { if ((rc = forces_reduced(h))) return rc; }
     }
     if (h->typesFlipped) { if ((rc = sync_old_types(h))) return rc; }
     h->typesFlipped = false;
@@ -2051,6 +2063,7 @@ int init_impl(const LbGpuParams* prm, const uint8_t* type_flags, const uint32_t*
         if (const char* e = getenv("LBGPU_FLOOD_GENS")) h->floodGens = atoi(e);
         if (const char* e = getenv("LBGPU_PREFETCH")) h->prefetchBlocks = (uint32_t)atoi(e);
         if (h->prefetchBlocks == 0xffffffffu) h->prefetchBlocks = (uint32_t)h->numSMs * 5u;
+        h->prefetchTiles = (uint32_t)h->numSMs * 5u;  // A/B, distance 0 / 370 / 740 / 1480 blocks: cfg4 0.504 / 0.493 / 0.492 / 0.498, cfg5 5.33 / 5.22 / 5.18 / 5.26 ms per step
         if (const char* e = getenv("LBGPU_PREFETCH_TILES")) h->prefetchTiles = (uint32_t)atoi(e);
 
         h->shear = prm->nonNewtonian || prm->turbulence;
@@ -2249,6 +2262,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
         phase_mark(h, 4);
         return lb_step(h);
     };
+    struct Lazy { LbGpuHandle* h; explicit Lazy(LbGpuHandle* hh) : h(hh) { h->lazyForces = true; } ~Lazy() { h->lazyForces = false; } } lazy(h);
     uint32_t k = 0;
     // A free-surface or coupled cycle is 10-25 small launches around the step kernel: on small lattices their issue cost
     // bounds the cycle.  In one process the cycle is a fixed sequence of stream operations (the flood fill of the coupling
@@ -2302,6 +2316,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
         }
     }
     for (; k < count; ++k) { if (int rc = cycle()) return rc; }
+    if (int rc = forces_reduced(h)) return rc;  // of the last cycle
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
 }
