@@ -2855,6 +2855,15 @@ int lbGpuCommInit(const uint8_t id[128], int32_t rank, int32_t world, int32_t de
     lbcomm::ncclUniqueId u;
     memcpy(u.internal, id, 128);
     NC(lbcomm::api().CommInitRank(&c.comm, world, u, rank));
+    {   // NCCL connects its rings / trees on the first collective (seconds at 8 ranks): pay that here, once per
+        // process, rather than inside the first lattice's initialisation
+        double* w = nullptr;
+        CU(cudaMalloc((void**)&w, sizeof(double)));
+        CU(cudaMemset(w, 0, sizeof(double)));
+        NC(lbcomm::api().AllReduce(w, w, 1, lbcomm::ncclFloat64, lbcomm::ncclSum, c.comm, (cudaStream_t)0));
+        CU(cudaDeviceSynchronize());
+        CU(cudaFree(w));
+    }
     return LBGPU_OK;
 }
 
