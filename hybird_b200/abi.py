@@ -46,7 +46,7 @@ EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRa
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuCountsLocal", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
            "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo", "lbGpuFluidSummary", "lbGpuWriteVti",
-           "lbGpuDemInit", "lbGpuDemStep", "lbGpuRunDem", "lbGpuDemState", "lbGpuGraphInfo", "lbGpuPhaseTrace", "lbGpuPhaseMs")
+           "lbGpuDemInit", "lbGpuDemStep", "lbGpuRunDem", "lbGpuDemState", "lbGpuDemContacts", "lbGpuGraphInfo", "lbGpuPhaseTrace", "lbGpuPhaseMs")
 
 _lib = None
 
@@ -128,6 +128,8 @@ def load_library(build_if_missing=True):
     L.lbGpuRunDem.argtypes = [vp, C.c_int, C.c_uint32]
     L.lbGpuDemState.restype = C.c_int
     L.lbGpuDemState.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_double * 3)]
+    L.lbGpuDemContacts.restype = C.c_int
+    L.lbGpuDemContacts.argtypes = [vp, vp, vp, vp, vp]
     L.lbGpuPhaseTrace.restype = C.c_int
     L.lbGpuPhaseTrace.argtypes = [vp, C.c_int]
     L.lbGpuPhaseMs.restype = C.c_int

@@ -35,6 +35,7 @@ struct Wall { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int moving, pad
 struct Elmt {
     double x[6][3], xp[6][3], w[6][3], wp[6][3];
     double radius, m, I[3];
+    double fc[4][3];  // FParticle, FWall, MParticle, MWall of the last sub-step (IO::exportForces reads the first two)
     int nearWall, pad;
 };
 struct V3 { double x, y, z; };
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e
     // every element reads the others' PREDICTED state (xp, wp) above and writes only its own corrected state (x, w);
     // xp := x / wp := w (the tail of elmt::correct) happens at the top of the next predict, which overwrites them anyway
     for (int q = 0; q < 6; ++q) { put(el.x[q], x[q]); put(el.w[q], w[q]); }
+    put(el.fc[0], FP); put(el.fc[1], FW); put(el.fc[2], MP); put(el.fc[3], MW);
 }
 
 // the lists the LB side reads (layout of LbGpuParticle / LbGpuElement, physical units): particle::updateCorrected for a

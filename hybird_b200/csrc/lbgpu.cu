@@ -2455,6 +2455,20 @@ int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double inf
     return LBGPU_OK;
 }
 
+int lbGpuDemContacts(LbGpuHandle* h, double* FParticle, double* FWall, double* MParticle, double* MWall) {
+    if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuDemContacts: no device-side DEM on this handle (lbGpuDemInit)");
+    CU(cudaSetDevice(h->device));
+    auto& D = h->dem;
+    std::vector<lbdem::Elmt> E(D.n);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(E.data(), D.e.p, sizeof(lbdem::Elmt) * D.n, cudaMemcpyDeviceToHost));
+    double* out[4] = { FParticle, FWall, MParticle, MWall };
+    for (uint32_t k = 0; k < D.n; ++k)
+        for (int a = 0; a < 4; ++a)
+            if (out[a]) for (int q = 0; q < 3; ++q) out[a][3 * k + q] = E[k].fc[a][q];
+    return LBGPU_OK;
+}
+
 int lbGpuSynchronize(LbGpuHandle* h) {
     if (!h) return fail(LBGPU_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));

@@ -201,6 +201,13 @@ class LB:
         abi.check(self.lib.lbGpuDemState(self.h, abi.ptr(x0), abi.ptr(x1), abi.ptr(w0), C.byref(info)))
         return dict(x0=x0, x1=x1, w0=w0, maxDisp=float(info[0]), rebuilds=int(info[1]), longest_list=int(info[2]))
 
+    def demContacts(self):
+        """elmt::FParticle, FWall, MParticle, MWall of the last DEM sub-step."""
+        n = self._dem_n
+        out = [np.zeros((n, 3)) for _ in range(4)]
+        abi.check(self.lib.lbGpuDemContacts(self.h, *[abi.ptr(a) for a in out]))
+        return dict(FParticle=out[0], FWall=out[1], MParticle=out[2], MWall=out[3])
+
     def synchronize(self):
         abi.check(self.lib.lbGpuSynchronize(self.h))
 

@@ -41,10 +41,12 @@
 
 #include "LB.h"
 #include "IO.h"
+#include "DEM.h"
 
 extern "C" {
 void LB_ref_latticeBoltzmannGet(LB*, GetPot&, GetPot&);
 void LB_ref_latticeBolzmannInit(LB*, cylinderList&, wallList&, particleList&, objectList&);
+void DEM_ref_discreteElementStep(DEM*, IO&);
 #ifdef LBGPU_SHIM_VERIFY
 void LB_ref_latticeBolzmannStep(LB*, elmtList&, particleList&, wallList&);
 void LB_ref_latticeBoltzmannCouplingStep(LB*, bool&, elmtList&, particleList&);
@@ -64,6 +66,10 @@ struct GpuState {
     unsigned int lastScreenExp = 0, lastFluidExp = 0;
     unsigned long long steps = 0, fetches = 0, summaries = 0, vtis = 0;
     double worst = 0.0;
+    // LBGPU_DEM=1: DEM::discreteElementStep runs on the device (lbGpuDem*), for single-sphere elements between plane walls
+    bool demChecked = false, demOnDevice = false, demPending = false;
+    DEM* dem = nullptr;
+    unsigned long long demSteps = 0;
     // fetch buffers
     std::vector<uint8_t> tf;
     std::vector<uint32_t> solid;
@@ -283,10 +289,67 @@ void LB::latticeBoltzmannCouplingStep(bool& newNeighborList, elmtList& elmts, pa
                         st.comps.data(), (uint32_t)st.comps.size()))
             die("lbGpuCouple");
     }
-    pack(st, elmts, particles);
+    if (!st.demPending) pack(st, elmts, particles);  // with the DEM on the device the resident lists are the current ones
     st.rescan = newNeighborList;
     st.couplePending = true;
     newNeighborList = false;  // LB.cpp:258
+}
+
+// ---------------------------------------------------------------------------------------------
+// DEM::discreteElementStep (DEM.cpp:331-376; renamed to DEM_ref_discreteElementStep in DEM.o, see Makefile).  With
+// LBGPU_DEM=1 and a DEM the device covers -- single-sphere elements, plane walls, no periodic DEM boundaries, cylinders or
+// objects, the fluid stepped from the first cycle on -- the sub-steps run on the device inside the same lbGpuRunDem call
+// that runs the LB side of this cycle; the host DEM object only keeps its clock and receives the elements' state back
+// for IO.  Anything else falls through to the reference's own step.
+// ---------------------------------------------------------------------------------------------
+void DEM::discreteElementStep(IO& io) {
+    GpuState* st = states().empty() ? nullptr : &states().begin()->second;
+    if (st && st->h && !st->demChecked) {
+        st->demChecked = true;
+        const char* e = getenv("LBGPU_DEM");
+        bool ok = e && e[0] == '1' && io.lbmSolve && demInitialRepeat == 0.0 && io.saveCount == 0 && !st->verify && !elmts.empty() &&
+                  pbcs.empty() && cylinders.empty() && objects.empty() && ghosts.empty();
+        for (size_t k = 0; ok && k < elmts.size(); ++k) ok = elmts[k].size == 1;
+        if (ok) {
+            LbGpuDemParams P;
+            memset(&P, 0, sizeof P);
+            P.contactModel = sphereMat.contactModel == HERTZIAN ? 1 : 0;
+            P.multiStep = (int32_t)multiStep;
+            P.knConst = sphereMat.knConst; P.ksConst = sphereMat.ksConst; P.dampCoeff = sphereMat.dampCoeff; P.viscTang = sphereMat.viscTang;
+            P.linearStiff = sphereMat.linearStiff; P.frictionCoefPart = sphereMat.frictionCoefPart; P.frictionCoefWall = sphereMat.frictionCoefWall;
+            P.numVisc = numVisc; P.demF[0] = demF.x; P.demF[1] = demF.y; P.demF[2] = demF.z;
+            P.deltat = deltat; P.nebrRange = nebrRange; P.maxDisp = maxDisp;
+            std::vector<LbGpuDemElement> E(elmts.size());
+            for (size_t k = 0; k < elmts.size(); ++k) {
+                const elmt& el = elmts[k];
+                LbGpuDemElement& o = E[k];
+                o.x0[0] = el.x0.x; o.x0[1] = el.x0.y; o.x0[2] = el.x0.z;
+                o.x1[0] = el.x1.x; o.x1[1] = el.x1.y; o.x1[2] = el.x1.z;
+                o.w0[0] = el.w0.x; o.w0[1] = el.w0.y; o.w0[2] = el.w0.z;
+                o.radius = el.radius; o.m = el.m; o.I[0] = el.I.x; o.I[1] = el.I.y; o.I[2] = el.I.z;
+            }
+            std::vector<LbGpuDemWall> W(walls.size());
+            for (size_t k = 0; k < walls.size(); ++k) {
+                const wall& w = walls[k];
+                LbGpuDemWall& o = W[k];
+                memset(&o, 0, sizeof o);
+                o.n[0] = w.n.x; o.n[1] = w.n.y; o.n[2] = w.n.z; o.p[0] = w.p.x; o.p[1] = w.p.y; o.p[2] = w.p.z;
+                o.vel[0] = w.vel.x; o.vel[1] = w.vel.y; o.vel[2] = w.vel.z; o.omega[0] = w.omega.x; o.omega[1] = w.omega.y; o.omega[2] = w.omega.z;
+                o.rotCenter[0] = w.rotCenter.x; o.rotCenter[1] = w.rotCenter.y; o.rotCenter[2] = w.rotCenter.z;
+                o.moving = w.moving ? 1 : 0;
+            }
+            if (lbGpuDemInit(st->h, &P, E.data(), (uint32_t)E.size(), W.empty() ? nullptr : W.data(), (uint32_t)W.size())) die("lbGpuDemInit");
+            st->demOnDevice = true;
+            st->dem = this;
+            cout << "lbgpu shim: DEM sub-steps on the GPU (" << elmts.size() << " spheres, " << walls.size() << " walls, " << multiStep << " per LB step)" << endl;
+        } else if (e && e[0] == '1') {
+            cout << "lbgpu shim: LBGPU_DEM=1, but this DEM is outside what the device covers (clusters, periodic boundaries, cylinders, "
+                    "objects, demInitialRepeat, saveCount): the host DEM runs" << endl;
+        }
+    }
+    if (!st || !st->demOnDevice) { DEM_ref_discreteElementStep(this, io); return; }
+    for (unsigned int it = 0; it < multiStep; ++it) { demTimeStep++; demTime += deltat; }  // the clock, accumulated as the reference does
+    st->demPending = true;  // the sub-steps themselves run inside this cycle's lbGpuRunDem (LB::latticeBolzmannStep)
 }
 
 void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList& walls) {
@@ -300,11 +363,36 @@ void LB::latticeBolzmannStep(elmtList& elmts, particleList& particles, wallList&
         for (size_t e = 0; e < refElmts.size(); ++e) refF.push_back(refElmts[e].FHydro);
     }
 #endif
+    if (st.demPending) {
+        // goCycle's order on the device: DEM step, free-surface step, coupling step, LB step
+        if (lbGpuRunDem(st.h, st.fsRequested ? 1 : 0, 1)) die("lbGpuRunDem");
+        ++st.demSteps;
+        const size_t nE = elmts.size();
+        std::vector<double> x0(3 * nE), x1(3 * nE), w0(3 * nE), FP(3 * nE), FW(3 * nE), MP(3 * nE), MW(3 * nE);
+        double info[3];
+        if (lbGpuDemState(st.h, x0.data(), x1.data(), w0.data(), info)) die("lbGpuDemState");
+        if (lbGpuDemContacts(st.h, FP.data(), FW.data(), MP.data(), MW.data())) die("lbGpuDemContacts");
+        // what IO and the driver read from the DEM object between steps: the corrected state of every element, its particle
+        for (size_t e = 0; e < nE; ++e) {
+            elmt& el = elmts[e];
+            el.x0 = el.xp0 = tVect(x0[3 * e], x0[3 * e + 1], x0[3 * e + 2]);
+            el.x1 = el.xp1 = tVect(x1[3 * e], x1[3 * e + 1], x1[3 * e + 2]);
+            el.w0 = el.wp0 = el.wGlobal = el.wpGlobal = el.wLocal = el.wpLocal = tVect(w0[3 * e], w0[3 * e + 1], w0[3 * e + 2]);
+            el.FParticle = tVect(FP[3 * e], FP[3 * e + 1], FP[3 * e + 2]); el.FWall = tVect(FW[3 * e], FW[3 * e + 1], FW[3 * e + 2]);
+            el.MParticle = tVect(MP[3 * e], MP[3 * e + 1], MP[3 * e + 2]); el.MWall = tVect(MW[3 * e], MW[3 * e + 1], MW[3 * e + 2]);
+        }
+        for (size_t k = 0; k < particles.size(); ++k) {
+            const elmt& el = elmts[particles[k].clusterIndex];
+            particles[k].x0 = el.x0; particles[k].x1 = el.x1;  // particle::updateCorrected for a one-sphere element
+        }
+        st.dem->maxDisp = info[0];
+    } else {
     if (!st.couplePending) pack(st, elmts, particles);  // computeHydroForces reads the lists it is given (LB.cpp:1851)
     if (lbGpuStep(st.h, st.fsRequested ? 1 : 0, st.couplePending ? 1 : 0, st.rescan ? 1 : 0, st.parts.data(), (uint32_t)st.parts.size(),
                   st.elmts.data(), (uint32_t)st.elmts.size(), st.comps.data(), (uint32_t)st.comps.size()))
         die("lbGpuStep");
-    st.fsRequested = false; st.couplePending = false; st.rescan = false;
+    }
+    st.fsRequested = false; st.couplePending = false; st.rescan = false; st.demPending = false;
     ++st.steps;
     const size_t nE = elmts.size(), nW = walls.size();
     std::vector<double> F(3 * nE + 1), M(3 * nE + 1), V(nE + 1), W(3 * nW + 1);

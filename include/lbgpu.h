@@ -184,6 +184,9 @@ int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count);
 /* elmt::x0, x1, w0 (3*nElmts each; any may be NULL); info[0] = DEM::maxDisp, info[1] = neighbour-table rebuilds so far,
  * info[2] = longest partner list.  Synchronises. */
 int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double info[3]);
+/* elmt::FParticle, FWall, MParticle, MWall of the last sub-step (3*nElmts each; any may be NULL): what IO::exportForces and
+ * the particle files print (IO.cpp:930-938).  Synchronises. */
+int lbGpuDemContacts(LbGpuHandle* h, double* FParticle, double* FWall, double* MParticle, double* MWall);
 
 /* Results of the last step in physical units; any pointer may be NULL. Synchronises. */
 int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHydro /*3*nElmts*/,

@@ -117,3 +117,34 @@ def test_verify_mode_reference_steps_alongside(name, steps, tmp_path):
     lines = [l for l in out.splitlines() if l.startswith("lbgpu verify: step")]
     assert len(lines) == steps, out[-2000:]
     assert "FAILED" not in out
+
+
+@pytest.mark.parametrize("name,steps", [("spheres_hertz", 80), ("bed_dem", 120)])
+def test_dem_on_device_through_the_reference_driver(name, steps, tmp_path):
+    """LBGPU_DEM=1: the shim's DEM::discreteElementStep keeps only the DEM clock on the host; the sub-steps (contacts, tables,
+    Gear integration) run on the device inside the cycle's lbGpuRunDem.  The unmodified driver's screen lines, force file and
+    particle files (positions, velocities, spins, contact / wall / hydrodynamic forces per particle) must be the reference's."""
+    _need_binaries()
+    case = dict(cases.catalogue()[name])
+    case.update(maximumTimeSteps=steps, screenExpTime=5.0, partExpTime=20.0)
+    cfg = cases.write_case_files(case, str(tmp_path))
+    rc_r, out_r = _run(REF_BIN, cfg, str(tmp_path / "ref"), threads=1)
+    rc_g, out_g = _run(GPU_BIN, cfg, str(tmp_path / "gpu"), env={"LBGPU_DEM": "1"}, threads=1)
+    assert rc_r == 0, out_r[-2000:]
+    assert rc_g == 0, out_g[-2000:]
+    assert "DEM sub-steps on the GPU" in out_g
+    for f in ("export.dat", "force.dat"):
+        tr, tg = open(tmp_path / "ref" / "run" / f).read(), open(tmp_path / "gpu" / "run" / f).read()
+        assert len(tr.splitlines()) == len(tg.splitlines()) >= 5, f
+        a, b = _numbers(tr), _numbers(tg)
+        assert a.shape == b.shape, f
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-9), (f, np.abs(a - b).max())
+    fr = sorted(os.listdir(tmp_path / "ref" / "run" / "particleData"))
+    fg = sorted(os.listdir(tmp_path / "gpu" / "run" / "particleData"))
+    assert fr == fg and len(fr) >= 3
+    for f in fr:
+        a = _numbers(open(tmp_path / "ref" / "run" / "particleData" / f).read())
+        b = _numbers(open(tmp_path / "gpu" / "run" / "particleData" / f).read())
+        assert a.shape == b.shape, f
+        # six printed digits; forces that cancel to ~0 are compared against the file's force scale
+        assert np.allclose(a, b, rtol=2e-5, atol=1e-7), (f, np.abs(a - b).max())
