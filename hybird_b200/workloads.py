@@ -153,6 +153,9 @@ def catalogue():
     C["cfg4"] = make_case("cfg4", lbSizeX=512, lbSizeY=128, lbSizeZ=256, freeSurfaceSolve=1, nonNewtonianSolve=1,
                           lbFZ=-1e-4, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,
                           fluid_box=(1, 128, 1, 126, 1, 192))
+    # (A/B of the step kernel's variants on cfg4's geometry: the same dam break with a Newtonian fluid, and the full column)
+    C["cfg4_newtonian"] = make_case("cfg4_newtonian", lbSizeX=512, lbSizeY=128, lbSizeZ=256, freeSurfaceSolve=1, lbFZ=-1e-4,
+                                    initVisc=1.0 / 30.0, fluid_box=(1, 128, 1, 126, 1, 192))
     C["cfg4_mini"] = make_case("cfg4_mini", lbSizeX=40, lbSizeY=12, lbSizeZ=24, freeSurfaceSolve=1, nonNewtonianSolve=1,
                                lbFZ=-1e-4, plasticVisc=1.0 / 30.0, yieldStress=1e-5, initVisc=1.0 / 30.0,
                                fluid_box=(1, 12, 1, 10, 1, 18))
