@@ -157,13 +157,15 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool view = false;  // part of somebody else's allocation (one cudaMalloc costs ~1 ms whatever its size)
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
         return cudaMalloc((void**)&p, count * sizeof(T));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void set_view(T* ptr, size_t count) { release(); p = ptr; n = count; view = true; }
+    void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
     ~DevBuf() { release(); }
 };
 
@@ -179,7 +181,7 @@ struct Slab {
     uint32_t blocks = 0;                 // blocks covering all N cells
     uint32_t ownBegin = 0, ownEnd = 0;   // cells of the planes the per-cell kernels cover (everything but remote ghost planes)
     Dev dev;                             // template for kernel parameters (pointers filled per launch)
-    DevBuf<double> fA, fB, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;
+    DevBuf<double> fA, fB, macroPool, n, ux, uy, uz, mass, newMass, visc, shearRate, hfx, hfy, hfz;  // n .. hfz (but newMass) are views into macroPool
     DevBuf<uint8_t> type0, type1, mark;
     DevBuf<uint32_t> solidIndex, bulk;
     DevBuf<uint32_t> curveRow;  // curved walls: row of the handle's curveDelta per cell
@@ -385,7 +387,7 @@ struct LbGpuHandle {
     // one chunk overlaps the DMA of the other; a plain cudaMemcpy from pageable memory serialises the two)
     char* stage[2] = { nullptr, nullptr };
     cudaEvent_t stageEv[2] = { nullptr, nullptr };
-    static constexpr size_t STAGE = 16u << 20;
+    static constexpr size_t STAGE = 4u << 20;  // (pinning costs ~1 ms per MB: two 16 MB stages were 30 ms of the first upload)
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
@@ -522,9 +524,24 @@ Dev dev_all(LbGpuHandle* h, Slab* s) {  // same, covering every cell including r
 }
 uint32_t own_blocks(const Slab* s) { return (s->ownEnd - s->ownBegin + BLOCK - 1) / BLOCK; }
 
+// The pinned stages are pooled over the life of the process: pinning 2 x 16 MB costs several milliseconds, which a host that
+// creates one engine after another (a parameter sweep, the bench's end-to-end job) would pay every time.
+struct StagePool {
+    std::mutex m;
+    std::vector<char*> free_;
+    char* get() {
+        { std::lock_guard<std::mutex> g(m); if (!free_.empty()) { char* p = free_.back(); free_.pop_back(); return p; } }
+        char* p = nullptr;
+        if (cudaHostAlloc((void**)&p, LbGpuHandle::STAGE, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        return p;
+    }
+    void put(char* p) { std::lock_guard<std::mutex> g(m); free_.push_back(p); }
+};
+StagePool& stage_pool() { static StagePool* p = new StagePool(); return *p; }  // never destroyed (the driver may be gone at exit)
+
 int ensure_stages(LbGpuHandle* h) {
     for (int k = 0; k < 2; ++k) {
-        if (!h->stage[k]) CU(cudaMallocHost((void**)&h->stage[k], LbGpuHandle::STAGE));
+        if (!h->stage[k]) { h->stage[k] = stage_pool().get(); if (!h->stage[k]) return fail(LBGPU_ECUDA, "pinned staging buffer: out of memory"); }
         if (!h->stageEv[k]) CU(cudaEventCreateWithFlags(&h->stageEv[k], cudaEventDisableTiming));
     }
     return 0;
@@ -1648,9 +1665,12 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
             CU(cudaMemset2DAsync(fb + s->pad + N, sizeof(double) * s->stride, 0, sizeof(double) * (s->stride - N), Q, st));
     }
     tr.mark("their memsets issued");
-    CU(s->n.alloc(N)); CU(s->ux.alloc(N)); CU(s->uy.alloc(N)); CU(s->uz.alloc(N));
-    CU(s->mass.alloc(N)); CU(s->visc.alloc(N)); CU(s->shearRate.alloc(N));
-    CU(s->hfx.alloc(N)); CU(s->hfy.alloc(N)); CU(s->hfz.alloc(N));
+    {   // ten per-cell arrays out of one allocation (each 256-byte aligned)
+        const size_t NA = ((size_t)N + 31) / 32 * 32;
+        CU(s->macroPool.alloc(10 * NA));
+        DevBuf<double>* arr[10] = { &s->n, &s->ux, &s->uy, &s->uz, &s->mass, &s->visc, &s->shearRate, &s->hfx, &s->hfy, &s->hfz };
+        for (int k = 0; k < 10; ++k) arr[k]->set_view(s->macroPool.p + (size_t)k * NA, N);
+    }
     tr.mark("macroscopic arrays allocated");
     const size_t NT = ((size_t)N + LIST_CELLS - 1) / LIST_CELLS * LIST_CELLS + BLOCK;  // the last block of a pass reads whole
     CU(s->type0.alloc(NT)); CU(s->solidIndex.alloc(N));
@@ -1720,6 +1740,8 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     {
         const bool gx = d.ghost[0], gy = d.ghost[2], gzLocal = perZ && !s->remoteLo;
         std::vector<uint32_t> gd, gs, gp;
+        std::vector<uint32_t> pmTable(512, 0xffffffffu);
+        { const size_t guess = 2 * ((size_t)X * Y + (size_t)Y * Zl + (size_t)X * Zl) + 64; gd.reserve(guess); gs.reserve(guess); gp.reserve(guess); }
         int cx[Q], cy[Q], cz[Q];  // (cvec() rebuilds its table on every run-time call)
         for (int j = 0; j < Q; ++j) { cx[j] = CXh(j); cy[j] = CYh(j); cz[j] = CZh(j); }
         auto idx = [&](int x, int y, int z) { return (uint32_t)x + (uint32_t)X * ((uint32_t)y + (uint32_t)Y * (uint32_t)z); };
@@ -1740,14 +1762,21 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
                     if (gx) { if (x == 0) sx = X - 2; else if (x == X - 1) sx = 1; }
                     if (gy) { if (y == 0) sy = Y - 2; else if (y == Y - 1) sy = 1; }
                     if (gzLocal) { if (z == 0) sz = Zl - 2; else if (z == Zl - 1) sz = 1; }
-                    uint32_t pm = 0;
-                    for (int j = 1; j < Q; ++j) {
-                        // population j is pulled out of this ghost by the cell at ghost + c_j, if that is an interior cell
-                        const int tx = x + cx[j], ty = y + cy[j], tz = z + cz[j];
-                        // (across a slab cut the pulling cell is the neighbour slab's: its copy of this plane is taken from here)
-                        if (tx >= 1 && tx <= X - 2 && ty >= 1 && ty <= Y - 2 && tz >= (s->remoteLo ? 0 : 1) && tz <= (s->remoteHi ? Zl - 1 : Zl - 2))
-                            pm |= 1u << j;
+                    // population j is pulled out of this ghost by the cell at ghost + c_j, if that is an interior cell (across a
+                    // slab cut the pulling cell is the neighbour slab's: its copy of this plane is taken from here).  Whether
+                    // coordinate v + c lies inside depends on v's class only: the 19-bit masks of the 125 class triples are
+                    // tabulated on first use (the loop over the 18 links per shell cell cost 6 ms on 256^3)
+                    auto cls = [](int v, int lo, int hi) {  // bit (c + 1): lo <= v + c <= hi
+                        return (uint32_t)((v - 1 >= lo && v - 1 <= hi) ? 1 : 0) | (uint32_t)((v >= lo && v <= hi) ? 2 : 0) | (uint32_t)((v + 1 >= lo && v + 1 <= hi) ? 4 : 0);
+                    };
+                    const uint32_t key = cls(x, 1, X - 2) | (cls(y, 1, Y - 2) << 3) | (cls(z, s->remoteLo ? 0 : 1, s->remoteHi ? Zl - 1 : Zl - 2) << 6);
+                    if (pmTable[key] == 0xffffffffu) {
+                        uint32_t m = 0;
+                        for (int j = 1; j < Q; ++j)
+                            if (((key >> (cx[j] + 1)) & 1u) && ((key >> (3 + cy[j] + 1)) & 1u) && ((key >> (6 + cz[j] + 1)) & 1u)) m |= 1u << j;
+                        pmTable[key] = m;
                     }
+                    uint32_t pm = pmTable[key];
                     if (h->slip) pm = (1u << Q) - 1u;
                     gd.push_back(idx(x, y, z)); gs.push_back(idx(sx, sy, sz)); gp.push_back(pm);
                 }
@@ -1789,11 +1818,15 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
     // staged upload: host (pageable) -> device scratch -> SoA
     { int rc;
       if ((rc = h2d_staged(h, s->type0.p, type_flags + hostOff, N))) return rc;
+      tr.mark("type up");
       if ((rc = h2d_staged(h, s->solidIndex.p, solidIndex + hostOff, sizeof(uint32_t) * N))) return rc;
+      tr.mark("solidIndex up");
       if ((rc = h2d_staged(h, s->n.p, n + hostOff, sizeof(double) * N))) return rc;
+      tr.mark("n up");
       if ((rc = h2d_staged(h, s->mass.p, mass + hostOff, sizeof(double) * N))) return rc;
+      tr.mark("mass up");
       if ((rc = h2d_staged(h, s->visc.p, visc + hostOff, sizeof(double) * N))) return rc; }
-    tr.mark("type, solidIndex, n, mass, visc up");
+    tr.mark("visc up");
     {
         DevBuf<double> tmp;
         CU(tmp.alloc((size_t)3 * N));
@@ -3059,7 +3092,7 @@ int lbGpuFinalize(LbGpuHandle* h) {
     for (cudaEvent_t e : h->kev0) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : h->kev1) if (e) cudaEventDestroy(e);
     if (h->pinned) cudaFreeHost(h->pinned);
-    for (int k = 0; k < 2; ++k) { if (h->stage[k]) cudaFreeHost(h->stage[k]); if (h->stageEv[k]) cudaEventDestroy(h->stageEv[k]); }
+    for (int k = 0; k < 2; ++k) { if (h->stage[k]) stage_pool().put(h->stage[k]); if (h->stageEv[k]) cudaEventDestroy(h->stageEv[k]); }
     if (h->pinnedStatus) cudaFreeHost(h->pinnedStatus);
     if (h->pinnedCounts) cudaFreeHost(h->pinnedCounts);
     if (h->stream) cudaStreamDestroy(h->stream);
