@@ -356,6 +356,9 @@ def main_ours(args, rank, world, local_rank):
     FIELDS = ("type_flags", "n", "u", "mass")
     if world == 1:
         Kj = min(K, 1000)
+        # the job is a run of its own, from host arrays to host arrays: the resident engine is closed first (its device memory
+        # stays with the library for the next engine of the same shape, see DevCache in lbgpu.cu)
+        lb.close()
         st_host = li.build_state(case, parts if len(parts) else None)  # the caller's data: not timed
         # ... resident in host memory like a driver's own arrays: numpy hands out untouched zero pages for np.zeros (solidIndex of
         # a lattice without particles), whose first read inside lbGpuInit would be timed as page faults, not as a transfer

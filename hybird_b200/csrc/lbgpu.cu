@@ -20,6 +20,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <memory>
+#include <map>
 #include <mutex>
 #include <new>
 #include <chrono>
@@ -153,19 +154,70 @@ lb::FastDiv make_div(uint32_t d) {
     return f;
 }
 
+// Device memory of closed engines is kept for the next one (per device, exact sizes of 1 MB and more, LBGPU_CACHE=0 turns it
+// off): a host that builds one lattice after another of the same shape -- a parameter sweep, a restart, the bench's end-to-end
+// job -- then issues no cudaMalloc at all.  A fresh cudaMalloc of a few GB normally takes ~1 ms, but was measured at 100-280 ms
+// per call right after another process had released its memory.  Nothing is assumed about the contents of an allocation.
+struct DevCache {
+    std::mutex m;
+    std::multimap<std::pair<int, size_t>, void*> blocks;
+    size_t bytes = 0;
+    bool on = true;
+    static constexpr size_t MIN_BYTES = 1u << 20, LIMIT = 120ull << 30;
+    DevCache() { if (const char* e = getenv("LBGPU_CACHE")) on = atoi(e) != 0; }
+    void* take(int dev, size_t b) {
+        std::lock_guard<std::mutex> g(m);
+        auto it = blocks.find({ dev, b });
+        if (it == blocks.end()) return nullptr;
+        void* p = it->second;
+        blocks.erase(it);
+        bytes -= b;
+        return p;
+    }
+    bool give(int dev, size_t b, void* p) {
+        if (!on || b < MIN_BYTES) return false;
+        std::lock_guard<std::mutex> g(m);
+        if (bytes + b > LIMIT) return false;
+        blocks.insert({ { dev, b }, p });
+        bytes += b;
+        return true;
+    }
+    void trim(int dev) {  // out of memory: hand everything cached on this device back to the driver
+        std::lock_guard<std::mutex> g(m);
+        for (auto it = blocks.begin(); it != blocks.end();) {
+            if (it->first.first == dev) { cudaFree(it->second); bytes -= it->first.second; it = blocks.erase(it); } else ++it;
+        }
+    }
+};
+inline DevCache& dev_cache() { static DevCache* c = new DevCache(); return *c; }  // never destroyed (the driver may be gone at exit)
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     bool view = false;  // part of somebody else's allocation (one cudaMalloc costs ~1 ms whatever its size)
+    int dev = -1;
     cudaError_t alloc(size_t count) {
         release();
         n = count;
         if (count == 0) return cudaSuccess;
-        return cudaMalloc((void**)&p, count * sizeof(T));
+        const size_t b = count * sizeof(T);
+        cudaGetDevice(&dev);
+        if (b >= DevCache::MIN_BYTES) { p = (T*)dev_cache().take(dev, b); if (p) return cudaSuccess; }
+        cudaError_t e = cudaMalloc((void**)&p, b);
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); dev_cache().trim(dev); e = cudaMalloc((void**)&p, b); }
+        if (e != cudaSuccess) { p = nullptr; n = 0; }
+        return e;
     }
     void set_view(T* ptr, size_t count) { release(); p = ptr; n = count; view = true; }
-    void release() { if (p && !view) cudaFree(p); p = nullptr; n = 0; view = false; }
+    void release() {
+        if (p && !view) {
+            // like cudaFree, which waits for the device: work that still uses the block may be in flight on some stream
+            if (dev_cache().on && n * sizeof(T) >= DevCache::MIN_BYTES) cudaDeviceSynchronize();
+            if (!dev_cache().give(dev, n * sizeof(T), (void*)p)) cudaFree(p);
+        }
+        p = nullptr; n = 0; view = false;
+    }
     ~DevBuf() { release(); }
 };
 
@@ -387,7 +439,12 @@ struct LbGpuHandle {
     // one chunk overlaps the DMA of the other; a plain cudaMemcpy from pageable memory serialises the two)
     char* stage[2] = { nullptr, nullptr };
     cudaEvent_t stageEv[2] = { nullptr, nullptr };
-    static constexpr size_t STAGE = 4u << 20;  // (pinning costs ~1 ms per MB: two 16 MB stages were 30 ms of the first upload)
+    static constexpr size_t STAGE_MAX = 16u << 20;
+    static size_t stage_bytes() {  // LBGPU_STAGE_MB: 1..16 (pinning costs ~1 ms per MB: two 16 MB stages were 30 ms of the first upload)
+        static size_t v = 0;
+        if (!v) { int mb = 4; if (const char* e = getenv("LBGPU_STAGE_MB")) mb = atoi(e); if (mb < 1) mb = 1; if (mb > 16) mb = 16; v = (size_t)mb << 20; }
+        return v;
+    }
     uint32_t* pinnedStatus = nullptr;
     uint32_t nParts = 0, nElmts = 0, nComps = 0;
     int cur = 0;      // population buffer holding the latest post-collision state (0 = A)
@@ -532,7 +589,7 @@ struct StagePool {
     char* get() {
         { std::lock_guard<std::mutex> g(m); if (!free_.empty()) { char* p = free_.back(); free_.pop_back(); return p; } }
         char* p = nullptr;
-        if (cudaHostAlloc((void**)&p, LbGpuHandle::STAGE, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaHostAlloc((void**)&p, LbGpuHandle::stage_bytes(), getenv("LBGPU_STAGE_PLAIN") ? cudaHostAllocDefault : cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
         return p;
     }
     void put(char* p) { std::lock_guard<std::mutex> g(m); free_.push_back(p); }
@@ -549,14 +606,14 @@ int ensure_stages(LbGpuHandle* h) {
 // pageable host -> device, chunked through the two pinned stages; asynchronous on the handle's stream for the caller
 // (the source may be reused on return)
 int h2d_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
-    if (bytes < LbGpuHandle::STAGE) {  // small lattices: not worth pinning two stages
+    if (bytes < LbGpuHandle::stage_bytes()) {  // small lattices: not worth pinning two stages
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
         return 0;
     }
     if (int rc = ensure_stages(h)) return rc;
     size_t off = 0;
-    for (int k = 0; off < bytes; ++k, off += LbGpuHandle::STAGE) {
-        const size_t len = bytes - off < LbGpuHandle::STAGE ? bytes - off : LbGpuHandle::STAGE;
+    for (int k = 0; off < bytes; ++k, off += LbGpuHandle::stage_bytes()) {
+        const size_t len = bytes - off < LbGpuHandle::stage_bytes() ? bytes - off : LbGpuHandle::stage_bytes();
         const int b = k & 1;
         if (k >= 2) CU(cudaEventSynchronize(h->stageEv[b]));
         par_memcpy(h->stage[b], (const char*)src + off, len);
@@ -569,7 +626,7 @@ int h2d_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
 }
 // device -> pageable host, the same way; complete on return
 int d2h_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
-    if (bytes < LbGpuHandle::STAGE) {
+    if (bytes < LbGpuHandle::stage_bytes()) {
         CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
         return 0;
@@ -577,20 +634,20 @@ int d2h_staged(LbGpuHandle* h, void* dst, const void* src, size_t bytes) {
     if (int rc = ensure_stages(h)) return rc;
     size_t off = 0, done = 0;
     int k = 0;
-    for (; off < bytes; ++k, off += LbGpuHandle::STAGE) {
-        const size_t len = bytes - off < LbGpuHandle::STAGE ? bytes - off : LbGpuHandle::STAGE;
+    for (; off < bytes; ++k, off += LbGpuHandle::stage_bytes()) {
+        const size_t len = bytes - off < LbGpuHandle::stage_bytes() ? bytes - off : LbGpuHandle::stage_bytes();
         const int b = k & 1;
         if (k >= 2) {  // the chunk that used this stage two rounds ago has landed: hand it to the caller
             CU(cudaEventSynchronize(h->stageEv[b]));
-            par_memcpy((char*)dst + done, h->stage[b], LbGpuHandle::STAGE);
-            done += LbGpuHandle::STAGE;
+            par_memcpy((char*)dst + done, h->stage[b], LbGpuHandle::stage_bytes());
+            done += LbGpuHandle::stage_bytes();
         }
         CU(cudaMemcpyAsync(h->stage[b], (const char*)src + off, len, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->stageEv[b], h->stream));
     }
     for (int r = (k >= 2 ? k - 2 : 0); r < k; ++r) {
         const int b = r & 1;
-        const size_t len = bytes - done < LbGpuHandle::STAGE ? bytes - done : LbGpuHandle::STAGE;
+        const size_t len = bytes - done < LbGpuHandle::stage_bytes() ? bytes - done : LbGpuHandle::stage_bytes();
         CU(cudaEventSynchronize(h->stageEv[b]));
         par_memcpy((char*)dst + done, h->stage[b], len);
         done += len;
@@ -1828,11 +1885,13 @@ int build_slab(LbGpuHandle* h, Slab* s, int hostZ0, const uint8_t* type_flags, c
       if ((rc = h2d_staged(h, s->visc.p, visc + hostOff, sizeof(double) * N))) return rc; }
     tr.mark("visc up");
     {
-        DevBuf<double> tmp;
-        CU(tmp.alloc((size_t)3 * N));
-        if (int rc = h2d_staged(h, tmp.p, u + 3 * hostOff, sizeof(double) * 3 * N)) return rc;
-        k_split3<<<s->blocks, BLOCK, 0, st>>>(N, tmp.p, s->ux.p, s->uy.p, s->uz.p);
-        CU(cudaStreamSynchronize(st));
+        // the cell-major velocities land in population buffer B, which nothing has written yet (k_upload_f below fills every
+        // cell's slots of both buffers), and are split into the three arrays from there: no temporary allocation
+        double* scratch = s->fB.p + s->pad;
+        if (int rc = h2d_staged(h, scratch, u + 3 * hostOff, sizeof(double) * 3 * N)) return rc;
+        k_split3<<<s->blocks, BLOCK, 0, st>>>(N, scratch, s->ux.p, s->uy.p, s->uz.p);
+        if (s->stride > N)  // the tails of the planes the scratch covered are zero again for the speculative pulls
+            CU(cudaMemset2DAsync(s->fB.p + s->pad + N, sizeof(double) * s->stride, 0, sizeof(double) * (s->stride - N), Q, st));
     }
     tr.mark("u up + split");
     Dev dd = dev_all(h, s);
