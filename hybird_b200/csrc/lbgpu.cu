@@ -2968,6 +2968,28 @@ int lbGpuCommInit(const uint8_t id[128], int32_t rank, int32_t world, int32_t de
         CU(cudaMemset(w, 0, sizeof(double)));
         NC(lbcomm::api().AllReduce(w, w, 1, lbcomm::ncclFloat64, lbcomm::ncclSum, c.comm, (cudaStream_t)0));
         CU(cudaDeviceSynchronize());
+        // ... and so is the first mapping of a neighbour's memory (peer access between the two devices is enabled then):
+        // every rank exports a dummy block, the handles are all-gathered, the ring neighbours' blocks are opened and closed
+        if (lbcomm::api().AllGather) {
+            cudaIpcMemHandle_t mine;
+            char* dh = nullptr;
+            if (cudaIpcGetMemHandle(&mine, w) == cudaSuccess && cudaMalloc((void**)&dh, sizeof mine * (size_t)(world + 1)) == cudaSuccess) {
+                std::vector<cudaIpcMemHandle_t> all((size_t)world);
+                CU(cudaMemcpy(dh, &mine, sizeof mine, cudaMemcpyHostToDevice));
+                NC(lbcomm::api().AllGather(dh, dh + sizeof mine, sizeof mine, lbcomm::ncclUint8, c.comm, (cudaStream_t)0));
+                CU(cudaMemcpy(all.data(), dh + sizeof mine, sizeof mine * (size_t)world, cudaMemcpyDeviceToHost));
+                const int nbs[2] = { (rank + world - 1) % world, (rank + 1) % world };
+                for (int k = 0; k < (world > 2 ? 2 : 1); ++k) {
+                    void* base = nullptr;
+                    if (nbs[k] != rank && cudaIpcOpenMemHandle(&base, all[(size_t)nbs[k]], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) cudaIpcCloseMemHandle(base);
+                }
+                cudaGetLastError();
+                // nobody frees its block while a neighbour may still be opening it
+                NC(lbcomm::api().AllReduce(w, w, 1, lbcomm::ncclFloat64, lbcomm::ncclSum, c.comm, (cudaStream_t)0));
+                CU(cudaDeviceSynchronize());
+                cudaFree(dh);
+            } else cudaGetLastError();
+        }
         CU(cudaFree(w));
     }
     return LBGPU_OK;
