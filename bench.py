@@ -241,13 +241,24 @@ def resident_run(name, args, rank, world, local_rank, dist, K, W, with_clocks):
 
     parts, elmts, comps = info["parts"], info["elmts"], info["comps"]
     fs = bool(info["params"]["freeSurface"])
-    if len(parts):
-        # particle state becomes resident with the first coupling step (rescan, as dem.newNeighborList does)
+    from hybird_b200 import dem_init
+    run = lb.run
+    info["dem"] = "none"
+    if len(parts) and case.get("motion") == "dem" and dem_init.covered(case, info["params"]):
+        # the configuration as the reference runs it: the DEM advances the spheres every cycle -- here on the device, inside
+        # the same call (lbGpuRunDem: DEM sub-steps, coupling step, LB step; no host round trip)
+        lb.demInit(dem_init.dem_from_case(case, info["params"]))
+        run = lb.runDem
+        info["dem"] = "device (lbGpuRunDem)"
+    elif len(parts):
+        # particle state becomes resident with the first coupling step (rescan, as dem.newNeighborList does); the particles
+        # then stay where they are (the device-side DEM does not cover periodic boundaries / clusters)
         if fs:
             lb.latticeBoltzmannFreeSurfaceStep()
         lb.latticeBoltzmannCouplingStep(True, elmts, parts, comps)
         lb.latticeBolzmannStep(elmts, parts)
-    lb.run(W)
+        info["dem"] = "particles fixed (lbGpuRun)"
+    run(W)
     barrier()
     sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None
     if sampler:
@@ -256,7 +267,7 @@ def resident_run(name, args, rank, world, local_rank, dist, K, W, with_clocks):
     l0 = lb.launch_count()
     barrier()
     t0w = time.time()
-    lb.run(K)
+    run(K)
     lb.synchronize()
     ms_dev = lb.last_step_ms()             # CUDA events on the engine's stream around the K steps
     kern_ms, kern_n = lb.last_kernel_ms()  # CUDA events around each step-kernel group (last <=512 of the K)
@@ -279,7 +290,7 @@ def resident_run(name, args, rank, world, local_rank, dist, K, W, with_clocks):
     size = info["params"]["size"]
     res = dict(value=active_total * K / (ms_dev * 1e-3) / 1e6, ms_per_step=ms_dev / K, launches=int(launches), clocks=clocks,
                init_s=round(t_init, 2), barrier=barrier,
-               lattice=[int(size[0]), int(size[1]), int(info["global_z"])], active_cells=int(active_total),
+               lattice=[int(size[0]), int(size[1]), int(info["global_z"])], active_cells=int(active_total), dem=info["dem"],
                roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "kernel": info["kernel"], "bytes_per_update": BYTES_PER_UPDATE,
                          "updates_per_launch": int(active_local), "kernel_ms": kern_ms,
@@ -440,7 +451,7 @@ def main_ours(args, rank, world, local_rank):
                 # where the device time of a cycle goes (CUDA events at the phase boundaries, a separate short run: the
                 # trace launches every cycle eagerly); rank 0's view
                 lbx.phase_trace(True)
-                lbx.run(min(Kx, 32))
+                (lbx.runDem if rx["dem"].startswith("device") else lbx.run)(min(Kx, 32))
                 ph, ncyc = lbx.phase_ms()
                 lbx.phase_trace(False)
                 rx["phase_ms"] = {k: round(v, 4) for k, v in ph.items()}
@@ -478,7 +489,7 @@ def main_ours(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_label(args.workload, world),
                    "lattice": res["lattice"], "active_cells": res["active_cells"],
-                   "parallelism": info["parallelism"],
+                   "parallelism": info["parallelism"], "particles": info.get("dem", "none"),
                    "l2": "working set %.1f GB per GPU >> 126 MB L2 (no flush needed)" % (info["bytes_resident"] / 1e9),
                    "init_s": res["init_s"], "init": info["init"]},
         "roofline": roof,

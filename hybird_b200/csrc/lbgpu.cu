@@ -477,7 +477,7 @@ struct LbGpuHandle {
         cudaGraphExec_t exec = nullptr;
         std::vector<uint32_t> tiles;   // visited tiles per slab the step kernels' grids were sized for
         uint64_t launches = 0;         // kernels per replay
-        int cur = -1, fs = -1;
+        int cur = -1, fs = -1, kind = -1;
         uint32_t nParts = 0;
         uint64_t replays = 0, captures = 0;
     } graph;
@@ -2341,29 +2341,20 @@ int lbGpuCouple(LbGpuHandle* h, int rescanParticles, const LbGpuParticle* parts,
     return coupling_step(h, rescanParticles != 0);
 }
 
-int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
-    if (!h) return fail(LBGPU_EINVAL, "lbGpuRun: null handle");
-    CU(cudaSetDevice(h->device));
-    CU(cudaEventRecord(h->evA, h->stream));
-    h->kevCount = 0;
-    auto cycle = [&]() -> int {
-        int rc;
-        phase_mark(h, 0); phase_mark(h, 1);
-        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
-        if (h->nParts > 0) { if ((rc = coupling_step(h, false))) return rc; }  // goCycle's order, particles of the last upload
-        phase_mark(h, 4);
-        return lb_step(h);
-    };
-    struct Lazy { LbGpuHandle* h; explicit Lazy(LbGpuHandle* hh) : h(hh) { h->lazyForces = true; } ~Lazy() { h->lazyForces = false; } } lazy(h);
+}  // extern "C"
+namespace {
+// `count` cycles.  A free-surface or coupled cycle is 10-25 small launches around the step kernel: on small lattices their
+// issue cost bounds the cycle.  In one process the cycle is a fixed sequence of stream operations (the flood fill of the
+// coupling step gates its generations on the device, see coupling_step; so are the DEM sub-steps), so two consecutive cycles
+// -- the population buffers alternate -- are captured once and replayed.  The last cycles of a call run eagerly: they carry
+// the CUDA events lbGpuLastKernelMs reads, and the list counts the host sizes grids with.  kind: which cycle (0 lbGpuRun, 1
+// lbGpuRunDem) the cached graph holds.
+template <class Cycle>
+int run_cycles(LbGpuHandle* h, uint32_t count, bool fsCycle, int kind, Cycle&& cycle) {
     uint32_t k = 0;
-    // A free-surface or coupled cycle is 10-25 small launches around the step kernel: on small lattices their issue cost
-    // bounds the cycle.  In one process the cycle is a fixed sequence of stream operations (the flood fill of the coupling
-    // step gates its generations on the device, see coupling_step), so two consecutive cycles are captured once and
-    // replayed.  The last cycles of a call run eagerly: they carry the CUDA events lbGpuLastKernelMs reads, and the list
-    // counts the host sizes grids with.
-    const bool fsCycle = h->fs && doFreeSurface, coupled = h->nParts > 0;
-    const bool graphable = h->graphAllowed && !h->phaseOn && (fsCycle || coupled) && (!h->fs || doFreeSurface) &&
-                           (!coupled || h->floodGens >= 2) && !lbcomm::active() && !h->dem.on && !h->dynWall && count >= 8;
+    const bool coupled = h->nParts > 0;
+    const bool graphable = h->graphAllowed && !h->phaseOn && (fsCycle || coupled) && (!h->fs || fsCycle) &&
+                           (!coupled || h->floodGens >= 2) && !lbcomm::active() && !h->dynWall && count >= 8;
     if (graphable) {
         constexpr uint32_t TAIL = 2;
         for (; k < count && (h->steps < 2 || h->eagerCycles < 2); ++k) { if (int rc = cycle()) return rc; }
@@ -2374,7 +2365,7 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
                 ++k;
                 continue;
             }
-            bool valid = h->graph.exec != nullptr && h->graph.cur == h->cur && h->graph.fs == (int)fsCycle && h->graph.nParts == h->nParts;
+            bool valid = h->graph.exec != nullptr && h->graph.cur == h->cur && h->graph.fs == (int)fsCycle && h->graph.nParts == h->nParts && h->graph.kind == kind;
             for (size_t q = 0; valid && q < h->slabs.size(); ++q) {
                 const uint32_t now = h->pinnedCounts[8 * q + 1], then = h->graph.tiles[q];
                 valid = now <= then + then / 32 && now + now / 4 + 64 >= then;  // the grids carry 1/16 of headroom
@@ -2395,11 +2386,11 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
                 h->graph.launches = h->launches - launches0;
                 h->launches = launches0;
                 if (rc) { if (g) cudaGraphDestroy(g); return rc; }
-                if (ce != cudaSuccess) return fail(LBGPU_ECUDA, "graph capture of the free-surface cycle: %s", cudaGetErrorString(ce));
+                if (ce != cudaSuccess) return fail(LBGPU_ECUDA, "graph capture of the cycle: %s", cudaGetErrorString(ce));
                 const cudaError_t ie = cudaGraphInstantiate(&h->graph.exec, g, 0);
                 cudaGraphDestroy(g);
                 if (ie != cudaSuccess) { h->graph.exec = nullptr; return fail(LBGPU_ECUDA, "graph instantiation: %s", cudaGetErrorString(ie)); }
-                h->graph.cur = h->cur; h->graph.fs = (int)fsCycle; h->graph.nParts = h->nParts;
+                h->graph.cur = h->cur; h->graph.fs = (int)fsCycle; h->graph.nParts = h->nParts; h->graph.kind = kind;
                 ++h->graph.captures;
             }
             CU(cudaGraphLaunch(h->graph.exec, h->stream));
@@ -2408,6 +2399,26 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
         }
     }
     for (; k < count; ++k) { if (int rc = cycle()) return rc; }
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
+    if (!h) return fail(LBGPU_EINVAL, "lbGpuRun: null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaEventRecord(h->evA, h->stream));
+    h->kevCount = 0;
+    auto cycle = [&]() -> int {
+        int rc;
+        phase_mark(h, 0); phase_mark(h, 1);
+        if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
+        if (h->nParts > 0) { if ((rc = coupling_step(h, false))) return rc; }  // goCycle's order, particles of the last upload
+        phase_mark(h, 4);
+        return lb_step(h);
+    };
+    struct Lazy { LbGpuHandle* h; explicit Lazy(LbGpuHandle* hh) : h(hh) { h->lazyForces = true; } ~Lazy() { h->lazyForces = false; } } lazy(h);
+    if (int rc = run_cycles(h, count, h->fs && doFreeSurface, 0, cycle)) return rc;
     if (int rc = forces_reduced(h)) return rc;  // of the last cycle
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
@@ -2512,16 +2523,18 @@ int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
     CU(cudaSetDevice(h->device));
     CU(cudaEventRecord(h->evA, h->stream));
     h->kevCount = 0;
-    for (uint32_t k = 0; k < count; ++k) {
+    auto cycle = [&]() -> int {
         int rc;
         phase_mark(h, 0);
-        if ((rc = dem_step(h, h->lastStepCoupled ? h->slabs[0]->elemOut.p : nullptr))) return rc;
+        // (after the first LB step the element sums lie on the device; before it the reference's FHydro is zero too)
+        if ((rc = dem_step(h, (h->lastStepCoupled || h->capturing) ? h->slabs[0]->elemOut.p : nullptr))) return rc;
         phase_mark(h, 1);
         if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
         if ((rc = coupling_step(h, false))) return rc;  // dem.newNeighborList is only raised with periodic DEM boundaries (DEM.cpp:1414)
         phase_mark(h, 4);
-        if ((rc = lb_step(h))) return rc;
-    }
+        return lb_step(h);
+    };
+    if (int rc = run_cycles(h, count, h->fs && doFreeSurface, 1, cycle)) return rc;
     CU(cudaEventRecord(h->evB, h->stream));
     return LBGPU_OK;
 }

@@ -1,0 +1,69 @@
+"""Host-side mirror of what DEM::discreteElementGet + DEM::discreteElementInit leave behind for a box problem with
+single-sphere elements (DEM.cpp:13-83, 186-296, 435-640, 1270-1312; elmt.cpp:13-87): the dict lbGpuDemInit takes through
+`LB.demInit` -- material constants, sub-step length, neighbour-table range, per-element mass and inertia, the plane walls of
+the lattice boundaries.  Same expressions in the same order as the reference (checked number by number against the values
+the unmodified reference holds after its own initialisation, tests/test_dem_port.py).  Periodic lattice boundaries make
+periodic DEM boundaries (ghost particles), which the device-side DEM does not cover: `covered` says so."""
+from __future__ import annotations
+
+import math
+
+from . import lattice_init as li
+
+
+def covered(case: dict, params: dict) -> bool:
+    """True when the device-side DEM (lbGpuDem*) covers this case: spheres only, no periodic boundary, box geometry."""
+    return (all(int(e["size"]) == 1 for e in case.get("elements", [])) and len(case.get("elements", [])) > 0 and
+            all(b != 4 for b in params["boundary"]) and case.get("problemName", "NONE") == "NONE" and int(case.get("multiStep", 1)) > 0 and
+            float(case.get("demInitialRepeat", 0.0)) == 0.0)
+
+
+def dem_from_case(case: dict, params: dict | None = None) -> dict:
+    prm = params or li.params_from_case(case)
+    if not covered(case, prm):
+        raise ValueError("dem_from_case: the device-side DEM covers single-sphere elements in a box without periodic boundaries "
+                         "and an imposed multiStep only")
+    L, T, D = prm["unitLength"], prm["unitTime"], prm["unitDensity"]
+    accel = L / T / T
+    # material (DEM.cpp:13-62); the HERTZIAN case of the switch falls through into LINEAR's damping coefficient
+    young, poisson = float(case["youngMod"]), float(case["poisson"])
+    rest = float(case["restitution"])
+    p = dict(
+        contactModel=1 if case.get("contactModel", "none") == "HERTZIAN" else 0,
+        multiStep=int(case["multiStep"]),
+        knConst=2.0 / 3.0 * young / (1 - poisson * poisson),
+        ksConst=2.0 * young / (2.0 - poisson) / (1.0 + poisson),
+        dampCoeff=-1.0 * math.sqrt(2.0) * math.log(rest) / math.sqrt((math.log(rest) * math.log(rest) + math.pi)),
+        viscTang=float(case["viscTang"]), linearStiff=float(case["linearStiff"]),
+        frictionCoefPart=float(case["frictionCoefPart"]), frictionCoefWall=float(case["frictionCoefWall"]),
+        numVisc=float(case.get("numVisc", 0.0)),
+        demF=[v * accel for v in prm["lbF"]],                      # DEM.cpp:193: demF = lbF * unit.Accel
+        deltat=T / float(int(case["multiStep"])),                  # DEM.cpp:213
+    )
+    density = float(case["density"])
+    elmts = []
+    for e in case["elements"]:
+        r = float(e["radius"])
+        single = 4.0 / 3.0 * density * math.pi * r * r * r           # elmt::initialize (elmt.cpp:63-70); size = 1, no transport term
+        m = 1 * single
+        inertia = 1 * 2.0 / 5.0 * single * r * r * 1.0
+        elmts.append(dict(size=1, radius=r, m=m, I=[inertia, inertia, inertia], x0=[float(v) for v in e["x0"]],
+                          x1=[float(v) for v in e["x1"]], w0=[float(v) for v in e["w"]]))
+    # neighbour-table range (DEM::initNeighborParameters, DEM.cpp:1270-1312)
+    max_rad = max(e["radius"] for e in elmts)
+    widths = []
+    for k in range(3):
+        dem_size = float(prm["size"][k]) * L
+        w = min(max_rad * 5.0, dem_size)
+        n_cells = int(math.ceil(dem_size / w))
+        widths.append(dem_size / float(n_cells))
+    p["nebrRange"] = max(max_rad * 3.0, 0.5 * min(widths[0], min(widths[1], widths[2])))
+    p["maxDisp"] = 0.5 * p["nebrRange"]
+    # walls (DEM::initializeWalls, DEM.cpp:435-640)
+    walls = []
+    for w in li.make_walls(prm, case.get("wall_vel", ())):
+        n = [0.0, 0.0, 0.0]; pnt = [0.0, 0.0, 0.0]
+        n[w.axis] = 1.0 if w.side == 0 else -1.0
+        pnt[w.axis] = 0.5 * L if w.side == 0 else (float(prm["size"][w.axis]) - 1.5) * L
+        walls.append(dict(n=n, p=pnt, vel=list(w.vel), omega=[0.0, 0.0, 0.0], rotCenter=[0.0, 0.0, 0.0], moving=int(w.moving)))
+    return dict(params=p, elmts=elmts, walls=walls, counts=dict(pbcs=0, cylinders=0, objects=0, ghosts=0))

@@ -7,7 +7,7 @@ import pytest
 
 import golden_util as gu
 
-DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem")
+DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
 
 
 @pytest.mark.parametrize("name", DEM_CASES)
@@ -29,3 +29,32 @@ def test_dem_port_follows_reference_trace(name):
     assert worst <= 1e-12, worst
     if name == "bed_dem":
         assert P.rebuilds >= 4  # the table is rebuilt several times and pairs enter / leave it
+
+
+@pytest.mark.parametrize("name", DEM_CASES)
+def test_host_mirror_of_the_dem_initialisation(name):
+    """hybird_b200.dem_init restates what DEM::discreteElementGet / discreteElementInit derive (material constants, sub-step,
+    neighbour-table range, masses, inertias, walls): number by number what the unmodified reference held after its init."""
+    import cases
+    from hybird_b200 import dem_init
+    g = gu.Golden(name)
+    ref = g.dem()
+    mine = dem_init.dem_from_case(cases.catalogue()[name])
+    assert set(mine["params"]) == set(ref["params"])
+    for k, v in ref["params"].items():
+        assert mine["params"][k] == v, k
+    assert len(mine["elmts"]) == len(ref["elmts"]) and len(mine["walls"]) == len(ref["walls"])
+    for a, b in zip(mine["elmts"], ref["elmts"]):
+        for k in ("size", "radius", "m", "I", "x0", "x1", "w0"):
+            assert a[k] == b[k], k
+    for a, b in zip(mine["walls"], ref["walls"]):
+        for k in ("n", "p", "vel", "omega", "rotCenter", "moving"):
+            assert a[k] == b[k], k
+
+
+def test_dem_init_refuses_what_the_device_does_not_cover():
+    import cases
+    from hybird_b200 import dem_init
+    for name in ("cluster_dem", "two_spheres_kin"):  # clusters; periodic boundaries (ghost particles)
+        with pytest.raises(ValueError):
+            dem_init.dem_from_case(cases.catalogue()[name])

@@ -11,7 +11,7 @@ import pytest
 import golden_util as gu
 
 pytestmark = pytest.mark.gpu
-DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem")
+DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
 TOL_DEM = 1e-12
 TOL_COUPLED = 1e-9
 
@@ -90,6 +90,65 @@ def test_run_dem_equals_single_cycles_and_restart():
         assert np.array_equal(fa[k], fb[k]) and np.array_equal(fa[k], fc[k]), k
     for lb in (a, b, c):
         lb.close()
+
+
+def test_graph_replay_of_the_dem_coupled_cycle(monkeypatch):
+    """lbGpuRunDem(count) replays two captured cycles (DEM sub-steps, coupling step, LB step): same as one by one."""
+    g = gu.Golden("bed_dem")
+    a = _gpu(g)
+    monkeypatch.setenv("LBGPU_GRAPH", "0")
+    b = _gpu(g)
+    monkeypatch.delenv("LBGPU_GRAPH")
+    for n in (30, 41):
+        a.runDem(n); b.runDem(n)
+    assert a.graph_info()[1] >= 25 and b.graph_info() == (0, 0)
+    sa, sb = a.demState(), b.demState()
+    for k in ("x0", "x1", "w0"):
+        assert np.array_equal(sa[k], sb[k]), k
+    assert sa["rebuilds"] == sb["rebuilds"] >= 2
+    fa, fb = a.fetch(), b.fetch()
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k
+    a.close(); b.close()
+
+
+def test_cfg3_at_full_size_with_the_dem_on_the_device():
+    """BASELINE's configuration 3 as the reference runs it -- the sphere's motion computed by the DEM every cycle -- for 1000
+    cycles on the device (lbGpuRunDem), against the full-size fixture of the unmodified reference: trajectory, forces, the
+    cell-type / particle-flag map at the fixture's 102 check points, the fields at steps 1 / 100 / 1000."""
+    import cases
+    import common
+    import golden_full_util as gfu
+    from hybird_b200 import LB, dem_init
+    g = gfu.GoldenFull("cfg3_full")
+    case = cases.catalogue()[g.case_name]
+    lb = LB(dict(g.params)).latticeBolzmannInit(*g.init_arrays()).demInit(dem_init.dem_from_case(case))
+    worst_x = worst_f = 0.0
+    for s in range(1, g.steps + 1):
+        lb.runDem(1)
+        if s in g.type_sha or s % 50 == 0:
+            parts, elmts, comps, flag = g.trace[s - 1]
+            st = lb.demState()
+            worst_x = max(worst_x, np.abs(st["x0"] - parts["x0"]).max(), np.abs(st["x1"] - elmts["x1"]).max())
+            F, M, V, W = lb.forces()
+            rF, rM, rV, rW = g.forces[s - 1]
+            worst_f = max(worst_f, np.abs(F - rF).max() / np.abs(rF).max(), np.abs(V - rV).max() / np.abs(rV).max())
+        if s in g.type_sha:
+            t = lb.fetch(("type_flags",))["type_flags"] & 0x1F
+            assert gfu.sha(t) == g.type_sha[s], "type / particle-flag map differs from the reference after step %d" % s
+        if s in g.dumps:
+            st = common.gpu_state(lb)
+            idx = np.arange(g.stride // 2, g.N, g.stride, dtype=np.int64)
+            act = np.isin(g.z["samp_type_%d" % s] & 0x0F, (0, 3))
+            for k in ("n", "u", "visc"):
+                a, b = st[k][idx][act], g.z["samp_%s_%d" % (k, s)][act]
+                # against the field's scale: on the symmetry planes of this case a velocity component is rounding noise of
+                # either sign, which a per-value relative error would compare with itself
+                e = float(np.abs(a - b).max() / np.abs(b).max())
+                assert e <= (1e-12 if s == 1 else TOL_COUPLED), (s, k, e)
+    print("cfg3 at full size, DEM on the device, 1000 cycles: trajectory %.2e, forces %.2e" % (worst_x, worst_f))
+    assert worst_x <= TOL_COUPLED and worst_f <= TOL_COUPLED, (worst_x, worst_f)
+    lb.close()
 
 
 def _coupled(g, n_slabs, steps):
