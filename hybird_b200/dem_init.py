@@ -2,8 +2,9 @@
 single-sphere elements (DEM.cpp:13-83, 186-296, 435-640, 1270-1312; elmt.cpp:13-87): the dict lbGpuDemInit takes through
 `LB.demInit` -- material constants, sub-step length, neighbour-table range, per-element mass and inertia, the plane walls of
 the lattice boundaries.  Same expressions in the same order as the reference (checked number by number against the values
-the unmodified reference holds after its own initialisation, tests/test_dem_port.py).  Periodic lattice boundaries make
-periodic DEM boundaries (ghost particles), which the device-side DEM does not cover: `covered` says so."""
+the unmodified reference holds after its own initialisation, tests/test_dem_port.py).  Periodic pairs of lattice boundaries make
+periodic DEM boundaries (DEM::initializePbcs, DEM.cpp:937-988; listed under `pbcs` for completeness), whose ghost particles the
+device-side DEM does not build: `covered` says so and `LB.demInit` refuses them."""
 from __future__ import annotations
 
 import math
@@ -12,7 +13,8 @@ from . import lattice_init as li
 
 
 def covered(case: dict, params: dict) -> bool:
-    """True when the device-side DEM (lbGpuDem*) covers this case: spheres only, no periodic boundary, box geometry."""
+    """True when the device-side DEM (lbGpuDem*) covers this case: spheres only, no periodic boundary (periodic DEM boundaries
+    mean ghost particles, DEM.cpp:1586-1660, which the device does not build), box geometry, an imposed number of sub-steps."""
     return (all(int(e["size"]) == 1 for e in case.get("elements", [])) and len(case.get("elements", [])) > 0 and
             all(b != 4 for b in params["boundary"]) and case.get("problemName", "NONE") == "NONE" and int(case.get("multiStep", 1)) > 0 and
             float(case.get("demInitialRepeat", 0.0)) == 0.0)
@@ -66,4 +68,12 @@ def dem_from_case(case: dict, params: dict | None = None) -> dict:
         n[w.axis] = 1.0 if w.side == 0 else -1.0
         pnt[w.axis] = 0.5 * L if w.side == 0 else (float(prm["size"][w.axis]) - 1.5) * L
         walls.append(dict(n=n, p=pnt, vel=list(w.vel), omega=[0.0, 0.0, 0.0], rotCenter=[0.0, 0.0, 0.0], moving=int(w.moving)))
-    return dict(params=p, elmts=elmts, walls=walls, counts=dict(pbcs=0, cylinders=0, objects=0, ghosts=0))
+    # periodic DEM boundaries (DEM::initializePbcs, DEM.cpp:937-988): one per periodic pair of lattice boundaries
+    pbcs = []
+    for a in range(3):
+        if prm["boundary"][2 * a] == 4:
+            pp = [0.0, 0.0, 0.0]; vv = [0.0, 0.0, 0.0]
+            pp[a] = 0.5 * L
+            vv[a] = (float(prm["size"][a]) - 2.0) * L
+            pbcs.append(dict(p=pp, v=vv))
+    return dict(params=p, elmts=elmts, walls=walls, pbcs=pbcs, counts=dict(pbcs=len(pbcs), cylinders=0, objects=0))

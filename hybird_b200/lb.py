@@ -159,6 +159,9 @@ class LB:
         DEM::discreteElementInit left: sphereMat constants, deltat, multiStep, nebrRange, maxDisp; per element x0, x1, w0,
         radius, m, I; per wall n, p, vel, omega, rotCenter, moving) -- physical units."""
         p = dem["params"]
+        if dem.get("pbcs"):
+            raise ValueError("demInit: periodic DEM boundaries (ghost particles) are not covered by the device-side DEM; keep the host DEM "
+                             "and latticeBoltzmannCouplingStep / latticeBolzmannStep")
         P = abi.LbGpuDemParams()
         P.contactModel = int(p["contactModel"]); P.multiStep = int(p["multiStep"])
         for k in ("knConst", "ksConst", "dampCoeff", "viscTang", "linearStiff", "frictionCoefPart", "frictionCoefWall", "numVisc",

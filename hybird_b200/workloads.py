@@ -141,6 +141,16 @@ def catalogue():
     C["spheres_hertz"] = make_case("spheres_hertz", lbSizeX=30, lbSizeY=26, lbSizeZ=30, lbFZ=-2e-5, initVisc=0.1, multiStep=2,
                                    contactModel="HERTZIAN", youngMod=4.0, poisson=0.3, restitution=0.8, viscTang=0.3,
                                    elements=copy.deepcopy(dem_spheres), motion="dem")
+    # periodic DEM boundaries: x and y periodic (two pbcs, so ghost particles in the corners too), walls in z; the reference's
+    # DEM in the loop, the LB side sees five ghost particles and a full rescan at every rebuild of the neighbour table
+    C["spheres_pbc_dem"] = make_case(
+        "spheres_pbc_dem", lbSizeX=30, lbSizeY=26, lbSizeZ=30, boundary0=4, boundary1=4, boundary2=4, boundary3=4, lbFZ=-3e-5,
+        initVisc=0.06, multiStep=2, density=6.0,
+        elements=[dict(size=1, radius=3.0, x0=[4.6, 12.0, 15.0], x1=[-0.11, 0.0, 0.0], w=[0.0, 0.0, 0.01]),
+                  dict(size=1, radius=3.2, x0=[24.0, 12.8, 15.6], x1=[0.09, 0.0, 0.0], w=[0.0, 0.02, 0.0]),
+                  dict(size=1, radius=2.6, x0=[3.4, 3.2, 21.0], x1=[-0.03, -0.04, 0.0], w=[0.01, 0.0, 0.0]),
+                  dict(size=1, radius=3.0, x0=[15.0, 13.0, 5.0], x1=[0.02, 0.05, -0.06], w=[0.0, 0.0, 0.0])],
+        motion="dem")
     # a loose bed: twelve heavy spheres with random velocities in a box wider than nebrRange -- several rebuilds of the
     # neighbour table, pairs that enter and leave it, wall contacts on every side
     bed = _sphere_bed(12, (1.0, 1.0, 1.0), (39.0, 35.0, 39.0), 2.2, 3.0, 777)

@@ -21,7 +21,7 @@ def read_dem_file(path):
 
 
 def parse_dem_text(text):
-    prm, elmts, walls, counts = {}, [], [], {}
+    prm, elmts, walls, counts, pbcs = {}, [], [], {}, []
     for ln in str(text).splitlines():
         t = ln.split()
         if not t:
@@ -40,10 +40,12 @@ def parse_dem_text(text):
         elif t[0] == "wall":
             walls.append(dict(n=[float(v) for v in t[3:6]], p=[float(v) for v in t[7:10]], vel=[float(v) for v in t[11:14]],
                               omega=[float(v) for v in t[15:18]], rotCenter=[float(v) for v in t[19:22]], moving=int(t[23])))
+        elif t[0] == "pbc":
+            pbcs.append(dict(p=[float(v) for v in t[3:6]], v=[float(v) for v in t[7:10]]))
         elif t[0] == "pbcs":
             counts = {t[i]: int(t[i + 1]) for i in range(0, len(t), 2)}
     prm["contactModel"] = int(prm["contactModel"]); prm["multiStep"] = int(prm["multiStep"])
-    return dict(params=prm, elmts=elmts, walls=walls, counts=counts)
+    return dict(params=prm, elmts=elmts, walls=walls, counts=counts, pbcs=pbcs)
 
 
 def _cross(a, b):

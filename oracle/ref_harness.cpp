@@ -339,6 +339,8 @@ int main(int argc, char** argv) {
                 fprintf(df, "wall %u n %.17g %.17g %.17g p %.17g %.17g %.17g vel %.17g %.17g %.17g omega %.17g %.17g %.17g rotCenter %.17g %.17g %.17g moving %d\n",
                         w.index, w.n.x, w.n.y, w.n.z, w.p.x, w.p.y, w.p.z, w.vel.x, w.vel.y, w.vel.z, w.omega.x, w.omega.y, w.omega.z,
                         w.rotCenter.x, w.rotCenter.y, w.rotCenter.z, (int)w.moving);
+            for (const pbc& b : dem.pbcs)
+                fprintf(df, "pbc %d p %.17g %.17g %.17g v %.17g %.17g %.17g\n", b.index, b.p.x, b.p.y, b.p.z, b.v.x, b.v.y, b.v.z);
             fprintf(df, "pbcs %zu cylinders %zu objects %zu ghosts %zu\n", dem.pbcs.size(), dem.cylinders.size(), dem.objects.size(), dem.ghosts.size());
             fclose(df);
         }
