@@ -100,3 +100,33 @@ def test_two_processes_two_gpus_match_one_gpu(name, mode, tmp_path):
         F0 = np.stack([f[0] for f in fref]); M0 = np.stack([f[1] for f in fref])
         assert np.abs(z["F"] - F0).max() <= 1e-9 * max(np.abs(F0).max(), 1e-300)
         assert np.abs(z["M"] - M0).max() <= 1e-9 * max(np.abs(M0).max(), 16.0 * np.abs(F0).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name", ["cfg5_mini", "cfg4_mini", "cfg2_mini", "cfg3_mini"])
+def test_four_processes_four_gpus_match_one_gpu(name, tmp_path):
+    """The same with four ranks (interior ranks have a neighbour on either side: two face launches, two peers)."""
+    if _n_gpus() < 4:
+        pytest.skip("needs 4 GPUs (gpurun --gpus 4)")
+    out = tmp_path / "ranks.npz"
+    port = 29400 + os.getpid() % 200
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "4", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), name, str(out)]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    z = np.load(out)
+    g = gu.Golden(name)
+    steps = int(z["steps"])
+    ref, fref = _run(g, 1, steps)
+    assert np.array_equal(z["type_flags"], ref["type_flags"])
+    act = np.isin(ref["type_flags"] & 15, (0, 3))
+    exact = not g.params["freeSurface"]
+    for k in ("f", "n", "u", "mass"):
+        a, b = z[k][act], ref[k][act]
+        if exact:
+            assert np.array_equal(a, b), k
+        else:
+            assert common.max_rel(a, b) <= 1e-9, (k, common.max_rel(a, b))
+    if g.params["nElmts"]:
+        F0 = np.stack([f[0] for f in fref]); M0 = np.stack([f[1] for f in fref])
+        assert np.abs(z["F"] - F0).max() <= 1e-9 * max(np.abs(F0).max(), 1e-300)
+        assert np.abs(z["M"] - M0).max() <= 1e-9 * max(np.abs(M0).max(), 16.0 * np.abs(F0).max(), 1e-300)
