@@ -17,8 +17,8 @@
 // partners in ascending index order: deterministic, no atomics.  Broad phase: the reference searches its table with
 // linked cells (DEM.cpp:1326-1375) whose width is at least nebrRange wherever the domain is wider than six radii, so its
 // table IS the set of pairs within nebrRange at rebuild time; here a rebuild compares all pairs through shared-memory
-// tiles (4e8 distance tests for 20 000 spheres, once every few LB steps) and the sub-steps in between only walk the
-// partner lists.  No periodic boundaries (ghost particles), cylinders, objects, clusters.
+// tiles (small beds) or bins the elements into a uniform grid (k_grid_*, large beds) and the sub-steps in between only walk
+// the partner lists.  No periodic boundaries (ghost particles), cylinders, objects, clusters.
 // Compiled with -fmad=false like the LB kernels: the reference's operation order is kept.
 #pragma once
 #include <stdint.h>
@@ -101,6 +101,139 @@ __global__ void __launch_bounds__(128) k_dem_neighbours(const Elmt* __restrict__
         nNbr[k] = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
         if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same partner lists through a uniform grid (the reference's linked cells, DEM.cpp:1326-1375, as a counting sort): cells
+// at least nebrRange wide over the bounding box of the elements, elements binned by cell (count - scan - fill), every element
+// looks at the 27 cells around its own and sorts what it finds, so the lists are the ascending lists of the all-pairs pass --
+// identical results, O(n) instead of O(n^2): 20 000 spheres 1.7 ms -> tens of microseconds, and beds of 1e6 become possible.
+// All launches are gated on the rebuild flag.  grid[0..2] = cells per axis, gridOrg/gridInv = origin and 1 / cell width.
+// ---------------------------------------------------------------------------------------------
+struct Grid { double org[3], inv[3]; uint32_t dim[3], nCells; };
+constexpr uint32_t GRID_MAX_CELLS = 1u << 21;
+
+__global__ void __launch_bounds__(1024) k_grid_bounds(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+                                                      Grid* __restrict__ g, uint32_t* __restrict__ cellCount) {
+    if (!*flag) return;
+    __shared__ double smin[3][32], smax[3][32];
+    double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x)
+        for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], e[k].x[0][c]); hi[c] = fmax(hi[c], e[k].x[0][c]); }
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o > 0; o >>= 1) { lo[c] = fmin(lo[c], __shfl_down_sync(0xffffffffu, lo[c], o)); hi[c] = fmax(hi[c], __shfl_down_sync(0xffffffffu, hi[c], o)); }
+        if ((threadIdx.x & 31) == 0) { smin[c][threadIdx.x >> 5] = lo[c]; smax[c][threadIdx.x >> 5] = hi[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double width = nebrRange;
+        for (;;) {  // cells of nebrRange, wider if that would be too many of them
+            unsigned long long cells = 1;
+            for (int c = 0; c < 3; ++c) {
+                double a = smin[c][0], b = smax[c][0];
+                for (int k = 1; k < 32; ++k) { a = fmin(a, smin[c][k]); b = fmax(b, smax[c][k]); }
+                g->org[c] = a; g->inv[c] = 1.0 / width;
+                g->dim[c] = (uint32_t)((b - a) / width) + 1u;
+                cells *= g->dim[c];
+            }
+            if (cells <= GRID_MAX_CELLS) { g->nCells = (uint32_t)cells; break; }
+            width *= 2.0;
+        }
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k <= g->nCells; k += blockDim.x) cellCount[k] = 0u;
+}
+__device__ __forceinline__ uint32_t grid_cell(const Grid& g, const double* x, int* cx, int* cy, int* cz) {
+    *cx = min((int)g.dim[0] - 1, max(0, (int)((x[0] - g.org[0]) * g.inv[0])));
+    *cy = min((int)g.dim[1] - 1, max(0, (int)((x[1] - g.org[1]) * g.inv[1])));
+    *cz = min((int)g.dim[2] - 1, max(0, (int)((x[2] - g.org[2]) * g.inv[2])));
+    return (uint32_t)*cx + g.dim[0] * ((uint32_t)*cy + g.dim[1] * (uint32_t)*cz);
+}
+__global__ void __launch_bounds__(128) k_grid_count(const Elmt* __restrict__ e, uint32_t n, const uint32_t* __restrict__ flag, const Grid* __restrict__ g,
+                                                    uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellOf) {
+    if (!*flag) return;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int cx, cy, cz;
+    const uint32_t c = grid_cell(*g, e[k].x[0], &cx, &cy, &cz);
+    cellOf[k] = c;
+    atomicAdd(&cellCount[c], 1u);
+}
+// exclusive scan of the cell counts in place (one block; cellCount[nCells] = n afterwards), fill counters zeroed
+__global__ void __launch_bounds__(1024) k_grid_scan(const uint32_t* __restrict__ flag, const Grid* __restrict__ g, uint32_t* __restrict__ cellCount,
+                                                    uint32_t* __restrict__ cellFill) {
+    if (!*flag) return;
+    __shared__ uint32_t sa[1024];
+    const uint32_t nC = g->nCells, per = (nC + 1023u) / 1024u;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(nC, b0 + per);
+    uint32_t s = 0;
+    for (uint32_t c = b0; c < b1; ++c) s += cellCount[c];
+    sa[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {
+        uint32_t v = 0;
+        if (threadIdx.x >= o) v = sa[threadIdx.x - o];
+        __syncthreads();
+        sa[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = sa[threadIdx.x] - s;
+    for (uint32_t c = b0; c < b1; ++c) { const uint32_t v = cellCount[c]; cellCount[c] = run; cellFill[c] = 0u; run += v; }
+    if (threadIdx.x == 1023) cellCount[nC] = sa[1023];
+}
+__global__ void __launch_bounds__(128) k_grid_fill(uint32_t n, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ cellStart,
+                                                   uint32_t* __restrict__ cellFill, const uint32_t* __restrict__ cellOf, uint32_t* __restrict__ sorted) {
+    if (!*flag) return;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t c = cellOf[k];
+    sorted[cellStart[c] + atomicAdd(&cellFill[c], 1u)] = k;
+}
+__global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+                                                             const Grid* __restrict__ gp, const uint32_t* __restrict__ cellStart,
+                                                             const uint32_t* __restrict__ sorted, uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr,
+                                                             uint32_t* __restrict__ status) {
+    if (!*flag) return;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const Grid g = *gp;
+    const V3 xk = v3(e[k].x[0]);
+    const double r2 = nebrRange * nebrRange;
+    int cx, cy, cz;
+    grid_cell(g, e[k].x[0], &cx, &cy, &cz);
+    uint32_t found[MAX_NBR];
+    uint32_t cnt = 0;
+    // cells may be wider than nebrRange but never narrower: the 27 cells around cover the range
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = cz + dz;
+        if (z < 0 || z >= (int)g.dim[2]) continue;
+        for (int dy = -1; dy <= 1; ++dy) {
+            const int y = cy + dy;
+            if (y < 0 || y >= (int)g.dim[1]) continue;
+            const int x0 = max(0, cx - 1), x1 = min((int)g.dim[0] - 1, cx + 1);
+            // the cells of a row are consecutive: one range of the sorted array
+            const uint32_t c0 = (uint32_t)x0 + g.dim[0] * ((uint32_t)y + g.dim[1] * (uint32_t)z), c1 = c0 + (uint32_t)(x1 - x0);
+            for (uint32_t q = cellStart[c0]; q < cellStart[c1 + 1]; ++q) {
+                const uint32_t j = sorted[q];
+                if (j == k) continue;
+                const V3 d = v3(e[j].x[0]) - xk;
+                if (norm2(d) < r2) {
+                    if (cnt < (uint32_t)MAX_NBR) found[cnt] = j;
+                    ++cnt;
+                }
+            }
+        }
+    }
+    const uint32_t m = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
+    for (uint32_t a = 1; a < m; ++a) {  // ascending, like the all-pairs pass (the order within a cell is whatever the atomics gave)
+        const uint32_t v = found[a];
+        uint32_t b = a;
+        while (b > 0 && found[b - 1] > v) { found[b] = found[b - 1]; --b; }
+        found[b] = v;
+    }
+    for (uint32_t a = 0; a < m; ++a) nbr[(size_t)k * MAX_NBR + a] = found[a];
+    nNbr[k] = m;
+    if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
 }
 
 __global__ void __launch_bounds__(128) k_dem_predict(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p,

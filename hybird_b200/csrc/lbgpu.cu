@@ -498,6 +498,10 @@ struct LbGpuHandle {
         DevBuf<lbdem::Elmt> e;
         DevBuf<lbdem::Wall> walls;
         DevBuf<uint32_t> nbr, nNbr, flag;  // flag[0] = rebuild in this sub-step, [1] = longest partner list, [2] = rebuilds so far
+        // uniform grid for the table rebuild of large beds (k_grid_*): LBGPU_DEM_GRID=0/1 overrides the choice by size
+        bool grid = false;
+        DevBuf<lbdem::Grid> gridDesc;
+        DevBuf<uint32_t> cellCount, cellFill, cellOf, sorted;
         DevBuf<double> scal, hydro;         // scal[0] = DEM::maxDisp; hydro: forces handed in from the host (lbGpuDemStep)
     } dem;
 };
@@ -2435,7 +2439,17 @@ int dem_step(LbGpuHandle* h, const double* hydro) {
     const uint32_t n = D.n, nb = (n + 127) / 128;
     for (int sub = 0; sub < D.prm.multiStep; ++sub) {
         lbdem::k_dem_trigger<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.deltat, D.prm.nebrRange, D.scal.p, D.flag.p);
-        lbdem::k_dem_neighbours<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
+        if (D.grid) {
+            lbdem::k_grid_bounds<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p);
+            lbdem::k_grid_count<<<nb, 128, 0, st>>>(D.e.p, n, D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellOf.p);
+            lbdem::k_grid_scan<<<1, 1024, 0, st>>>(D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellFill.p);
+            lbdem::k_grid_fill<<<nb, 128, 0, st>>>(n, D.flag.p, D.cellCount.p, D.cellFill.p, D.cellOf.p, D.sorted.p);
+            lbdem::k_dem_neighbours_grid<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p, D.sorted.p, D.nbr.p, D.nNbr.p,
+                                                             D.flag.p + 1);
+            h->launches += 4;
+        } else {
+            lbdem::k_dem_neighbours<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
+        }
         lbdem::k_dem_predict<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, D.nWalls, D.flag.p);
         lbdem::k_dem_forces_correct<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, hydro, D.nbr.p, D.nNbr.p);
         h->launches += 4;
@@ -2485,6 +2499,12 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
     }
     CU(D.e.alloc(nElmts)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)nElmts * lbdem::MAX_NBR)); CU(D.nNbr.alloc(nElmts));
     CU(D.flag.alloc(4)); CU(D.scal.alloc(2)); CU(D.hydro.alloc((size_t)7 * nElmts));
+    D.grid = nElmts >= 4096;  // below that the all-pairs pass (one launch) is as fast as the five launches of the grid
+    if (const char* e = getenv("LBGPU_DEM_GRID")) D.grid = atoi(e) != 0;
+    if (D.grid) {
+        CU(D.gridDesc.alloc(1)); CU(D.cellCount.alloc(lbdem::GRID_MAX_CELLS + 2)); CU(D.cellFill.alloc(lbdem::GRID_MAX_CELLS + 2));
+        CU(D.cellOf.alloc(nElmts)); CU(D.sorted.alloc(nElmts));
+    }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(D.e.p, E.data(), sizeof(lbdem::Elmt) * nElmts, cudaMemcpyHostToDevice));
     if (nWalls) CU(cudaMemcpy(D.walls.p, walls, sizeof(lbdem::Wall) * nWalls, cudaMemcpyHostToDevice));

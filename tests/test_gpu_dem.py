@@ -194,6 +194,49 @@ def test_coupled_cycle_on_two_gpus(tmp_path):
     assert np.abs(z["dem_x0"] - parts["x0"]).max() <= TOL_COUPLED
 
 
+def _bed(n, seed=4321):
+    """A bed of n spheres (radii 3-4, random velocities) between six walls, cfg5's recipe scaled to n."""
+    from hybird_b200 import workloads
+    g = gu.Golden("spheres_dem")
+    dem = g.dem()
+    side = (n / 20000.0) ** (1.0 / 3.0)
+    hi = (160.0 * side, 255.0 * side, 1023.0 * side)
+    bed = workloads._sphere_bed(n, (1.0, 1.0, 1.0), hi, 3.0, 4.0, seed)
+    rng = np.random.default_rng(seed)
+    rho = 2.5
+    dem["elmts"] = [dict(size=1, radius=e["radius"], m=4.0 / 3.0 * rho * np.pi * e["radius"] ** 3, I=[0.4 * 4.0 / 3.0 * rho * np.pi * e["radius"] ** 5] * 3,
+                         x0=e["x0"], x1=list(rng.uniform(-0.4, 0.4, 3)), w0=list(rng.uniform(-0.02, 0.02, 3))) for e in bed]
+    dem["walls"] = [dict(n=[1 if a == k and s == 0 else (-1 if a == k else 0) for a in range(3)],
+                         p=[(0.5 if s == 0 else hi[k] + 0.5) if a == k else 0.0 for a in range(3)],
+                         vel=[0.0] * 3, omega=[0.0] * 3, rotCenter=[0.0] * 3, moving=0) for k in range(3) for s in (0, 1)]
+    p = dem["params"]
+    p["multiStep"] = 1; p["deltat"] = 1.0; p["nebrRange"] = 12.0; p["maxDisp"] = 6.0; p["demF"] = [-1e-3, 0.0, 3e-4]
+    return g, dem
+
+
+def test_grid_rebuild_equals_all_pairs(monkeypatch):
+    """The neighbour table through the uniform grid (count - scan - fill, 27 cells, sorted lists) == the all-pairs pass: the
+    same partner lists, hence bit-identical trajectories through contacts and a dozen rebuilds."""
+    from hybird_b200 import LB
+    g, dem = _bed(6000)
+    out = []
+    for grid in ("0", "1"):
+        monkeypatch.setenv("LBGPU_DEM_GRID", grid)
+        lb = LB(dict(g.params)).latticeBolzmannInit(*g.init_arrays()).demInit(dem)
+        hydro = np.zeros((len(dem["elmts"]), 7))
+        lb.demStep(hydro)
+        for _ in range(120):
+            lb.demStep()
+        out.append((lb.demState(), lb.demContacts()))
+        lb.close()
+    monkeypatch.delenv("LBGPU_DEM_GRID")
+    (a, ca), (b, cb) = out
+    assert a["rebuilds"] == b["rebuilds"] >= 5 and a["longest_list"] == b["longest_list"] == 0  # (nonzero only on overflow)
+    for k in ("x0", "x1", "w0"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(ca["FParticle"], cb["FParticle"]) and np.abs(ca["FParticle"]).max() > 0  # contacts happened
+
+
 def test_partner_list_overflow_is_an_error():
     from hybird_b200 import LB
     from hybird_b200.abi import LbGpuError
