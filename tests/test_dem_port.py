@@ -58,3 +58,18 @@ def test_dem_init_refuses_what_the_device_does_not_cover():
     for name in ("cluster_dem", "two_spheres_kin"):  # clusters; periodic boundaries (ghost particles)
         with pytest.raises(ValueError):
             dem_init.dem_from_case(cases.catalogue()[name])
+
+
+def test_lb_mirror_refuses_clusters_and_periodic_dem_before_touching_the_device():
+    """LB.demInit checks what the device-side DEM covers on the host side (no CUDA call is made for a refused set-up)."""
+    from hybird_b200 import LB
+    g = gu.Golden("cluster_dem")
+    lb = LB(dict(g.params))
+    dem = gu.Golden("spheres_dem").dem()
+    dem["elmts"][0]["size"] = 2
+    with pytest.raises(ValueError, match="single-sphere"):
+        lb.demInit(dem)
+    dem = gu.Golden("spheres_pbc_dem").dem()
+    assert len(dem["pbcs"]) == 2
+    with pytest.raises(ValueError, match="periodic DEM boundaries"):
+        lb.demInit(dem)
