@@ -141,6 +141,14 @@ def catalogue():
     C["spheres_hertz"] = make_case("spheres_hertz", lbSizeX=30, lbSizeY=26, lbSizeZ=30, lbFZ=-2e-5, initVisc=0.1, multiStep=2,
                                    contactModel="HERTZIAN", youngMod=4.0, poisson=0.3, restitution=0.8, viscTang=0.3,
                                    elements=copy.deepcopy(dem_spheres), motion="dem")
+    # clusters in contact: a pair of spheres and a triangle collide in mid-fluid, a tetrahedron lands on the floor (lever arms of
+    # the contact forces, rotation in the body frame, per-particle neighbour and wall tables)
+    C["clusters_hit"] = make_case(
+        "clusters_hit", lbSizeX=34, lbSizeY=28, lbSizeZ=32, lbFZ=-4e-5, initVisc=0.05, multiStep=2, density=6.0,
+        elements=[dict(size=2, radius=2.4, x0=[11.0, 13.0, 18.0], x1=[0.10, 0.0, 0.0], w=[0.0, 0.0, 0.02]),
+                  dict(size=3, radius=2.2, x0=[22.5, 14.0, 18.6], x1=[-0.09, 0.0, 0.0], w=[0.0, 0.01, 0.0]),
+                  dict(size=4, radius=2.0, x0=[16.0, 13.0, 6.3], x1=[0.0, 0.01, -0.08], w=[0.01, 0.0, 0.0])],
+        motion="dem")
     # periodic DEM boundaries: x and y periodic (two pbcs, so ghost particles in the corners too), walls in z; the reference's
     # DEM in the loop, the LB side sees five ghost particles and a full rescan at every rebuild of the neighbour table
     C["spheres_pbc_dem"] = make_case(

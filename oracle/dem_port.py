@@ -224,3 +224,246 @@ class DemPort:
         for _ in range(self.p["multiStep"]):
             self.substep()
         return self.x[0].copy(), self.x[1].copy(), self.w[0].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Elements of several spheres (clusters, size 2-4): the general restatement.  Adds to the above the orientation
+# quaternions q0..q5 of elmt::predict / elmt::correct (elmt.cpp:139-254), the particles of an element at
+# e.x0 + r * project(prototype, q0) (particle::updatePredicted / updateCorrected, elmt.cpp:261-290; prototypes of
+# DEM::compositeProperties, DEM.cpp:404-433), per-particle neighbour and wall tables, the lever arms of the contact forces
+# (centerDist, DEM.cpp:1841-1890, 1936-1976) and the rotation in the body frame (DEM.cpp:1164-1180; project / newtonAcc /
+# quatAcc of vector.cpp:481-504).  TEST INFRASTRUCTURE like everything in this file.
+# ---------------------------------------------------------------------------------------------------------------------
+def _qmul(q, r):
+    """quaternion::multiply (vector.cpp:301-310): q.multiply(r)."""
+    return np.array([r[0] * q[0] - r[1] * q[1] - r[2] * q[2] - r[3] * q[3],
+                     r[0] * q[1] + r[1] * q[0] - r[2] * q[3] + r[3] * q[2],
+                     r[0] * q[2] + r[1] * q[3] + r[2] * q[0] - r[3] * q[1],
+                     r[0] * q[3] - r[1] * q[2] + r[2] * q[1] + r[3] * q[0]])
+
+
+def _qadj(q):
+    return np.array([q[0], -q[1], -q[2], -q[3]])
+
+
+def _qnormalize(q):
+    n = math.sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])
+    return np.array([q[0] / n, q[1] / n, q[2] / n, q[3] / n])
+
+
+def _project(v, q):
+    """project(vec, quat) = quat2vec(q (0, v) q*) (vector.cpp:481-491)."""
+    rot = _qmul(_qmul(q, np.array([0.0, v[0], v[1], v[2]])), _qadj(q))
+    return np.array([rot[1], rot[2], rot[3]])
+
+
+def prototypes():
+    s3, s2, s6 = math.sqrt(3), math.sqrt(2), math.sqrt(6)
+    return {1: [np.zeros(3)],
+            2: [np.array([0.5, 0.0, 0.0]), np.array([-0.5, 0.0, 0.0])],
+            3: [np.array([0.0, 1.0, 0.0]), np.array([-s3 / 2, -0.5, 0.0]), np.array([s3 / 2, -0.5, 0.0])],  # C++: -1/2 is integer 0!
+            4: [np.array([0.0, 0.0, 1.0]), np.array([0.0, 2.0 * s2 / 3.0, -1.0 / 3.0]),
+                np.array([2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0]), np.array([-2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0])]}
+
+
+class DemPortClusters(DemPort):
+    def __init__(self, dem):
+        E = dem["elmts"]
+        sizes = [int(e["size"]) for e in E]
+        saved = [e["size"] for e in E]
+        for e in E:
+            e["size"] = 1
+        try:
+            super().__init__(dem)
+        finally:
+            for e, s in zip(E, saved):
+                e["size"] = s
+        n = self.n
+        self.size = sizes
+        self.proto = prototypes()
+        # DEM.cpp:423-424 writes -1/2 with integers: the y component of the second and third sphere of a triangle is 0
+        self.proto[3] = [np.array([0.0, 1.0, 0.0]), np.array([-math.sqrt(3) / 2, 0.0, 0.0]), np.array([math.sqrt(3) / 2, 0.0, 0.0])]
+        ident = np.array([1.0, 0.0, 0.0, 0.0])
+        self.q = [np.tile(ident, (n, 1))] + [np.zeros((n, 4)) for _ in range(5)]
+        self.qp = [self.q[0].copy()] + [np.zeros((n, 4)) for _ in range(5)]
+        self.wGlobal = self.w[0].copy(); self.wLocal = self.w[0].copy(); self.wpGlobal = self.w[0].copy(); self.wpLocal = self.w[0].copy()
+        # particles (DEM.cpp:236-245, elmt::generateParticles)
+        self.cluster, self.pproto = [], []
+        for k in range(n):
+            for i in range(sizes[k]):
+                self.cluster.append(k); self.pproto.append(i)
+        self.P = len(self.cluster)
+        self.comp = [[p for p in range(self.P) if self.cluster[p] == k] for k in range(n)]
+        self.px0 = np.zeros((self.P, 3)); self.px1 = np.zeros((self.P, 3)); self.prv = np.zeros((self.P, 3))
+        self.pr = np.array([self.radius[k] for k in self.cluster])
+        self._update_particles(corrected=True)
+        self.nearWallP = [-1] * self.P
+        self.ppairs = []
+
+    def _update_particles(self, corrected):
+        x0 = self.x[0] if corrected else self.xp[0]
+        x1 = self.x[1] if corrected else self.xp[1]
+        q0 = self.q[0] if corrected else self.qp[0]
+        wg = self.wGlobal if corrected else self.wpGlobal
+        for p in range(self.P):
+            k = self.cluster[p]
+            self.px0[p] = x0[k]; self.prv[p] = 0.0; self.px1[p] = x1[k]
+            if self.size[k] > 1:
+                self.px0[p] = x0[k] + self.pr[p] * _project(self.proto[self.size[k]][self.pproto[p]], q0[k])
+                self.prv[p] = self.px0[p] - x0[k]
+                self.px1[p] = x1[k] + _cross(wg[k], self.prv[p])
+
+    def substep(self):
+        p, n, c = self.p, self.n, self.c
+        x, xp, w, wp, q, qp = self.x, self.xp, self.w, self.wp, self.q, self.qp
+        maxVel = 0.0
+        for k in range(n):
+            maxVel = max(maxVel, _norm2(x[1][k]))
+        self.maxDisp += math.sqrt(maxVel) * p["deltat"]
+        if self.maxDisp > 0.25 * self.nebrRange:
+            self.maxDisp = 0.0
+            self.rebuilds += 1
+            r2 = self.nebrRange * self.nebrRange
+            self.ppairs = [(a, b) for a in range(self.P) for b in range(a + 1, self.P)
+                           if self.cluster[a] != self.cluster[b] and _norm2(self.px0[b] - self.px0[a]) < r2]
+            for a in range(self.P):
+                self.nearWallP[a] = -1
+                for wi, wl in enumerate(self.walls):
+                    if float(np.dot(np.array(wl["n"]), self.px0[a] - np.array(wl["p"]))) < self.nebrRange:
+                        self.nearWallP[a] = wi
+                        break
+        # predictor: positions and spins as for spheres, plus the quaternions (c2 coefficients) and the frames
+        xp[0] = x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4]
+        xp[1] = x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3]
+        xp[2] = x[2] + x[3] * c[0] + x[4] * c[1] + x[5] * c[2]
+        xp[3] = x[3] + x[4] * c[0] + x[5] * c[1]
+        xp[4] = x[4] + x[5] * c[0]
+        xp[5] = x[5].copy()
+        qp[0] = q[0] + q[1] * c[0] + q[2] * c[1] + q[3] * c[2] + q[4] * c[3] + q[5] * c[4]
+        qp[1] = q[1] + q[2] * c[0] + q[3] * c[1] + q[4] * c[2] + q[5] * c[3]
+        qp[2] = q[2] + q[3] * c[0] + q[4] * c[1] + q[5] * c[2]
+        qp[3] = q[3] + q[4] * c[0] + q[5] * c[1]
+        qp[4] = q[4] + q[5] * c[0]
+        qp[5] = q[5].copy()
+        for k in range(n):
+            qp[0][k] = _qnormalize(qp[0][k])
+        wp[0] = w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4]
+        wp[1] = w[1] + w[2] * c[0] + w[3] * c[1] + w[4] * c[2] + w[5] * c[3]
+        wp[2] = w[2] + w[3] * c[0] + w[4] * c[1] + w[5] * c[2]
+        wp[3] = w[3] + w[4] * c[0] + w[5] * c[1]
+        wp[4] = w[4] + w[5] * c[0]
+        wp[5] = w[5].copy()
+        self.wpGlobal = wp[0].copy()
+        self.wpLocal = np.array([_project(self.wpGlobal[k], _qadj(qp[0][k])) for k in range(n)])
+        self._update_particles(corrected=False)
+        FP, FW, MP, MW = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        for a, b in self.ppairs:
+            d = self.px0[b] - self.px0[a]
+            sig = self.pr[a] + self.pr[b]
+            if not (_norm2(d) < sig * sig):
+                continue
+            i, j = self.cluster[a], self.cluster[b]
+            dist = math.sqrt(_norm2(d))
+            overlap = self.pr[a] + self.pr[b] - dist
+            relVel = self.px1[b] - self.px1[a]
+            en = d / dist
+            vn = float(np.dot(relVel, en))
+            normalRelVel = en * vn
+            effMass = self.m[i] * self.m[j] / (self.m[i] + self.m[j])
+            effRad = self.pr[a] * self.pr[b] / (self.pr[a] + self.pr[b])
+            fn = self.normal(overlap, vn, effRad, effMass)
+            nf = en * fn
+            vecRadI, vecRadJ = self.pr[a] * en, -self.pr[b] * en
+            cdI, cdJ = vecRadI + self.prv[a], vecRadJ + self.prv[b]
+            FP[i] = FP[i] - nf
+            if self.size[i] > 1:
+                MP[i] = MP[i] - _cross(cdI, nf)
+            FP[j] = FP[j] + nf
+            if self.size[j] > 1:
+                MP[j] = MP[j] + _cross(cdJ, nf)
+            relC = relVel - _cross(self.wpGlobal[i], vecRadI) + _cross(self.wpGlobal[j], vecRadJ)
+            tang = relC - normalRelVel
+            nt = math.sqrt(_norm2(tang))
+            if nt != 0.0:
+                ft = self.tangential(nt, fn, effRad, effMass, p["frictionCoefPart"])
+                et = tang / nt
+                tf = ft * et
+                MP[i] = MP[i] + _cross(cdI, tf); FP[i] = FP[i] + tf
+                MP[j] = MP[j] - _cross(cdJ, tf); FP[j] = FP[j] - tf
+        for a in range(self.P):
+            wi = self.nearWallP[a]
+            if wi < 0:
+                continue
+            k = self.cluster[a]
+            wl = self.walls[wi]
+            en = np.array(wl["n"])
+            dist = float(np.dot(en, self.px0[a] - np.array(wl["p"])))
+            overlap = self.pr[a] - dist
+            if overlap > 0.0:
+                cpv = np.zeros(3)
+                if wl["moving"]:
+                    dc = self.px0[a] - np.array(wl["rotCenter"])
+                    cpv = np.array(wl["vel"]) + _cross(np.array(wl["omega"]), dc - float(np.dot(dc, en)) * en)
+                relVel = self.px1[a] - cpv
+                vn = float(np.dot(relVel, en))
+                normalRelVel = en * vn
+                fn = self.normal(2.0 * overlap, vn, self.pr[a], self.m[k])
+                nf = en * fn
+                vecRadJ = -self.pr[a] * en
+                cdJ = vecRadJ
+                if self.size[k] > 1:
+                    cdJ = cdJ + (self.px0[a] - xp[0][k])
+                FW[k] = FW[k] + nf
+                if self.size[k] > 1:
+                    MW[k] = MW[k] + _cross(cdJ, nf)
+                relC = relVel + _cross(self.wpGlobal[k], vecRadJ)
+                tang = relC - normalRelVel
+                nt = math.sqrt(_norm2(tang))
+                if nt != 0.0:
+                    ft = self.tangential(nt, fn, self.pr[a], self.m[k], p["frictionCoefWall"])
+                    et = tang / math.sqrt(_norm2(tang))
+                    tf = ft * et
+                    MW[k] = MW[k] - _cross(cdJ, tf)
+                    FW[k] = FW[k] - tf
+        demF = np.array(p["demF"])
+        for k in range(n):
+            FVisc = -6.0 * math.pi * p["numVisc"] * self.radius[k] * xp[1][k]
+            MVisc = -8.0 * math.pi * p["numVisc"] * self.radius[k] * self.radius[k] * self.radius[k] * self.wpGlobal[k]
+            x[2][k] = (FVisc + self.FHydro[k] + FP[k] + FW[k]) / self.m[k] + demF
+            mom = MVisc + self.MHydro[k] + MP[k] + MW[k]
+            momBf = _project(mom, _qadj(qp[0][k]))
+            I, wl_ = self.I[k], self.wpLocal[k]
+            waBf = np.array([(momBf[0] + (I[1] - I[2]) * wl_[1] * wl_[2]) / I[0], (momBf[1] + (I[2] - I[0]) * wl_[2] * wl_[0]) / I[1],
+                             (momBf[2] + (I[0] - I[1]) * wl_[0] * wl_[1]) / I[2]])
+            w[1][k] = _project(waBf, qp[0][k])
+            if self.size[k] > 1:
+                n2 = qp[1][k][0] ** 2 + qp[1][k][1] ** 2 + qp[1][k][2] ** 2 + qp[1][k][3] ** 2
+                waQuat = np.array([-2.0 * n2, waBf[0], waBf[1], waBf[2]])
+                q[2][k] = 0.5 * _qmul(qp[0][k], waQuat)
+        c2, c1 = self.coeff2, self.coeff1
+        x2c = x[2] - xp[2]
+        x[0] = xp[0] + x2c * c2[0]; x[1] = xp[1] + x2c * c2[1]
+        x[3] = xp[3] + x2c * c2[3]; x[4] = xp[4] + x2c * c2[4]; x[5] = xp[5] + x2c * c2[5]
+        for k in range(6):
+            xp[k] = x[k].copy()
+        w1c = w[1] - wp[1]
+        w[0] = wp[0] + w1c * c1[0]
+        w[2] = wp[2] + w1c * c1[2]; w[3] = wp[3] + w1c * c1[3]; w[4] = wp[4] + w1c * c1[4]; w[5] = wp[5] + w1c * c1[5]
+        for k in range(6):
+            wp[k] = w[k].copy()
+        q2c = q[2] - qp[2]
+        q[0] = qp[0] + q2c * c2[0]; q[1] = qp[1] + q2c * c2[1]
+        q[3] = qp[3] + q2c * c2[3]; q[4] = qp[4] + q2c * c2[4]; q[5] = qp[5] + q2c * c2[5]
+        for k in range(n):
+            q[0][k] = _qnormalize(q[0][k])
+        for k in range(6):
+            qp[k] = q[k].copy()
+        self.wGlobal = w[0].copy()
+        self.wLocal = np.array([_project(self.wGlobal[k], _qadj(q[0][k])) for k in range(n)])
+        self._update_particles(corrected=True)
+
+    def step(self, FHydro, MHydro):
+        self.FHydro = np.asarray(FHydro, dtype=float).reshape(-1, 3); self.MHydro = np.asarray(MHydro, dtype=float).reshape(-1, 3)
+        for _ in range(self.p["multiStep"]):
+            self.substep()
+        return self.px0.copy(), self.prv.copy(), self.x[1].copy(), self.wGlobal.copy()

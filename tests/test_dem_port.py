@@ -73,3 +73,24 @@ def test_lb_mirror_refuses_clusters_and_periodic_dem_before_touching_the_device(
     assert len(dem["pbcs"]) == 2
     with pytest.raises(ValueError, match="periodic DEM boundaries"):
         lb.demInit(dem)
+
+
+@pytest.mark.parametrize("name", ("cluster_dem", "clusters_hit"))
+def test_cluster_port_follows_reference_trace(name):
+    """The general restatement (elements of 2-4 spheres: quaternions, lever arms, per-particle tables) against the reference's
+    recorded particles -- positions and lever arms of every sphere, velocity and spin of every element, every LB step."""
+    import dem_port
+    g = gu.Golden(name)
+    dem = g.dem()
+    P = dem_port.DemPortClusters(dem)
+    n = len(dem["elmts"])
+    F = np.zeros((n, 3)); M = np.zeros((n, 3))
+    worst = 0.0
+    for s in range(g.steps):
+        parts, elmts, comps, flag = g.trace[s]
+        px0, prv, x1, wg = P.step(F, M)
+        assert len(px0) == len(parts)
+        worst = max(worst, np.abs(px0 - parts["x0"]).max(), np.abs(prv - parts["radiusVec"]).max(), np.abs(x1 - elmts["x1"]).max(),
+                    np.abs(wg - elmts["wGlobal"]).max())
+        F, M = g.forces[s][0], g.forces[s][1]
+    assert worst <= 1e-12, worst
