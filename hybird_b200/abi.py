@@ -37,7 +37,8 @@ class LbGpuDemParams(C.Structure):
                 ("nebrRange", C.c_double), ("maxDisp", C.c_double)]
 
 
-DEM_ELEMENT_DTYPE = np.dtype([("x0", "<f8", 3), ("x1", "<f8", 3), ("w0", "<f8", 3), ("radius", "<f8"), ("m", "<f8"), ("I", "<f8", 3)])
+DEM_ELEMENT_DTYPE = np.dtype([("x0", "<f8", 3), ("x1", "<f8", 3), ("w0", "<f8", 3), ("radius", "<f8"), ("m", "<f8"), ("I", "<f8", 3),
+                              ("size", "<i4"), ("pad", "<i4")])
 DEM_WALL_DTYPE = np.dtype([("n", "<f8", 3), ("p", "<f8", 3), ("vel", "<f8", 3), ("omega", "<f8", 3), ("rotCenter", "<f8", 3),
                            ("moving", "<i4"), ("pad", "<i4")])
 
@@ -46,7 +47,7 @@ EXPORTS = ("lbGpuLastError", "lbGpuAbiVersion", "lbGpuDeviceCount", "lbGpuSlabRa
            "lbGpuParticleForces", "lbGpuFetchFields", "lbGpuStateBytes", "lbGpuSaveState", "lbGpuLoadState", "lbGpuCounts", "lbGpuCountsLocal", "lbGpuSynchronize", "lbGpuLastStepMs",
            "lbGpuLastKernelMs", "lbGpuLaunchCount", "lbGpuSelfTest", "lbGpuFinalize", "lbGpuCommUniqueId",
            "lbGpuCommInit", "lbGpuCommInfo", "lbGpuCommFinalize", "lbGpuPeerHalo", "lbGpuFluidSummary", "lbGpuWriteVti",
-           "lbGpuDemInit", "lbGpuDemStep", "lbGpuRunDem", "lbGpuDemState", "lbGpuDemContacts", "lbGpuGraphInfo", "lbGpuPhaseTrace", "lbGpuPhaseMs")
+           "lbGpuDemInit", "lbGpuDemStep", "lbGpuRunDem", "lbGpuDemState", "lbGpuDemContacts", "lbGpuDemParticles", "lbGpuGraphInfo", "lbGpuPhaseTrace", "lbGpuPhaseMs")
 
 _lib = None
 
@@ -128,6 +129,8 @@ def load_library(build_if_missing=True):
     L.lbGpuRunDem.argtypes = [vp, C.c_int, C.c_uint32]
     L.lbGpuDemState.restype = C.c_int
     L.lbGpuDemState.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_double * 3)]
+    L.lbGpuDemParticles.restype = C.c_int
+    L.lbGpuDemParticles.argtypes = [vp, C.POINTER(C.c_uint32), vp, vp, vp]
     L.lbGpuDemContacts.restype = C.c_int
     L.lbGpuDemContacts.argtypes = [vp, vp, vp, vp, vp]
     L.lbGpuPhaseTrace.restype = C.c_int

@@ -1,24 +1,27 @@
-// lb_dem.cuh -- the DEM sub-steps of a coupled cycle on the device, for single-sphere elements.
+// lb_dem.cuh -- the DEM sub-steps of a coupled cycle on the device: elements of one to four spheres
+// (single spheres and the reference's clusters) between plane walls.
 //
 // What DEM::discreteElementStep (DEM.cpp:331-376) does between two LB steps, restated per element:
 //   k_dem_trigger          DEM::evalMaxDisp + the neighbour-table trigger (DEM.cpp:1314-1324, 340-346)
-//   k_dem_neighbours       when triggered: DEM::evalNeighborTable (DEM.cpp:1377-1494) as one partner list per element -- every
-//                          element whose centre is closer than nebrRange NOW, in ascending index order
-//   k_dem_predict          DEM::evalNearWallTable when triggered (DEM.cpp:1496-1513: the FIRST wall within nebrRange, at the
-//                          corrected position), elmt::predict (elmt.cpp:139-177), particle::updatePredicted
+//   k_dem_neighbours       when triggered: DEM::evalNeighborTable (DEM.cpp:1377-1494) as one partner list per PARTICLE -- every
+//                          particle of another element whose centre is closer than nebrRange NOW, in ascending index order
+//                          (k_grid_* + k_dem_neighbours_grid: the same lists through a uniform grid, for large beds)
+//   k_dem_predict          DEM::evalNearWallTable when triggered (DEM.cpp:1496-1513: the FIRST wall within nebrRange of a
+//                          particle, at the corrected position), elmt::predict (elmt.cpp:139-177: positions, orientation
+//                          quaternions, spins), particle::updatePredicted (elmt.cpp:261-275)
 //   k_dem_forces_correct   particle-particle and wall-particle contacts (DEM.cpp:1668-1717, 1801-1982) with the LINEAR /
-//                          HERTZIAN laws (DEM.cpp:2138-2224), Newton's equations (DEM.cpp:1150-1181), elmt::correct
-//                          (elmt.cpp:179-254), particle::updateCorrected
+//                          HERTZIAN laws (DEM.cpp:2138-2224) and the lever arms of non-spherical elements, Newton's equations
+//                          in the body frame (DEM.cpp:1150-1181), elmt::correct (elmt.cpp:179-254), particle::updateCorrected
 //   k_dem_export           the particle / element lists LB::latticeBoltzmannCouplingStep and LB::computeHydroForces read
 // The hydrodynamic force and torque come straight from the LB step's per-element reduction (physical units), the
 // positions and velocities go straight into the coupling step: a coupled cycle has no host round trip for the particles.
-// The contact laws are memoryless (no tangential spring), and a pair's force is bit-identical whichever of the two is
-// "I" (both threads of a pair evaluate it with the lower index as I), so every element sums the contacts with its
-// partners in ascending index order: deterministic, no atomics.  Broad phase: the reference searches its table with
+// The contact laws are memoryless (no tangential spring), and both threads of a pair evaluate the contact with the lower
+// particle index as "I", so the pair's force is identical on both sides and every element sums the contacts of its particles
+// with their partners in ascending index order: deterministic, no atomics.  Broad phase: the reference searches its table with
 // linked cells (DEM.cpp:1326-1375) whose width is at least nebrRange wherever the domain is wider than six radii, so its
 // table IS the set of pairs within nebrRange at rebuild time; here a rebuild compares all pairs through shared-memory
-// tiles (small beds) or bins the elements into a uniform grid (k_grid_*, large beds) and the sub-steps in between only walk
-// the partner lists.  No periodic boundaries (ghost particles), cylinders, objects, clusters.
+// tiles (small beds) or bins the particles into a uniform grid (k_grid_*, large beds) and the sub-steps in between only walk
+// the partner lists.  No periodic boundaries (ghost particles), cylinders, objects.
 // Compiled with -fmad=false like the LB kernels: the reference's operation order is kept.
 #pragma once
 #include <stdint.h>
@@ -30,15 +33,23 @@ struct Params {
     double knConst, ksConst, dampCoeff, viscTang, linearStiff, frictionCoefPart, frictionCoefWall, numVisc;
     double demF[3], deltat, nebrRange;
     double c[5], coeff1[6], coeff2[6];  // DEM::predictor / DEM::corrector constants (DEM.cpp:1067-1112), computed on the host
+    double proto[5][4][3];              // DEM::compositeProperties (DEM.cpp:404-433): sphere i of an element of `size`, unit = radius
 };
 struct Wall { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int moving, pad; };
 struct Elmt {
     double x[6][3], xp[6][3], w[6][3], wp[6][3];
+    double q[6][4], qp[6][4];  // orientation (elmt::q0..q5): the identity and zeros for a single sphere, never touched then
     double radius, m, I[3];
     double fc[4][3];  // FParticle, FWall, MParticle, MWall of the last sub-step (IO::exportForces reads the first two)
-    int nearWall, pad;
+    int size, pBegin;  // its particles: [pBegin, pBegin + size)
+};
+// one sphere of an element: corrected (c) and predicted (p) centre, lever arm (radiusVec) and velocity
+struct Part {
+    double xc[3], rvc[3], xp[3], rvp[3], vp[3];
+    int cluster, proto, nearWall, pad;
 };
 struct V3 { double x, y, z; };
+struct Q4 { double q0, q1, q2, q3; };
 __device__ __forceinline__ V3 v3(const double* a) { return { a[0], a[1], a[2] }; }
 __device__ __forceinline__ V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
 __device__ __forceinline__ V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
@@ -50,6 +61,26 @@ __device__ __forceinline__ double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y
 __device__ __forceinline__ double norm2(V3 a) { return a.x * a.x + a.y * a.y + a.z * a.z; }
 __device__ __forceinline__ V3 cross(V3 a, V3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
 __device__ __forceinline__ void put(double* d, V3 a) { d[0] = a.x; d[1] = a.y; d[2] = a.z; }
+// quaternions as the reference writes them (vector.cpp:269-310, 463-504)
+__device__ __forceinline__ Q4 q4(const double* a) { return { a[0], a[1], a[2], a[3] }; }
+__device__ __forceinline__ void putq(double* d, Q4 a) { d[0] = a.q0; d[1] = a.q1; d[2] = a.q2; d[3] = a.q3; }
+__device__ __forceinline__ Q4 operator+(Q4 a, Q4 b) { return { a.q0 + b.q0, a.q1 + b.q1, a.q2 + b.q2, a.q3 + b.q3 }; }
+__device__ __forceinline__ Q4 operator-(Q4 a, Q4 b) { return { a.q0 - b.q0, a.q1 - b.q1, a.q2 - b.q2, a.q3 - b.q3 }; }
+__device__ __forceinline__ Q4 operator*(Q4 a, double s) { return { a.q0 * s, a.q1 * s, a.q2 * s, a.q3 * s }; }
+__device__ __forceinline__ Q4 operator*(double s, Q4 a) { return { s * a.q0, s * a.q1, s * a.q2, s * a.q3 }; }
+__device__ __forceinline__ Q4 qadj(Q4 a) { return { a.q0, -a.q1, -a.q2, -a.q3 }; }
+__device__ __forceinline__ Q4 qmul(Q4 q, Q4 r) {  // q.multiply(r)
+    return { r.q0 * q.q0 - r.q1 * q.q1 - r.q2 * q.q2 - r.q3 * q.q3, r.q0 * q.q1 + r.q1 * q.q0 - r.q2 * q.q3 + r.q3 * q.q2,
+             r.q0 * q.q2 + r.q1 * q.q3 + r.q2 * q.q0 - r.q3 * q.q1, r.q0 * q.q3 - r.q1 * q.q2 + r.q2 * q.q1 + r.q3 * q.q0 };
+}
+__device__ __forceinline__ Q4 qnormalize(Q4 a) {
+    const double n = sqrt(a.q0 * a.q0 + a.q1 * a.q1 + a.q2 * a.q2 + a.q3 * a.q3);
+    return { a.q0 / n, a.q1 / n, a.q2 / n, a.q3 / n };
+}
+__device__ __forceinline__ V3 project(V3 v, Q4 q) {  // quat2vec(q (0, v) q*)
+    const Q4 r = qmul(qmul(q, Q4{ 0.0, v.x, v.y, v.z }), qadj(q));
+    return { r.q1, r.q2, r.q3 };
+}
 
 // scal[0] = maxDisp, flag[0] = rebuild the tables in this sub-step, flag[2] = rebuilds so far
 __global__ void __launch_bounds__(1024) k_dem_trigger(const Elmt* __restrict__ e, uint32_t n, double deltat, double nebrRange,
@@ -71,55 +102,58 @@ __global__ void __launch_bounds__(1024) k_dem_trigger(const Elmt* __restrict__ e
     }
 }
 
-// partner lists: nbr[k * MAX_NBR + q], q < nNbr[k], ascending.  status[0] = largest list length seen (> MAX_NBR: error)
+// partner lists of the PARTICLES: nbr[a * MAX_NBR + q], q < nNbr[a], ascending particle indices of other elements.
+// status[0] = largest list length seen (> MAX_NBR: error)
 constexpr int MAX_NBR = 48;
-__global__ void __launch_bounds__(128) k_dem_neighbours(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+__global__ void __launch_bounds__(128) k_dem_neighbours(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
                                                         uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr, uint32_t* __restrict__ status) {
     if (!*flag) return;
     __shared__ double sx[128], sy[128], sz[128];
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = k < n;
-    const V3 xk = live ? v3(e[k].x[0]) : V3{ 0, 0, 0 };
+    __shared__ int sc[128];
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = a < nP;
+    const V3 xa = live ? v3(pt[a].xc) : V3{ 0, 0, 0 };
+    const int ca = live ? pt[a].cluster : -1;
     const double r2 = nebrRange * nebrRange;
     uint32_t cnt = 0;
-    for (uint32_t base = 0; base < n; base += 128) {
+    for (uint32_t base = 0; base < nP; base += 128) {
         const uint32_t j = base + threadIdx.x;
         __syncthreads();
-        if (j < n) { sx[threadIdx.x] = e[j].x[0][0]; sy[threadIdx.x] = e[j].x[0][1]; sz[threadIdx.x] = e[j].x[0][2]; }
+        if (j < nP) { sx[threadIdx.x] = pt[j].xc[0]; sy[threadIdx.x] = pt[j].xc[1]; sz[threadIdx.x] = pt[j].xc[2]; sc[threadIdx.x] = pt[j].cluster; }
         __syncthreads();
-        const uint32_t m = n - base < 128u ? n - base : 128u;
+        const uint32_t m = nP - base < 128u ? nP - base : 128u;
         if (live)
             for (uint32_t q = 0; q < m; ++q) {
-                const V3 d = { sx[q] - xk.x, sy[q] - xk.y, sz[q] - xk.z };
-                if (base + q != k && norm2(d) < r2) {
-                    if (cnt < (uint32_t)MAX_NBR) nbr[(size_t)k * MAX_NBR + cnt] = base + q;
+                const V3 d = { sx[q] - xa.x, sy[q] - xa.y, sz[q] - xa.z };
+                if (sc[q] != ca && norm2(d) < r2) {
+                    if (cnt < (uint32_t)MAX_NBR) nbr[(size_t)a * MAX_NBR + cnt] = base + q;
                     ++cnt;
                 }
             }
     }
     if (live) {
-        nNbr[k] = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
+        nNbr[a] = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
         if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // The same partner lists through a uniform grid (the reference's linked cells, DEM.cpp:1326-1375, as a counting sort): cells
-// at least nebrRange wide over the bounding box of the elements, elements binned by cell (count - scan - fill), every element
-// looks at the 27 cells around its own and sorts what it finds, so the lists are the ascending lists of the all-pairs pass --
-// identical results, O(n) instead of O(n^2): 20 000 spheres 1.7 ms -> tens of microseconds, and beds of 1e6 become possible.
-// All launches are gated on the rebuild flag.  grid[0..2] = cells per axis, gridOrg/gridInv = origin and 1 / cell width.
+// at least nebrRange wide over the bounding box of the particles, particles binned by cell (count - scan - fill), every
+// particle looks at the 27 cells around its own and sorts what it finds, so the lists are the ascending lists of the all-pairs
+// pass -- identical results, O(n) instead of O(n^2): 20 000 spheres 1.7 ms -> 0.2 ms, and beds of 1e6 become possible.
+// All launches are gated on the rebuild flag.
 // ---------------------------------------------------------------------------------------------
 struct Grid { double org[3], inv[3]; uint32_t dim[3], nCells; };
 constexpr uint32_t GRID_MAX_CELLS = 1u << 21;
 
-__global__ void __launch_bounds__(1024) k_grid_bounds(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+__global__ void __launch_bounds__(1024) k_grid_bounds(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
                                                       Grid* __restrict__ g, uint32_t* __restrict__ cellCount) {
     if (!*flag) return;
     __shared__ double smin[3][32], smax[3][32];
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x)
-        for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], e[k].x[0][c]); hi[c] = fmax(hi[c], e[k].x[0][c]); }
+    for (uint32_t k = threadIdx.x; k < nP; k += blockDim.x)
+        for (int c = 0; c < 3; ++c) { lo[c] = fmin(lo[c], pt[k].xc[c]); hi[c] = fmax(hi[c], pt[k].xc[c]); }
     for (int c = 0; c < 3; ++c) {
         for (int o = 16; o > 0; o >>= 1) { lo[c] = fmin(lo[c], __shfl_down_sync(0xffffffffu, lo[c], o)); hi[c] = fmax(hi[c], __shfl_down_sync(0xffffffffu, hi[c], o)); }
         if ((threadIdx.x & 31) == 0) { smin[c][threadIdx.x >> 5] = lo[c]; smax[c][threadIdx.x >> 5] = hi[c]; }
@@ -149,13 +183,13 @@ __device__ __forceinline__ uint32_t grid_cell(const Grid& g, const double* x, in
     *cz = min((int)g.dim[2] - 1, max(0, (int)((x[2] - g.org[2]) * g.inv[2])));
     return (uint32_t)*cx + g.dim[0] * ((uint32_t)*cy + g.dim[1] * (uint32_t)*cz);
 }
-__global__ void __launch_bounds__(128) k_grid_count(const Elmt* __restrict__ e, uint32_t n, const uint32_t* __restrict__ flag, const Grid* __restrict__ g,
+__global__ void __launch_bounds__(128) k_grid_count(const Part* __restrict__ pt, uint32_t nP, const uint32_t* __restrict__ flag, const Grid* __restrict__ g,
                                                     uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellOf) {
     if (!*flag) return;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= nP) return;
     int cx, cy, cz;
-    const uint32_t c = grid_cell(*g, e[k].x[0], &cx, &cy, &cz);
+    const uint32_t c = grid_cell(*g, pt[k].xc, &cx, &cy, &cz);
     cellOf[k] = c;
     atomicAdd(&cellCount[c], 1u);
 }
@@ -181,26 +215,27 @@ __global__ void __launch_bounds__(1024) k_grid_scan(const uint32_t* __restrict__
     for (uint32_t c = b0; c < b1; ++c) { const uint32_t v = cellCount[c]; cellCount[c] = run; cellFill[c] = 0u; run += v; }
     if (threadIdx.x == 1023) cellCount[nC] = sa[1023];
 }
-__global__ void __launch_bounds__(128) k_grid_fill(uint32_t n, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ cellStart,
+__global__ void __launch_bounds__(128) k_grid_fill(uint32_t nP, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ cellStart,
                                                    uint32_t* __restrict__ cellFill, const uint32_t* __restrict__ cellOf, uint32_t* __restrict__ sorted) {
     if (!*flag) return;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= nP) return;
     const uint32_t c = cellOf[k];
     sorted[cellStart[c] + atomicAdd(&cellFill[c], 1u)] = k;
 }
-__global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Elmt* __restrict__ e, uint32_t n, double nebrRange, const uint32_t* __restrict__ flag,
+__global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
                                                              const Grid* __restrict__ gp, const uint32_t* __restrict__ cellStart,
                                                              const uint32_t* __restrict__ sorted, uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr,
                                                              uint32_t* __restrict__ status) {
     if (!*flag) return;
-    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nP) return;
     const Grid g = *gp;
-    const V3 xk = v3(e[k].x[0]);
+    const V3 xa = v3(pt[a].xc);
+    const int ca = pt[a].cluster;
     const double r2 = nebrRange * nebrRange;
     int cx, cy, cz;
-    grid_cell(g, e[k].x[0], &cx, &cy, &cz);
+    grid_cell(g, pt[a].xc, &cx, &cy, &cz);
     uint32_t found[MAX_NBR];
     uint32_t cnt = 0;
     // cells may be wider than nebrRange but never narrower: the 27 cells around cover the range
@@ -215,8 +250,8 @@ __global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Elmt* __restr
             const uint32_t c0 = (uint32_t)x0 + g.dim[0] * ((uint32_t)y + g.dim[1] * (uint32_t)z), c1 = c0 + (uint32_t)(x1 - x0);
             for (uint32_t q = cellStart[c0]; q < cellStart[c1 + 1]; ++q) {
                 const uint32_t j = sorted[q];
-                if (j == k) continue;
-                const V3 d = v3(e[j].x[0]) - xk;
+                if (pt[j].cluster == ca) continue;
+                const V3 d = v3(pt[j].xc) - xa;
                 if (norm2(d) < r2) {
                     if (cnt < (uint32_t)MAX_NBR) found[cnt] = j;
                     ++cnt;
@@ -225,44 +260,91 @@ __global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Elmt* __restr
         }
     }
     const uint32_t m = cnt < (uint32_t)MAX_NBR ? cnt : (uint32_t)MAX_NBR;
-    for (uint32_t a = 1; a < m; ++a) {  // ascending, like the all-pairs pass (the order within a cell is whatever the atomics gave)
-        const uint32_t v = found[a];
-        uint32_t b = a;
+    for (uint32_t u = 1; u < m; ++u) {  // ascending, like the all-pairs pass (the order within a cell is whatever the atomics gave)
+        const uint32_t v = found[u];
+        uint32_t b = u;
         while (b > 0 && found[b - 1] > v) { found[b] = found[b - 1]; --b; }
         found[b] = v;
     }
-    for (uint32_t a = 0; a < m; ++a) nbr[(size_t)k * MAX_NBR + a] = found[a];
-    nNbr[k] = m;
+    for (uint32_t u = 0; u < m; ++u) nbr[(size_t)a * MAX_NBR + u] = found[u];
+    nNbr[a] = m;
     if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
 }
 
-__global__ void __launch_bounds__(128) k_dem_predict(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p,
+// particle::updateCorrected (elmt.cpp:277-290): the spheres of element el at its corrected state
+__device__ __forceinline__ void particles_corrected(const Params& p, const Elmt& el, Part* __restrict__ pt) {
+    const V3 x0 = v3(el.x[0]);
+    for (int i = 0; i < el.size; ++i) {
+        Part& a = pt[el.pBegin + i];
+        V3 xa = x0, rv = { 0.0, 0.0, 0.0 };
+        if (el.size > 1) {
+            xa = x0 + el.radius * project(v3(p.proto[el.size][i]), q4(el.q[0]));
+            rv = xa - x0;
+        }
+        put(a.xc, xa); put(a.rvc, rv);
+    }
+}
+__global__ void __launch_bounds__(128) k_dem_init_particles(const Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p, Part* __restrict__ pt) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) particles_corrected(p, e[k], pt);
+}
+
+__global__ void __launch_bounds__(128) k_dem_predict(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p, Part* __restrict__ pt,
                                                      const Wall* __restrict__ walls, uint32_t nWalls, const uint32_t* __restrict__ flag) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     Elmt& el = e[k];
     if (*flag) {
-        int nw = -1;
-        const V3 x0 = v3(el.x[0]);
-        for (uint32_t w = 0; w < nWalls; ++w)
-            if (dot(v3(walls[w].n), x0 - v3(walls[w].p)) < p.nebrRange) { nw = (int)w; break; }
-        el.nearWall = nw;
+        for (int i = 0; i < el.size; ++i) {
+            Part& a = pt[el.pBegin + i];
+            int nw = -1;
+            const V3 xa = v3(a.xc);
+            for (uint32_t w = 0; w < nWalls; ++w)
+                if (dot(v3(walls[w].n), xa - v3(walls[w].p)) < p.nebrRange) { nw = (int)w; break; }
+            a.nearWall = nw;
+        }
     }
     const double* c = p.c;
     V3 x[6], w[6];
     for (int q = 0; q < 6; ++q) { x[q] = v3(el.x[q]); w[q] = v3(el.w[q]); }
-    put(el.xp[0], x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4]);
-    put(el.xp[1], x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3]);
+    const V3 xp0 = x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4];
+    const V3 xp1 = x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3];
+    put(el.xp[0], xp0);
+    put(el.xp[1], xp1);
     put(el.xp[2], x[2] + x[3] * c[0] + x[4] * c[1] + x[5] * c[2]);
     put(el.xp[3], x[3] + x[4] * c[0] + x[5] * c[1]);
     put(el.xp[4], x[4] + x[5] * c[0]);
     put(el.xp[5], x[5]);
-    put(el.wp[0], w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4]);
+    const V3 wp0 = w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4];
+    put(el.wp[0], wp0);
     put(el.wp[1], w[1] + w[2] * c[0] + w[3] * c[1] + w[4] * c[2] + w[5] * c[3]);
     put(el.wp[2], w[2] + w[3] * c[0] + w[4] * c[1] + w[5] * c[2]);
     put(el.wp[3], w[3] + w[4] * c[0] + w[5] * c[1]);
     put(el.wp[4], w[4] + w[5] * c[0]);
     put(el.wp[5], w[5]);
+    Q4 qp0 = { 1.0, 0.0, 0.0, 0.0 };
+    if (el.size > 1) {
+        Q4 q[6];
+        for (int s = 0; s < 6; ++s) q[s] = q4(el.q[s]);
+        qp0 = qnormalize(q[0] + q[1] * c[0] + q[2] * c[1] + q[3] * c[2] + q[4] * c[3] + q[5] * c[4]);
+        putq(el.qp[0], qp0);
+        putq(el.qp[1], q[1] + q[2] * c[0] + q[3] * c[1] + q[4] * c[2] + q[5] * c[3]);
+        putq(el.qp[2], q[2] + q[3] * c[0] + q[4] * c[1] + q[5] * c[2]);
+        putq(el.qp[3], q[3] + q[4] * c[0] + q[5] * c[1]);
+        putq(el.qp[4], q[4] + q[5] * c[0]);
+        putq(el.qp[5], q[5]);
+    }
+    // particle::updatePredicted (elmt.cpp:261-275); elmt::wpGlobal = wp0 (wSolver)
+    for (int i = 0; i < el.size; ++i) {
+        Part& a = pt[el.pBegin + i];
+        V3 xa = xp0, rv = { 0.0, 0.0, 0.0 }, va = xp1;
+        if (el.size > 1) {
+            xa = xp0 + el.radius * project(v3(p.proto[el.size][i]), qp0);
+            rv = xa - xp0;
+            va = xp1 + cross(wp0, rv);
+        }
+        put(a.xp, xa); put(a.rvp, rv); put(a.vp, va);
+    }
 }
 
 __device__ __forceinline__ double normal_contact(const Params& p, double overlap, double vreln, double effRad, double effMass) {
@@ -282,7 +364,7 @@ __device__ __forceinline__ double tangential_contact(const Params& p, double vre
 }
 
 // hydro: per element {FHydro(3), MHydro(3), fluidVolume} in physical units, as the LB step's reduction left them
-__global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p,
+__global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p, Part* __restrict__ pt,
                                                             const Wall* __restrict__ walls, const double* __restrict__ hydro,
                                                             const uint32_t* __restrict__ nbr, const uint32_t* __restrict__ nNbr) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -290,82 +372,109 @@ __global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e
     Elmt& el = e[k];
     const V3 xk = v3(el.xp[0]), vk = v3(el.xp[1]), wk = v3(el.wp[0]);
     const double rk = el.radius, mk = el.m;
+    const bool cluster = el.size > 1;
     V3 FP = { 0, 0, 0 }, FW = { 0, 0, 0 }, MP = { 0, 0, 0 }, MW = { 0, 0, 0 };
-    const uint32_t nn = nNbr[k];
-    for (uint32_t q = 0; q < nn; ++q) {
-        const uint32_t j = nbr[(size_t)k * MAX_NBR + q];
-        const Elmt& o = e[j];
-        const V3 xo = v3(o.xp[0]);
-        const bool iAmI = k < j;  // the pair's force is evaluated in the role assignment (lower index = I); see the header
-        const V3 d = iAmI ? xo - xk : xk - xo;  // partJ->x0 - partI->x0
-        const double rI = iAmI ? rk : o.radius, rJ = iAmI ? o.radius : rk;
-        const double sig = rI + rJ;
-        if (!(norm2(d) < sig * sig)) continue;
-        const double mI = iAmI ? mk : o.m, mJ = iAmI ? o.m : mk;
-        const V3 vI = iAmI ? vk : v3(o.xp[1]), vJ = iAmI ? v3(o.xp[1]) : vk;
-        const V3 wI = iAmI ? wk : v3(o.wp[0]), wJ = iAmI ? v3(o.wp[0]) : wk;
-        const double dist = sqrt(norm2(d));
-        const double overlap = rI + rJ - dist;
-        const V3 relVel = vJ - vI;
-        const V3 en = d / dist;
-        const double vn = dot(relVel, en);
-        const V3 normalRelVel = en * vn;
-        const double effMass = mI * mJ / (mI + mJ);
-        const double effRad = rI * rJ / (rI + rJ);
-        const double fn = normal_contact(p, overlap, vn, effRad, effMass);
-        const V3 nf = en * fn;
-        const V3 vecRadI = rI * en, vecRadJ = -rJ * en;
-        FP = iAmI ? FP - nf : FP + nf;
-        const V3 relC = relVel - cross(wI, vecRadI) + cross(wJ, vecRadJ);
-        const V3 tang = relC - normalRelVel;
-        const double nt = sqrt(norm2(tang));
-        if (nt != 0.0) {
-            const double ft = tangential_contact(p, nt, fn, effRad, effMass, p.frictionCoefPart);
-            const V3 et = tang / nt;
-            const V3 tf = ft * et;
-            if (iAmI) { MP = MP + cross(vecRadI, tf); FP = FP + tf; }
-            else { MP = MP - cross(vecRadJ, tf); FP = FP - tf; }
-        }
-    }
-    if (el.nearWall >= 0) {
-        const Wall wl = walls[el.nearWall];
-        const V3 en = v3(wl.n);
-        const double dist = dot(en, xk - v3(wl.p));
-        const double overlap = rk - dist;
-        if (overlap > 0.0) {
-            V3 cpv = { 0.0, 0.0, 0.0 };
-            if (wl.moving) {
-                const V3 dc = xk - v3(wl.rotCenter);
-                cpv = v3(wl.vel) + cross(v3(wl.omega), dc - dot(dc, en) * en);
-            }
-            const V3 relVel = vk - cpv;
+    for (int i = 0; i < el.size; ++i) {
+        const uint32_t a = (uint32_t)el.pBegin + (uint32_t)i;
+        const Part pa = pt[a];
+        const uint32_t nn = nNbr[a];
+        for (uint32_t q = 0; q < nn; ++q) {
+            const uint32_t b = nbr[(size_t)a * MAX_NBR + q];
+            const Part& pb = pt[b];
+            const Elmt& o = e[pb.cluster];
+            const bool iAmI = a < b;  // the pair's force is evaluated in one role assignment (lower particle index = I) on both sides
+            const V3 xI = iAmI ? v3(pa.xp) : v3(pb.xp), xJ = iAmI ? v3(pb.xp) : v3(pa.xp);
+            const V3 d = xJ - xI;  // partJ->x0 - partI->x0
+            const double rI = iAmI ? rk : o.radius, rJ = iAmI ? o.radius : rk;
+            const double sig = rI + rJ;
+            if (!(norm2(d) < sig * sig)) continue;
+            const double mI = iAmI ? mk : o.m, mJ = iAmI ? o.m : mk;
+            const V3 vI = iAmI ? v3(pa.vp) : v3(pb.vp), vJ = iAmI ? v3(pb.vp) : v3(pa.vp);
+            const V3 wI = iAmI ? wk : v3(o.wp[0]), wJ = iAmI ? v3(o.wp[0]) : wk;
+            const double dist = sqrt(norm2(d));
+            const double overlap = rI + rJ - dist;
+            const V3 relVel = vJ - vI;
+            const V3 en = d / dist;
             const double vn = dot(relVel, en);
             const V3 normalRelVel = en * vn;
-            const double fn = normal_contact(p, 2.0 * overlap, vn, rk, mk);
+            const double effMass = mI * mJ / (mI + mJ);
+            const double effRad = rI * rJ / (rI + rJ);
+            const double fn = normal_contact(p, overlap, vn, effRad, effMass);
             const V3 nf = en * fn;
-            const V3 vecRadJ = -rk * en;
-            FW = FW + nf;
-            const V3 relC = relVel + cross(wk, vecRadJ);
+            const V3 vecRadI = rI * en, vecRadJ = -rJ * en;
+            // lever arm of the contact point about the element's centre: vecRad + particle::radiusVec (DEM.cpp:1841-1846)
+            const V3 cdMine = iAmI ? vecRadI + v3(pa.rvp) : vecRadJ + v3(pa.rvp);
+            if (iAmI) { FP = FP - nf; if (cluster) MP = MP - cross(cdMine, nf); }
+            else { FP = FP + nf; if (cluster) MP = MP + cross(cdMine, nf); }
+            const V3 relC = relVel - cross(wI, vecRadI) + cross(wJ, vecRadJ);
             const V3 tang = relC - normalRelVel;
             const double nt = sqrt(norm2(tang));
             if (nt != 0.0) {
-                const double ft = tangential_contact(p, nt, fn, rk, mk, p.frictionCoefWall);
-                const V3 et = tang / sqrt(norm2(tang));
+                const double ft = tangential_contact(p, nt, fn, effRad, effMass, p.frictionCoefPart);
+                const V3 et = tang / nt;
                 const V3 tf = ft * et;
-                MW = MW - cross(vecRadJ, tf);
-                FW = FW - tf;
+                if (iAmI) { MP = MP + cross(cdMine, tf); FP = FP + tf; }
+                else { MP = MP - cross(cdMine, tf); FP = FP - tf; }
+            }
+        }
+        if (pa.nearWall >= 0) {
+            const Wall wl = walls[pa.nearWall];
+            const V3 en = v3(wl.n);
+            const V3 xa = v3(pa.xp), va = v3(pa.vp);
+            const double dist = dot(en, xa - v3(wl.p));
+            const double overlap = rk - dist;
+            if (overlap > 0.0) {
+                V3 cpv = { 0.0, 0.0, 0.0 };
+                if (wl.moving) {
+                    const V3 dc = xa - v3(wl.rotCenter);
+                    cpv = v3(wl.vel) + cross(v3(wl.omega), dc - dot(dc, en) * en);
+                }
+                const V3 relVel = va - cpv;
+                const double vn = dot(relVel, en);
+                const V3 normalRelVel = en * vn;
+                const double fn = normal_contact(p, 2.0 * overlap, vn, rk, mk);
+                const V3 nf = en * fn;
+                const V3 vecRadJ = -rk * en;
+                V3 cdJ = vecRadJ;
+                if (cluster) cdJ = cdJ + (xa - xk);  // DEM.cpp:1937-1941
+                FW = FW + nf;
+                if (cluster) MW = MW + cross(cdJ, nf);
+                const V3 relC = relVel + cross(wk, vecRadJ);
+                const V3 tang = relC - normalRelVel;
+                const double nt = sqrt(norm2(tang));
+                if (nt != 0.0) {
+                    const double ft = tangential_contact(p, nt, fn, rk, mk, p.frictionCoefWall);
+                    const V3 et = tang / sqrt(norm2(tang));
+                    const V3 tf = ft * et;
+                    MW = MW - cross(cdJ, tf);
+                    FW = FW - tf;
+                }
             }
         }
     }
-    // Newton's equations (DEM.cpp:1150-1181); a sphere's body frame stays the global one (header)
+    // Newton's equations (DEM.cpp:1150-1181)
     const V3 FH = hydro ? v3(hydro + (size_t)7 * k) : V3{ 0, 0, 0 }, MH = hydro ? v3(hydro + (size_t)7 * k + 3) : V3{ 0, 0, 0 };
     const V3 FVisc = -6.0 * M_PI * p.numVisc * rk * vk;
     const V3 MVisc = -8.0 * M_PI * p.numVisc * rk * rk * rk * wk;
     const V3 x2 = (FVisc + FH + FP + FW) / mk + v3(p.demF);
     const V3 mom = MVisc + MH + MP + MW;
     const double* I = el.I;
-    const V3 w1 = { (mom.x + (I[1] - I[2]) * wk.y * wk.z) / I[0], (mom.y + (I[2] - I[0]) * wk.z * wk.x) / I[1],
-                    (mom.z + (I[0] - I[1]) * wk.x * wk.y) / I[2] };
+    V3 w1;
+    Q4 q2 = { 0.0, 0.0, 0.0, 0.0 };
+    if (!cluster) {
+        // a sphere's body frame stays the global one (its quaternion is the identity: the projections are exact identities)
+        w1 = { (mom.x + (I[1] - I[2]) * wk.y * wk.z) / I[0], (mom.y + (I[2] - I[0]) * wk.z * wk.x) / I[1],
+               (mom.z + (I[0] - I[1]) * wk.x * wk.y) / I[2] };
+    } else {
+        const Q4 qp0 = q4(el.qp[0]), qp1 = q4(el.qp[1]);
+        const V3 momBf = project(mom, qadj(qp0));
+        const V3 wl = project(wk, qadj(qp0));  // elmt::wpLocal (elmt.cpp:164-167)
+        const V3 waBf = { (momBf.x + (I[1] - I[2]) * wl.y * wl.z) / I[0], (momBf.y + (I[2] - I[0]) * wl.z * wl.x) / I[1],
+                          (momBf.z + (I[0] - I[1]) * wl.x * wl.y) / I[2] };
+        w1 = project(waBf, qp0);
+        const Q4 waQuat = { -2.0 * (qp1.q0 * qp1.q0 + qp1.q1 * qp1.q1 + qp1.q2 * qp1.q2 + qp1.q3 * qp1.q3), waBf.x, waBf.y, waBf.z };
+        q2 = 0.5 * qmul(qp0, waQuat);
+    }
     // elmt::correct
     const double* c2 = p.coeff2; const double* c1 = p.coeff1;
     V3 xp[6], wp[6];
@@ -378,25 +487,44 @@ __global__ void __launch_bounds__(128) k_dem_forces_correct(Elmt* __restrict__ e
     V3 w[6];
     w[0] = wp[0] + w1c * c1[0]; w[1] = w1;
     w[2] = wp[2] + w1c * c1[2]; w[3] = wp[3] + w1c * c1[3]; w[4] = wp[4] + w1c * c1[4]; w[5] = wp[5] + w1c * c1[5];
-    // every element reads the others' PREDICTED state (xp, wp) above and writes only its own corrected state (x, w);
-    // xp := x / wp := w (the tail of elmt::correct) happens at the top of the next predict, which overwrites them anyway
+    // every element reads the others' PREDICTED state (xp, wp, the particles' xp / rvp / vp) above and writes only its own
+    // corrected state (x, w, q, the particles' xc / rvc); xp := x ... (the tail of elmt::correct) happens at the top of the next
+    // predict, which overwrites them anyway
     for (int q = 0; q < 6; ++q) { put(el.x[q], x[q]); put(el.w[q], w[q]); }
+    if (cluster) {
+        Q4 qp[6];
+        for (int s = 0; s < 6; ++s) qp[s] = q4(el.qp[s]);
+        const Q4 q2c = q2 - qp[2];
+        putq(el.q[0], qnormalize(qp[0] + q2c * c2[0]));
+        putq(el.q[1], qp[1] + q2c * c2[1]);
+        putq(el.q[2], q2);
+        putq(el.q[3], qp[3] + q2c * c2[3]);
+        putq(el.q[4], qp[4] + q2c * c2[4]);
+        putq(el.q[5], qp[5] + q2c * c2[5]);
+    }
     put(el.fc[0], FP); put(el.fc[1], FW); put(el.fc[2], MP); put(el.fc[3], MW);
+    particles_corrected(p, el, pt);
 }
 
-// the lists the LB side reads (layout of LbGpuParticle / LbGpuElement, physical units): particle::updateCorrected for a
-// one-sphere element is x0 = elmt::x0 (the prototype offset is zero), r = radius; elmt::wGlobal = w0 (wSolver, elmt.cpp:232-235)
+// the lists the LB side reads (layout of LbGpuParticle / LbGpuElement, physical units): particle::updateCorrected, elmt::x1,
+// elmt::wGlobal = w0 (wSolver, elmt.cpp:232-235), elmt::components = the element's particles
 struct OutParticle { double x0[3], r, radiusVec[3]; uint32_t clusterIndex, particleIndex; };
 struct OutElement { double x1[3], wGlobal[3]; uint32_t compBegin, compEnd; };
-__global__ void __launch_bounds__(128) k_dem_export(const Elmt* __restrict__ e, uint32_t n, OutParticle* __restrict__ parts, OutElement* __restrict__ elmts,
-                                                    uint32_t* __restrict__ comps) {
+__global__ void __launch_bounds__(128) k_dem_export(const Elmt* __restrict__ e, uint32_t n, const Part* __restrict__ pt, OutParticle* __restrict__ parts,
+                                                    OutElement* __restrict__ elmts, uint32_t* __restrict__ comps) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    OutParticle op; OutElement oe;
-    for (int c = 0; c < 3; ++c) { op.x0[c] = e[k].x[0][c]; op.radiusVec[c] = 0.0; oe.x1[c] = e[k].x[1][c]; oe.wGlobal[c] = e[k].w[0][c]; }
-    op.r = e[k].radius; op.clusterIndex = k; op.particleIndex = k;
-    oe.compBegin = k; oe.compEnd = k + 1;
-    parts[k] = op; elmts[k] = oe; comps[k] = k;
+    OutElement oe;
+    for (int c = 0; c < 3; ++c) { oe.x1[c] = e[k].x[1][c]; oe.wGlobal[c] = e[k].w[0][c]; }
+    oe.compBegin = (uint32_t)e[k].pBegin; oe.compEnd = (uint32_t)(e[k].pBegin + e[k].size);
+    elmts[k] = oe;
+    for (int i = 0; i < e[k].size; ++i) {
+        const uint32_t a = (uint32_t)e[k].pBegin + (uint32_t)i;
+        OutParticle op;
+        for (int c = 0; c < 3; ++c) { op.x0[c] = pt[a].xc[c]; op.radiusVec[c] = pt[a].rvc[c]; }
+        op.r = e[k].radius; op.clusterIndex = k; op.particleIndex = a;
+        parts[a] = op; comps[a] = a;
+    }
 }
 
 }  // namespace lbdem

@@ -494,8 +494,9 @@ struct LbGpuHandle {
     struct Dem {
         bool on = false;
         lbdem::Params prm;
-        uint32_t n = 0, nWalls = 0;
+        uint32_t n = 0, nP = 0, nWalls = 0;  // elements, their particles (spheres), walls
         DevBuf<lbdem::Elmt> e;
+        DevBuf<lbdem::Part> pt;
         DevBuf<lbdem::Wall> walls;
         DevBuf<uint32_t> nbr, nNbr, flag;  // flag[0] = rebuild in this sub-step, [1] = longest partner list, [2] = rebuilds so far
         // uniform grid for the table rebuild of large beds (k_grid_*): LBGPU_DEM_GRID=0/1 overrides the choice by size
@@ -2436,26 +2437,26 @@ int dem_step(LbGpuHandle* h, const double* hydro) {
     static_assert(sizeof(lbdem::OutParticle) == sizeof(RawParticle) && sizeof(lbdem::OutElement) == sizeof(RawElement), "list layout");
     auto& D = h->dem;
     cudaStream_t st = h->stream;
-    const uint32_t n = D.n, nb = (n + 127) / 128;
+    const uint32_t n = D.n, nb = (n + 127) / 128, nP = D.nP, pb = (nP + 127) / 128;
     for (int sub = 0; sub < D.prm.multiStep; ++sub) {
         lbdem::k_dem_trigger<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.deltat, D.prm.nebrRange, D.scal.p, D.flag.p);
         if (D.grid) {
-            lbdem::k_grid_bounds<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p);
-            lbdem::k_grid_count<<<nb, 128, 0, st>>>(D.e.p, n, D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellOf.p);
+            lbdem::k_grid_bounds<<<1, 1024, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p);
+            lbdem::k_grid_count<<<pb, 128, 0, st>>>(D.pt.p, nP, D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellOf.p);
             lbdem::k_grid_scan<<<1, 1024, 0, st>>>(D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellFill.p);
-            lbdem::k_grid_fill<<<nb, 128, 0, st>>>(n, D.flag.p, D.cellCount.p, D.cellFill.p, D.cellOf.p, D.sorted.p);
-            lbdem::k_dem_neighbours_grid<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p, D.sorted.p, D.nbr.p, D.nNbr.p,
+            lbdem::k_grid_fill<<<pb, 128, 0, st>>>(nP, D.flag.p, D.cellCount.p, D.cellFill.p, D.cellOf.p, D.sorted.p);
+            lbdem::k_dem_neighbours_grid<<<pb, 128, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p, D.sorted.p, D.nbr.p, D.nNbr.p,
                                                              D.flag.p + 1);
             h->launches += 4;
         } else {
-            lbdem::k_dem_neighbours<<<nb, 128, 0, st>>>(D.e.p, n, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
+            lbdem::k_dem_neighbours<<<pb, 128, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
         }
-        lbdem::k_dem_predict<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, D.nWalls, D.flag.p);
-        lbdem::k_dem_forces_correct<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.walls.p, hydro, D.nbr.p, D.nNbr.p);
+        lbdem::k_dem_predict<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.pt.p, D.walls.p, D.nWalls, D.flag.p);
+        lbdem::k_dem_forces_correct<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.pt.p, D.walls.p, hydro, D.nbr.p, D.nNbr.p);
         h->launches += 4;
     }
-    lbdem::k_dem_export<<<nb, 128, 0, st>>>(D.e.p, n, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
-    k_prepare_particles<<<nb, 128, 0, st>>>(h->rawParts.p, n, h->rawElmts.p, n, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
+    lbdem::k_dem_export<<<nb, 128, 0, st>>>(D.e.p, n, D.pt.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
+    k_prepare_particles<<<(std::max(nP, n) + 127) / 128, 128, 0, st>>>(h->rawParts.p, nP, h->rawElmts.p, n, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
     h->launches += 2;
     CU(cudaGetLastError());
     return 0;
@@ -2485,8 +2486,20 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
     for (int k = 0; k < 5; ++k) P.c[k] = c[k];
     P.coeff1[0] = g1[0] * c[0]; P.coeff2[0] = g2[0] * c[1];
     for (int k = 1; k < 6; ++k) { P.coeff1[k] = g1[k] * c[0] / c[k - 1]; P.coeff2[k] = g2[k] * c[1] / c[k - 1]; }
+    // DEM::compositeProperties (DEM.cpp:404-433), unit = radius.  The triangle's "-1/2" is an integer division in the reference:
+    // its second and third sphere sit at y = 0 (kept: the reference's inertia and contacts are those of that shape)
+    memset(P.proto, 0, sizeof P.proto);
+    {
+        const double s2 = sqrt(2.0), s3 = sqrt(3.0), s6 = sqrt(6.0);
+        const double p2[2][3] = { { 0.5, 0.0, 0.0 }, { -0.5, 0.0, 0.0 } };
+        const double p3[3][3] = { { 0.0, 1.0, 0.0 }, { -s3 / 2, (double)(-1 / 2), 0.0 }, { s3 / 2, (double)(-1 / 2), 0.0 } };
+        const double p4[4][3] = { { 0.0, 0.0, 1.0 }, { 0.0, 2.0 * s2 / 3.0, -1.0 / 3.0 }, { 2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0 },
+                                  { -2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0 } };
+        memcpy(P.proto[2], p2, sizeof p2); memcpy(P.proto[3], p3, sizeof p3); memcpy(P.proto[4], p4, sizeof p4);
+    }
     std::vector<lbdem::Elmt> E(nElmts);
     memset(E.data(), 0, sizeof(lbdem::Elmt) * nElmts);
+    std::vector<lbdem::Part> PT;
     for (uint32_t k = 0; k < nElmts; ++k) {
         for (int q = 0; q < 3; ++q) {
             E[k].x[0][q] = E[k].xp[0][q] = elmts[k].x0[q];
@@ -2494,33 +2507,46 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
             E[k].w[0][q] = elmts[k].w0[q];
             E[k].I[q] = elmts[k].I[q];
         }
-        E[k].radius = elmts[k].radius; E[k].m = elmts[k].m; E[k].nearWall = -1;
+        E[k].q[0][0] = E[k].qp[0][0] = 1.0;  // elmt::q0 = (1, 0, 0, 0), q1 = 0 (the particle file of a fresh run)
+        E[k].radius = elmts[k].radius; E[k].m = elmts[k].m;
+        E[k].size = elmts[k].size > 0 ? elmts[k].size : 1;
+        E[k].pBegin = (int)PT.size();
+        if (E[k].size > 4) return fail(LBGPU_EINVAL, "lbGpuDemInit: element %u has %d spheres (DEM::compositeProperties knows 1-4)", k, E[k].size);
         if (!(E[k].radius > 0.0) || !(E[k].m > 0.0)) return fail(LBGPU_EINVAL, "lbGpuDemInit: element %u has no radius or mass", k);
+        for (int i = 0; i < E[k].size; ++i) {
+            lbdem::Part a;
+            memset(&a, 0, sizeof a);
+            a.cluster = (int)k; a.proto = i; a.nearWall = -1;
+            PT.push_back(a);
+        }
     }
-    CU(D.e.alloc(nElmts)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)nElmts * lbdem::MAX_NBR)); CU(D.nNbr.alloc(nElmts));
+    const uint32_t nP = (uint32_t)PT.size();
+    CU(D.e.alloc(nElmts)); CU(D.pt.alloc(nP)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)nP * lbdem::MAX_NBR)); CU(D.nNbr.alloc(nP));
     CU(D.flag.alloc(4)); CU(D.scal.alloc(2)); CU(D.hydro.alloc((size_t)7 * nElmts));
-    D.grid = nElmts >= 4096;  // below that the all-pairs pass (one launch) is as fast as the five launches of the grid
+    D.grid = nP >= 4096;  // below that the all-pairs pass (one launch) is as fast as the five launches of the grid
     if (const char* e = getenv("LBGPU_DEM_GRID")) D.grid = atoi(e) != 0;
     if (D.grid) {
         CU(D.gridDesc.alloc(1)); CU(D.cellCount.alloc(lbdem::GRID_MAX_CELLS + 2)); CU(D.cellFill.alloc(lbdem::GRID_MAX_CELLS + 2));
-        CU(D.cellOf.alloc(nElmts)); CU(D.sorted.alloc(nElmts));
+        CU(D.cellOf.alloc(nP)); CU(D.sorted.alloc(nP));
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(D.e.p, E.data(), sizeof(lbdem::Elmt) * nElmts, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(D.pt.p, PT.data(), sizeof(lbdem::Part) * nP, cudaMemcpyHostToDevice));
     if (nWalls) CU(cudaMemcpy(D.walls.p, walls, sizeof(lbdem::Wall) * nWalls, cudaMemcpyHostToDevice));
-    CU(cudaMemset(D.nNbr.p, 0, sizeof(uint32_t) * nElmts));
+    CU(cudaMemset(D.nNbr.p, 0, sizeof(uint32_t) * nP));
     CU(cudaMemset(D.flag.p, 0, sizeof(uint32_t) * 4));
     const double sc[2] = { prm->maxDisp, 0.0 };
     CU(cudaMemcpy(D.scal.p, sc, sizeof sc, cudaMemcpyHostToDevice));
     CU(cudaDeviceSynchronize());  // the copies ran on the legacy stream (see lbGpuSetCurves)
-    D.n = nElmts; D.nWalls = nWalls; D.on = true;
-    // the resident lists of the coupling step: one particle per element
-    if (int rc = particle_capacity(h, nElmts, nElmts, nElmts)) return rc;
-    h->nParts = h->nElmts = h->nComps = nElmts;
+    D.n = nElmts; D.nP = nP; D.nWalls = nWalls; D.on = true;
+    // the resident lists of the coupling step: the particles of every element
+    if (int rc = particle_capacity(h, nP, nElmts, nP)) return rc;
+    h->nParts = nP; h->nElmts = nElmts; h->nComps = nP;
     const uint32_t nb = (nElmts + 127) / 128;
-    lbdem::k_dem_export<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
-    k_prepare_particles<<<nb, 128, 0, h->stream>>>(h->rawParts.p, nElmts, h->rawElmts.p, nElmts, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
-    h->launches += 2;
+    lbdem::k_dem_init_particles<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, D.prm, D.pt.p);
+    lbdem::k_dem_export<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, D.pt.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
+    k_prepare_particles<<<(std::max(nP, nElmts) + 127) / 128, 128, 0, h->stream>>>(h->rawParts.p, nP, h->rawElmts.p, nElmts, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
+    h->launches += 3;
     CU(cudaGetLastError());
     return LBGPU_OK;
 }
@@ -2577,6 +2603,22 @@ int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double inf
             if (w0) w0[3 * k + q] = E[k].w[0][q];
         }
     if (info) { info[0] = sc[0]; info[1] = (double)f[2]; info[2] = (double)f[1]; }
+    return LBGPU_OK;
+}
+
+int lbGpuDemParticles(LbGpuHandle* h, uint32_t* nParticles, double* x0, double* radiusVec, uint32_t* clusterIndex) {
+    if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuDemParticles: no device-side DEM on this handle (lbGpuDemInit)");
+    CU(cudaSetDevice(h->device));
+    auto& D = h->dem;
+    if (nParticles) *nParticles = D.nP;
+    if (!x0 && !radiusVec && !clusterIndex) return LBGPU_OK;
+    std::vector<lbdem::Part> PT(D.nP);
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(PT.data(), D.pt.p, sizeof(lbdem::Part) * D.nP, cudaMemcpyDeviceToHost));
+    for (uint32_t a = 0; a < D.nP; ++a) {
+        for (int q = 0; q < 3; ++q) { if (x0) x0[3 * a + q] = PT[a].xc[q]; if (radiusVec) radiusVec[3 * a + q] = PT[a].rvc[q]; }
+        if (clusterIndex) clusterIndex[a] = (uint32_t)PT[a].cluster;
+    }
     return LBGPU_OK;
 }
 
@@ -3100,8 +3142,8 @@ int visit_state(LbGpuHandle* h, F&& fn) {
     if (h->nComps && (rc = fn((void*)h->comps.p, sizeof(uint32_t) * h->nComps))) return rc;
     if (h->dem.on) {  // the elements' Gear state and tables (the handle the blob is loaded into went through lbGpuDemInit)
         auto& D = h->dem;
-        if ((rc = fn((void*)D.e.p, sizeof(lbdem::Elmt) * D.n)) || (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) ||
-            (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.n)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
+        if ((rc = fn((void*)D.e.p, sizeof(lbdem::Elmt) * D.n)) || (rc = fn((void*)D.pt.p, sizeof(lbdem::Part) * D.nP)) ||
+            (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) || (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.nP)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
             (rc = fn((void*)D.scal.p, sizeof(double) * 2)))
             return rc;
     }

@@ -13,18 +13,30 @@ from . import lattice_init as li
 
 
 def covered(case: dict, params: dict) -> bool:
-    """True when the device-side DEM (lbGpuDem*) covers this case: spheres only, no periodic boundary (periodic DEM boundaries
-    mean ghost particles, DEM.cpp:1586-1660, which the device does not build), box geometry, an imposed number of sub-steps."""
-    return (all(int(e["size"]) == 1 for e in case.get("elements", [])) and len(case.get("elements", [])) > 0 and
+    """True when the device-side DEM (lbGpuDem*) covers this case: spheres and clusters of 2-4 spheres, no periodic boundary
+    (periodic DEM boundaries mean ghost particles, DEM.cpp:1586-1660, which the device does not build), box geometry, an imposed
+    number of sub-steps."""
+    return (all(1 <= int(e["size"]) <= 4 for e in case.get("elements", [])) and len(case.get("elements", [])) > 0 and
             all(b != 4 for b in params["boundary"]) and case.get("problemName", "NONE") == "NONE" and int(case.get("multiStep", 1)) > 0 and
             float(case.get("demInitialRepeat", 0.0)) == 0.0)
+
+
+def prototypes():
+    """DEM::compositeProperties (DEM.cpp:404-433): sphere i of an element of `size`, unit = radius.  The reference writes the
+    triangle's y = -1/2 with integers, i.e. 0: kept, the reference's inertia and contacts are those of that shape."""
+    s2, s3, s6 = math.sqrt(2), math.sqrt(3), math.sqrt(6)
+    return {1: [(0.0, 0.0, 0.0)],
+            2: [(0.5, 0.0, 0.0), (-0.5, 0.0, 0.0)],
+            3: [(0.0, 1.0, 0.0), (-s3 / 2, 0.0, 0.0), (s3 / 2, 0.0, 0.0)],
+            4: [(0.0, 0.0, 1.0), (0.0, 2.0 * s2 / 3.0, -1.0 / 3.0), (2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0),
+                (-2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0)]}
 
 
 def dem_from_case(case: dict, params: dict | None = None) -> dict:
     prm = params or li.params_from_case(case)
     if not covered(case, prm):
-        raise ValueError("dem_from_case: the device-side DEM covers single-sphere elements in a box without periodic boundaries "
-                         "and an imposed multiStep only")
+        raise ValueError("dem_from_case: the device-side DEM covers spheres / clusters of 2-4 spheres in a box without periodic "
+                         "boundaries and an imposed multiStep only")
     L, T, D = prm["unitLength"], prm["unitTime"], prm["unitDensity"]
     accel = L / T / T
     # material (DEM.cpp:13-62); the HERTZIAN case of the switch falls through into LINEAR's damping coefficient
@@ -44,12 +56,17 @@ def dem_from_case(case: dict, params: dict | None = None) -> dict:
     )
     density = float(case["density"])
     elmts = []
+    protos = prototypes()
     for e in case["elements"]:
-        r = float(e["radius"])
-        single = 4.0 / 3.0 * density * math.pi * r * r * r           # elmt::initialize (elmt.cpp:63-70); size = 1, no transport term
-        m = 1 * single
-        inertia = 1 * 2.0 / 5.0 * single * r * r * 1.0
-        elmts.append(dict(size=1, radius=r, m=m, I=[inertia, inertia, inertia], x0=[float(v) for v in e["x0"]],
+        r = float(e["radius"]); size = int(e["size"])
+        single = 4.0 / 3.0 * density * math.pi * r * r * r           # elmt::initialize (elmt.cpp:63-75)
+        m = size * single
+        inertia = [size * 2.0 / 5.0 * single * r * r * 1.0] * 3
+        for i in range(size):  # Huygens-Steiner: + singleMass r^2 prototype.transport()
+            px, py, pz = protos[size][i]
+            tr = (py * py + pz * pz, pz * pz + px * px, px * px + py * py)
+            inertia = [inertia[k] + single * r * r * tr[k] for k in range(3)]
+        elmts.append(dict(size=size, radius=r, m=m, I=inertia, x0=[float(v) for v in e["x0"]],
                           x1=[float(v) for v in e["x1"]], w0=[float(v) for v in e["w"]]))
     # neighbour-table range (DEM::initNeighborParameters, DEM.cpp:1270-1312)
     max_rad = max(e["radius"] for e in elmts)

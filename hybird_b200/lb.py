@@ -170,11 +170,11 @@ class LB:
         P.demF[:] = [float(v) for v in p["demF"]]
         E = np.zeros(len(dem["elmts"]), dtype=abi.DEM_ELEMENT_DTYPE)
         for k, e in enumerate(dem["elmts"]):
-            if int(e.get("size", 1)) != 1:
-                raise ValueError("demInit: the device-side DEM covers single-sphere elements only (element %d has size %d)" % (k, e["size"]))
+            if not 1 <= int(e.get("size", 1)) <= 4:
+                raise ValueError("demInit: elements are spheres or clusters of 2-4 spheres (element %d has size %d)" % (k, e["size"]))
             for f in ("x0", "x1", "w0", "I"):
                 E[k][f] = e[f]
-            E[k]["radius"] = e["radius"]; E[k]["m"] = e["m"]
+            E[k]["radius"] = e["radius"]; E[k]["m"] = e["m"]; E[k]["size"] = int(e.get("size", 1))
         W = np.zeros(len(dem["walls"]), dtype=abi.DEM_WALL_DTYPE)
         for k, w in enumerate(dem["walls"]):
             for f in ("n", "p", "vel", "omega", "rotCenter"):
@@ -182,7 +182,8 @@ class LB:
             W[k]["moving"] = int(w["moving"])
         abi.check(self.lib.lbGpuDemInit(self.h, C.byref(P), abi.ptr(E), len(E), abi.ptr(W) if len(W) else None, len(W)))
         self._dem_n = len(E)
-        self._last = (np.zeros(len(E), abi_particle_dtype()), np.zeros(len(E), abi_element_dtype()), np.arange(len(E), dtype=np.uint32))
+        nP = int(E["size"].sum())
+        self._last = (np.zeros(nP, abi_particle_dtype()), np.zeros(len(E), abi_element_dtype()), np.arange(nP, dtype=np.uint32))
         return self
 
     def demStep(self, hydro=None):
@@ -203,6 +204,14 @@ class LB:
         x0 = np.zeros((n, 3)); x1 = np.zeros((n, 3)); w0 = np.zeros((n, 3)); info = (C.c_double * 3)()
         abi.check(self.lib.lbGpuDemState(self.h, abi.ptr(x0), abi.ptr(x1), abi.ptr(w0), C.byref(info)))
         return dict(x0=x0, x1=x1, w0=w0, maxDisp=float(info[0]), rebuilds=int(info[1]), longest_list=int(info[2]))
+
+    def demParticles(self):
+        """The spheres of the elements (particle::updateCorrected): x0, radiusVec, clusterIndex."""
+        n = C.c_uint32()
+        abi.check(self.lib.lbGpuDemParticles(self.h, C.byref(n), None, None, None))
+        x0 = np.zeros((n.value, 3)); rv = np.zeros((n.value, 3)); ci = np.zeros(n.value, dtype=np.uint32)
+        abi.check(self.lib.lbGpuDemParticles(self.h, C.byref(n), abi.ptr(x0), abi.ptr(rv), abi.ptr(ci)))
+        return dict(x0=x0, radiusVec=rv, clusterIndex=ci)
 
     def demContacts(self):
         """elmt::FParticle, FWall, MParticle, MWall of the last DEM sub-step."""

@@ -326,7 +326,7 @@ void DEM::discreteElementStep(IO& io) {
                 o.x0[0] = el.x0.x; o.x0[1] = el.x0.y; o.x0[2] = el.x0.z;
                 o.x1[0] = el.x1.x; o.x1[1] = el.x1.y; o.x1[2] = el.x1.z;
                 o.w0[0] = el.w0.x; o.w0[1] = el.w0.y; o.w0[2] = el.w0.z;
-                o.radius = el.radius; o.m = el.m; o.I[0] = el.I.x; o.I[1] = el.I.y; o.I[2] = el.I.z;
+                o.radius = el.radius; o.m = el.m; o.I[0] = el.I.x; o.I[1] = el.I.y; o.I[2] = el.I.z; o.size = 1; o.pad = 0;
             }
             std::vector<LbGpuDemWall> W(walls.size());
             for (size_t k = 0; k < walls.size(); ++k) {

@@ -161,8 +161,8 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
  * 5th-order Gear predictor / corrector (elmt.cpp:139-254), LINEAR / HERTZIAN particle-particle and particle-wall contacts
  * (DEM.cpp:1668-1717, 1801-1982, 2138-2224), Newton's equations with the hydrodynamic force and torque of the last LB step
  * (DEM.cpp:1150-1181).  The particle / element lists of the coupling step and of LB::computeHydroForces are refreshed on
- * the device, so a coupled cycle has no host round trip.  Not covered: clusters (size > 1), periodic DEM boundaries
- * (ghost particles), cylinders, objects -- those keep the host DEM and lbGpuStep.  All values in physical units, as the
+ * the device, so a coupled cycle has no host round trip.  Elements are single spheres or clusters of 2-4 spheres.  Not
+ * covered: periodic DEM boundaries (ghost particles), cylinders, objects -- those keep the host DEM and lbGpuStep.  All values in physical units, as the
  * reference's DEM holds them.  With a communicator every rank advances the same (replicated) elements.
  *   contactModel  0 LINEAR, 1 HERTZIAN (material::contactModel, DEM.cpp:150-158)
  *   deltat, multiStep, nebrRange, maxDisp: DEM::deltat / multiStep / nebrRange / maxDisp after DEM::discreteElementInit */
@@ -171,7 +171,10 @@ typedef struct {
     double knConst, ksConst, dampCoeff, viscTang, linearStiff, frictionCoefPart, frictionCoefWall, numVisc;
     double demF[3], deltat, nebrRange, maxDisp;
 } LbGpuDemParams;
-typedef struct { double x0[3], x1[3], w0[3], radius, m, I[3]; } LbGpuDemElement;   /* elmt::x0, x1, w0, radius, m, I (elmt.h:60-110) */
+typedef struct { double x0[3], x1[3], w0[3], radius, m, I[3]; int32_t size, pad; } LbGpuDemElement;
+/* elmt::x0, x1, w0, radius, m, I, size (elmt.h:60-110).  size 1: a sphere; 2-4: the reference's clusters (DEM::compositeProperties,
+ * DEM.cpp:404-433) with their orientation quaternion (q0 = identity, q1 = 0 as in the particle file of a fresh run); I is the
+ * inertia elmt::initialize computed (principal axes, transport terms included); 0 is read as 1. */
 typedef struct { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int32_t moving, pad; } LbGpuDemWall; /* wall.h */
 int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* params, const LbGpuDemElement* elmts, uint32_t nElmts,
                  const LbGpuDemWall* walls, uint32_t nWalls);
@@ -187,6 +190,9 @@ int lbGpuDemState(LbGpuHandle* h, double* x0, double* x1, double* w0, double inf
 /* elmt::FParticle, FWall, MParticle, MWall of the last sub-step (3*nElmts each; any may be NULL): what IO::exportForces and
  * the particle files print (IO.cpp:930-938).  Synchronises. */
 int lbGpuDemContacts(LbGpuHandle* h, double* FParticle, double* FWall, double* MParticle, double* MWall);
+/* the particles (spheres) of the elements as particle::updateCorrected left them: *nParticles = their number; x0, radiusVec
+ * (3 per particle) and clusterIndex may be NULL.  Synchronises. */
+int lbGpuDemParticles(LbGpuHandle* h, uint32_t* nParticles, double* x0, double* radiusVec, uint32_t* clusterIndex);
 
 /* Results of the last step in physical units; any pointer may be NULL. Synchronises. */
 int lbGpuParticleForces(LbGpuHandle* h, double* FHydro /*3*nElmts*/, double* MHydro /*3*nElmts*/,

@@ -8,6 +8,7 @@ import pytest
 import golden_util as gu
 
 DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
+CLUSTER_CASES = ("cluster_dem", "clusters_hit")
 
 
 @pytest.mark.parametrize("name", DEM_CASES)
@@ -31,7 +32,7 @@ def test_dem_port_follows_reference_trace(name):
         assert P.rebuilds >= 4  # the table is rebuilt several times and pairs enter / leave it
 
 
-@pytest.mark.parametrize("name", DEM_CASES)
+@pytest.mark.parametrize("name", DEM_CASES + CLUSTER_CASES)
 def test_host_mirror_of_the_dem_initialisation(name):
     """hybird_b200.dem_init restates what DEM::discreteElementGet / discreteElementInit derive (material constants, sub-step,
     neighbour-table range, masses, inertias, walls): number by number what the unmodified reference held after its init."""
@@ -55,19 +56,19 @@ def test_host_mirror_of_the_dem_initialisation(name):
 def test_dem_init_refuses_what_the_device_does_not_cover():
     import cases
     from hybird_b200 import dem_init
-    for name in ("cluster_dem", "two_spheres_kin"):  # clusters; periodic boundaries (ghost particles)
+    for name in ("two_spheres_kin", "spheres_pbc_dem"):  # periodic boundaries (ghost particles)
         with pytest.raises(ValueError):
             dem_init.dem_from_case(cases.catalogue()[name])
 
 
-def test_lb_mirror_refuses_clusters_and_periodic_dem_before_touching_the_device():
+def test_lb_mirror_refuses_unknown_shapes_and_periodic_dem_before_touching_the_device():
     """LB.demInit checks what the device-side DEM covers on the host side (no CUDA call is made for a refused set-up)."""
     from hybird_b200 import LB
     g = gu.Golden("cluster_dem")
     lb = LB(dict(g.params))
     dem = gu.Golden("spheres_dem").dem()
-    dem["elmts"][0]["size"] = 2
-    with pytest.raises(ValueError, match="single-sphere"):
+    dem["elmts"][0]["size"] = 5  # DEM::compositeProperties knows elements of one to four spheres
+    with pytest.raises(ValueError, match="clusters of 2-4"):
         lb.demInit(dem)
     dem = gu.Golden("spheres_pbc_dem").dem()
     assert len(dem["pbcs"]) == 2

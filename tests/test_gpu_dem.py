@@ -11,7 +11,7 @@ import pytest
 import golden_util as gu
 
 pytestmark = pytest.mark.gpu
-DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
+DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini", "cluster_dem", "clusters_hit")  # the last two: elements of 2-4 spheres
 TOL_DEM = 1e-12
 TOL_COUPLED = 1e-9
 
@@ -23,12 +23,21 @@ def _gpu(g):
     return lb.demInit(g.dem())
 
 
+def _worst(lb, parts, elmts):
+    """Largest deviation of the device's particles / elements from the reference's recorded ones."""
+    st, pt = lb.demState(), lb.demParticles()
+    assert len(pt["x0"]) == len(parts) and np.array_equal(pt["clusterIndex"], parts["clusterIndex"])
+    return max(np.abs(pt["x0"] - parts["x0"]).max(), np.abs(pt["radiusVec"] - parts["radiusVec"]).max(),
+               np.abs(st["x1"] - elmts["x1"]).max(), np.abs(st["w0"] - elmts["wGlobal"]).max())
+
+
 @pytest.mark.parametrize("name", DEM_CASES)
 def test_device_dem_follows_reference_trace(name):
     import dem_port
     g = gu.Golden(name)
     lb = _gpu(g)
-    P = dem_port.DemPort(g.dem())
+    clusters = any(e["size"] > 1 for e in g.dem()["elmts"])
+    P = (dem_port.DemPortClusters if clusters else dem_port.DemPort)(g.dem())
     n = len(g.dem()["elmts"])
     hydro = np.zeros((n, 7))
     worst = worst_port = 0.0
@@ -36,9 +45,10 @@ def test_device_dem_follows_reference_trace(name):
         parts, elmts, comps, flag = g.trace[s]
         lb.demStep(hydro)
         st = lb.demState()
-        px0, px1, pw = P.step(hydro[:, 0:3], hydro[:, 3:6])
-        worst = max(worst, np.abs(st["x0"] - parts["x0"]).max(), np.abs(st["x1"] - elmts["x1"]).max(), np.abs(st["w0"] - elmts["wGlobal"]).max())
-        worst_port = max(worst_port, np.abs(st["x0"] - px0).max(), np.abs(st["x1"] - px1).max(), np.abs(st["w0"] - pw).max())
+        out = P.step(hydro[:, 0:3], hydro[:, 3:6])
+        worst = max(worst, _worst(lb, parts, elmts))
+        px1, pw = (out[2], out[3]) if clusters else (out[1], out[2])
+        worst_port = max(worst_port, np.abs(st["x1"] - px1).max(), np.abs(st["w0"] - pw).max())
         hydro[:, 0:3], hydro[:, 3:6] = g.forces[s][0], g.forces[s][1]
     assert st["rebuilds"] == P.rebuilds
     assert worst <= TOL_DEM and worst_port <= TOL_DEM, (worst, worst_port)
@@ -53,8 +63,7 @@ def test_coupled_cycle_on_device_matches_reference(name):
     for s in range(1, g.steps + 1):
         parts, elmts, comps, flag = g.trace[s - 1]
         lb.runDem(1)
-        st = lb.demState()
-        worst_x = max(worst_x, np.abs(st["x0"] - parts["x0"]).max(), np.abs(st["x1"] - elmts["x1"]).max(), np.abs(st["w0"] - elmts["wGlobal"]).max())
+        worst_x = max(worst_x, _worst(lb, parts, elmts))
         t = lb.fetch(("type_flags",))["type_flags"]
         assert np.array_equal(t & 0x1F, g.types[s]), "type / particle-flag map differs from the reference after step %d" % s
         F, M, V, W = lb.forces()
