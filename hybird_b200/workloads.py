@@ -149,14 +149,15 @@ def catalogue():
                   dict(size=3, radius=2.2, x0=[22.5, 14.0, 18.6], x1=[-0.09, 0.0, 0.0], w=[0.0, 0.01, 0.0]),
                   dict(size=4, radius=2.0, x0=[16.0, 13.0, 6.3], x1=[0.0, 0.01, -0.08], w=[0.01, 0.0, 0.0])],
         motion="dem")
-    # periodic DEM boundaries: x and y periodic (two pbcs, so ghost particles in the corners too), walls in z; the reference's
-    # DEM in the loop, the LB side sees five ghost particles and a full rescan at every rebuild of the neighbour table
+    # periodic DEM boundaries: x and y periodic (two pbcs, so ghost particles in the corners too), walls in z.  Spheres 0 and 1
+    # collide ACROSS the x face (a contact between a particle and a ghost), sphere 2 leaves through the x and the y face and
+    # re-enters on the other side (DEM::pbcShift), the ghost count changes from rebuild to rebuild, the LB side rescans
     C["spheres_pbc_dem"] = make_case(
         "spheres_pbc_dem", lbSizeX=30, lbSizeY=26, lbSizeZ=30, boundary0=4, boundary1=4, boundary2=4, boundary3=4, lbFZ=-3e-5,
-        initVisc=0.06, multiStep=2, density=6.0,
-        elements=[dict(size=1, radius=3.0, x0=[4.6, 12.0, 15.0], x1=[-0.11, 0.0, 0.0], w=[0.0, 0.0, 0.01]),
-                  dict(size=1, radius=3.2, x0=[24.0, 12.8, 15.6], x1=[0.09, 0.0, 0.0], w=[0.0, 0.02, 0.0]),
-                  dict(size=1, radius=2.6, x0=[3.4, 3.2, 21.0], x1=[-0.03, -0.04, 0.0], w=[0.01, 0.0, 0.0]),
+        initVisc=0.04, multiStep=2, density=8.0,
+        elements=[dict(size=1, radius=3.0, x0=[4.6, 12.0, 15.0], x1=[-0.12, 0.0, 0.0], w=[0.0, 0.0, 0.01]),
+                  dict(size=1, radius=3.2, x0=[24.0, 12.8, 15.6], x1=[0.096, 0.0, 0.0], w=[0.0, 0.02, 0.0]),
+                  dict(size=1, radius=2.6, x0=[3.4, 3.2, 21.0], x1=[-0.06, -0.072, 0.0], w=[0.01, 0.0, 0.0]),
                   dict(size=1, radius=3.0, x0=[15.0, 13.0, 5.0], x1=[0.02, 0.05, -0.06], w=[0.0, 0.0, 0.0])],
         motion="dem")
     # a loose bed: twelve heavy spheres with random velocities in a box wider than nebrRange -- several rebuilds of the

@@ -467,3 +467,189 @@ class DemPortClusters(DemPort):
         for _ in range(self.p["multiStep"]):
             self.substep()
         return self.px0.copy(), self.prv.copy(), self.x[1].copy(), self.wGlobal.copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Periodic DEM boundaries (single spheres): at every rebuild of the neighbour table the elements that left the domain are
+# shifted back (DEM::pbcShift, DEM.cpp:1554-1584), particles within nebrRange of a periodic plane get a ghost on the other
+# side, particles with two ghosts one more in the corner (DEM::createGhosts, DEM.cpp:1586-1660), and the table is built over
+# particles and ghosts; between rebuilds a ghost follows its origin (particle::ghostUpdate, elmt.cpp:292-299).  A contact
+# acts on the standard particles of the pair only (DEM.cpp:1849, 1856, 1885, 1889).  dem.newNeighborList tells the LB side
+# to rescan after every rebuild (DEM.cpp:1414).
+# ---------------------------------------------------------------------------------------------------------------------
+class DemPortPbc(DemPort):
+    def __init__(self, dem):
+        super().__init__(dem)
+        self.pbcs = []
+        for b in dem["pbcs"]:
+            p, v = np.array(b["p"], dtype=float), np.array(b["v"], dtype=float)
+            n1 = v / math.sqrt(_norm2(v))
+            self.pbcs.append(dict(v=v, p1=p, n1=n1, p2=p + v, n2=-1.0 * n1))
+        self.ghosts = []       # (origin element, shift vector) in creation order
+        self.allpairs = []     # (a, b) particle indices, a < b, over particles + ghosts
+        self.new_list = False
+
+    def particle_x(self, a, pred):
+        src = self.xp[0] if pred else self.x[0]
+        if a < self.n:
+            return src[a]
+        o, sh = self.ghosts[a - self.n]
+        return src[o] + sh
+
+    def origin(self, a):
+        return a if a < self.n else self.ghosts[a - self.n][0]
+
+    def lists(self):
+        """(x0 of every particle, clusterIndex, components per element) as the LB side receives them."""
+        P = self.n + len(self.ghosts)
+        x0 = np.array([self.particle_x(a, False) for a in range(P)])
+        comps = [[k] + [self.n + g for g, (o, _) in enumerate(self.ghosts) if o == k] for k in range(self.n)]
+        return x0, np.array([self.origin(a) for a in range(P)]), comps
+
+    def substep(self):
+        p, n, c = self.p, self.n, self.c
+        x, xp, w, wp = self.x, self.xp, self.w, self.wp
+        maxVel = 0.0
+        for k in range(n):
+            maxVel = max(maxVel, _norm2(x[1][k]))
+        self.maxDisp += math.sqrt(maxVel) * p["deltat"]
+        if self.maxDisp > 0.25 * self.nebrRange:
+            self.maxDisp = 0.0
+            self.rebuilds += 1
+            self.new_list = True
+            for b in self.pbcs:  # pbcShift
+                for k in range(n):
+                    left = float(np.dot(b["n1"], x[0][k] - b["p1"]))
+                    right = float(np.dot(b["n2"], x[0][k] - b["p2"]))
+                    if left < 0.0:
+                        x[0][k] = x[0][k] + b["v"]; xp[0][k] = xp[0][k] + b["v"]
+                    if right < 0.0:
+                        x[0][k] = x[0][k] + (-1.0 * b["v"]); xp[0][k] = xp[0][k] + (-1.0 * b["v"])
+            self.ghosts = []
+            for b in self.pbcs:  # createGhosts
+                for k in range(n):
+                    left = float(np.dot(b["n1"], x[0][k] - b["p1"]))
+                    right = float(np.dot(b["n2"], x[0][k] - b["p2"]))
+                    if left < self.nebrRange:
+                        self.ghosts.append((k, b["v"]))
+                    elif right < self.nebrRange:
+                        self.ghosts.append((k, -1.0 * b["v"]))
+            corner = []
+            for g1 in range(len(self.ghosts)):
+                for g2 in range(g1 + 1, len(self.ghosts)):
+                    if self.ghosts[g1][0] == self.ghosts[g2][0]:
+                        corner.append((self.ghosts[g1][0], self.ghosts[g1][1] + self.ghosts[g2][1]))
+            self.ghosts += corner
+            P = n + len(self.ghosts)
+            r2 = self.nebrRange * self.nebrRange
+            self.allpairs = [(a, b) for a in range(P) for b in range(a + 1, P) if self.origin(a) != self.origin(b) and
+                             _norm2(self.particle_x(b, False) - self.particle_x(a, False)) < r2]
+            for k in range(n):
+                self.nearWall[k] = -1
+                for wi, wl in enumerate(self.walls):
+                    if float(np.dot(np.array(wl["n"]), x[0][k] - np.array(wl["p"]))) < self.nebrRange:
+                        self.nearWall[k] = wi
+                        break
+        xp[0] = x[0] + x[1] * c[0] + x[2] * c[1] + x[3] * c[2] + x[4] * c[3] + x[5] * c[4]
+        xp[1] = x[1] + x[2] * c[0] + x[3] * c[1] + x[4] * c[2] + x[5] * c[3]
+        xp[2] = x[2] + x[3] * c[0] + x[4] * c[1] + x[5] * c[2]
+        xp[3] = x[3] + x[4] * c[0] + x[5] * c[1]
+        xp[4] = x[4] + x[5] * c[0]
+        xp[5] = x[5].copy()
+        wp[0] = w[0] + w[1] * c[0] + w[2] * c[1] + w[3] * c[2] + w[4] * c[3] + w[5] * c[4]
+        wp[1] = w[1] + w[2] * c[0] + w[3] * c[1] + w[4] * c[2] + w[5] * c[3]
+        wp[2] = w[2] + w[3] * c[0] + w[4] * c[1] + w[5] * c[2]
+        wp[3] = w[3] + w[4] * c[0] + w[5] * c[1]
+        wp[4] = w[4] + w[5] * c[0]
+        wp[5] = w[5].copy()
+        FP, FW, MP, MW = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+        for a, b in self.allpairs:
+            if a >= n and b >= n:
+                continue  # two ghosts: nobody to push
+            i, j = self.origin(a), self.origin(b)
+            d = self.particle_x(b, True) - self.particle_x(a, True)
+            sig = self.radius[i] + self.radius[j]
+            if not (_norm2(d) < sig * sig):
+                continue
+            dist = math.sqrt(_norm2(d))
+            overlap = self.radius[i] + self.radius[j] - dist
+            relVel = xp[1][j] - xp[1][i]
+            en = d / dist
+            vn = float(np.dot(relVel, en))
+            normalRelVel = en * vn
+            effMass = self.m[i] * self.m[j] / (self.m[i] + self.m[j])
+            effRad = self.radius[i] * self.radius[j] / (self.radius[i] + self.radius[j])
+            fn = self.normal(overlap, vn, effRad, effMass)
+            nf = en * fn
+            vecRadI, vecRadJ = self.radius[i] * en, -self.radius[j] * en
+            if a < n:
+                FP[i] = FP[i] - nf
+            if b < n:
+                FP[j] = FP[j] + nf
+            relC = relVel - _cross(wp[0][i], vecRadI) + _cross(wp[0][j], vecRadJ)
+            tang = relC - normalRelVel
+            nt = math.sqrt(_norm2(tang))
+            if nt != 0.0:
+                ft = self.tangential(nt, fn, effRad, effMass, p["frictionCoefPart"])
+                et = tang / nt
+                tf = ft * et
+                if a < n:
+                    MP[i] = MP[i] + _cross(vecRadI, tf); FP[i] = FP[i] + tf
+                if b < n:
+                    MP[j] = MP[j] - _cross(vecRadJ, tf); FP[j] = FP[j] - tf
+        for k in range(n):
+            wi = self.nearWall[k]
+            if wi < 0:
+                continue
+            wl = self.walls[wi]
+            en = np.array(wl["n"])
+            dist = float(np.dot(en, xp[0][k] - np.array(wl["p"])))
+            overlap = self.radius[k] - dist
+            if overlap > 0.0:
+                cpv = np.zeros(3)
+                if wl["moving"]:
+                    dc = xp[0][k] - np.array(wl["rotCenter"])
+                    cpv = np.array(wl["vel"]) + _cross(np.array(wl["omega"]), dc - float(np.dot(dc, en)) * en)
+                relVel = xp[1][k] - cpv
+                vn = float(np.dot(relVel, en))
+                normalRelVel = en * vn
+                fn = self.normal(2.0 * overlap, vn, self.radius[k], self.m[k])
+                nf = en * fn
+                vecRadJ = -self.radius[k] * en
+                FW[k] = FW[k] + nf
+                relC = relVel + _cross(wp[0][k], vecRadJ)
+                tang = relC - normalRelVel
+                nt = math.sqrt(_norm2(tang))
+                if nt != 0.0:
+                    ft = self.tangential(nt, fn, self.radius[k], self.m[k], p["frictionCoefWall"])
+                    et = tang / math.sqrt(_norm2(tang))
+                    tf = ft * et
+                    MW[k] = MW[k] - _cross(vecRadJ, tf)
+                    FW[k] = FW[k] - tf
+        demF = np.array(p["demF"])
+        for k in range(n):
+            FVisc = -6.0 * math.pi * p["numVisc"] * self.radius[k] * xp[1][k]
+            MVisc = -8.0 * math.pi * p["numVisc"] * self.radius[k] * self.radius[k] * self.radius[k] * wp[0][k]
+            x[2][k] = (FVisc + self.FHydro[k] + FP[k] + FW[k]) / self.m[k] + demF
+            mom = MVisc + self.MHydro[k] + MP[k] + MW[k]
+            I, wl_ = self.I[k], wp[0][k]
+            w[1][k] = np.array([(mom[0] + (I[1] - I[2]) * wl_[1] * wl_[2]) / I[0], (mom[1] + (I[2] - I[0]) * wl_[2] * wl_[0]) / I[1],
+                                (mom[2] + (I[0] - I[1]) * wl_[0] * wl_[1]) / I[2]])
+        c2, c1 = self.coeff2, self.coeff1
+        x2c = x[2] - xp[2]
+        x[0] = xp[0] + x2c * c2[0]; x[1] = xp[1] + x2c * c2[1]
+        x[3] = xp[3] + x2c * c2[3]; x[4] = xp[4] + x2c * c2[4]; x[5] = xp[5] + x2c * c2[5]
+        for k in range(6):
+            xp[k] = x[k].copy()
+        w1c = w[1] - wp[1]
+        w[0] = wp[0] + w1c * c1[0]
+        w[2] = wp[2] + w1c * c1[2]; w[3] = wp[3] + w1c * c1[3]; w[4] = wp[4] + w1c * c1[4]; w[5] = wp[5] + w1c * c1[5]
+        for k in range(6):
+            wp[k] = w[k].copy()
+
+    def step(self, FHydro, MHydro):
+        self.new_list = False
+        self.FHydro = np.asarray(FHydro, dtype=float).reshape(-1, 3); self.MHydro = np.asarray(MHydro, dtype=float).reshape(-1, 3)
+        for _ in range(self.p["multiStep"]):
+            self.substep()
+        return self.lists() + (self.x[1].copy(), self.w[0].copy(), self.new_list)

@@ -95,3 +95,26 @@ def test_cluster_port_follows_reference_trace(name):
                     np.abs(wg - elmts["wGlobal"]).max())
         F, M = g.forces[s][0], g.forces[s][1]
     assert worst <= 1e-12, worst
+
+
+def test_periodic_port_follows_reference_trace():
+    """Periodic DEM boundaries (pbcShift, ghost particles incl. the corner ghost, table over particles and ghosts, contacts
+    across a periodic face): the particle list the LB side receives -- positions of particles and ghosts, their elements, the
+    elements' component lists, the rescan flag -- against the reference's recording, every LB step."""
+    import dem_port
+    g = gu.Golden("spheres_pbc_dem")
+    dem = g.dem()
+    P = dem_port.DemPortPbc(dem)
+    n = len(dem["elmts"])
+    F = np.zeros((n, 3)); M = np.zeros((n, 3))
+    worst = 0.0
+    counts = set()
+    for s in range(g.steps):
+        parts, elmts, comps, flag = g.trace[s]
+        x0, ci, cl, x1, wg, new_list = P.step(F, M)
+        assert len(x0) == len(parts) and np.array_equal(ci, parts["clusterIndex"])
+        assert list(comps) == [p for c in cl for p in c] and bool(flag) == new_list
+        worst = max(worst, np.abs(x0 - parts["x0"]).max(), np.abs(x1 - elmts["x1"]).max(), np.abs(wg - elmts["wGlobal"]).max())
+        counts.add(len(parts))
+        F, M = g.forces[s][0], g.forces[s][1]
+    assert worst <= 1e-12 and P.rebuilds >= 4 and len(counts) >= 2, (worst, P.rebuilds, counts)
