@@ -34,7 +34,8 @@ class LbGpuDemParams(C.Structure):
     _fields_ = [("contactModel", C.c_int32), ("multiStep", C.c_int32), ("knConst", C.c_double), ("ksConst", C.c_double),
                 ("dampCoeff", C.c_double), ("viscTang", C.c_double), ("linearStiff", C.c_double), ("frictionCoefPart", C.c_double),
                 ("frictionCoefWall", C.c_double), ("numVisc", C.c_double), ("demF", C.c_double * 3), ("deltat", C.c_double),
-                ("nebrRange", C.c_double), ("maxDisp", C.c_double)]
+                ("nebrRange", C.c_double), ("maxDisp", C.c_double), ("nPbc", C.c_int32), ("pad", C.c_int32),
+                ("pbcP", (C.c_double * 3) * 3), ("pbcV", (C.c_double * 3) * 3)]
 
 
 DEM_ELEMENT_DTYPE = np.dtype([("x0", "<f8", 3), ("x1", "<f8", 3), ("w0", "<f8", 3), ("radius", "<f8"), ("m", "<f8"), ("I", "<f8", 3),

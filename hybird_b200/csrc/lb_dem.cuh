@@ -21,7 +21,7 @@
 // linked cells (DEM.cpp:1326-1375) whose width is at least nebrRange wherever the domain is wider than six radii, so its
 // table IS the set of pairs within nebrRange at rebuild time; here a rebuild compares all pairs through shared-memory
 // tiles (small beds) or bins the particles into a uniform grid (k_grid_*, large beds) and the sub-steps in between only walk
-// the partner lists.  No periodic boundaries (ghost particles), cylinders, objects.
+// the partner lists.  Periodic boundaries (ghost particles) for single spheres (k_dem_pbc).  No cylinders, objects.
 // Compiled with -fmad=false like the LB kernels: the reference's operation order is kept.
 #pragma once
 #include <stdint.h>
@@ -34,6 +34,10 @@ struct Params {
     double demF[3], deltat, nebrRange;
     double c[5], coeff1[6], coeff2[6];  // DEM::predictor / DEM::corrector constants (DEM.cpp:1067-1112), computed on the host
     double proto[5][4][3];              // DEM::compositeProperties (DEM.cpp:404-433): sphere i of an element of `size`, unit = radius
+    // periodic DEM boundaries (DEM::initializePbcs, DEM.cpp:937-988; pbc::setPlanes, utils.cpp:240-245): plane 1 through p with
+    // normal v / |v|, plane 2 through p + v with the opposite normal
+    int nPbc, padPbc;
+    double pbcP[3][3], pbcV[3][3], pbcN[3][3];
 };
 struct Wall { double n[3], p[3], vel[3], omega[3], rotCenter[3]; int moving, pad; };
 struct Elmt {
@@ -46,6 +50,7 @@ struct Elmt {
 // one sphere of an element: corrected (c) and predicted (p) centre, lever arm (radiusVec) and velocity
 struct Part {
     double xc[3], rvc[3], xp[3], rvp[3], vp[3];
+    double shift[3];  // a ghost particle (periodic boundaries): its origin's centre + shift; zero for a standard particle
     int cluster, proto, nearWall, pad;
 };
 struct V3 { double x, y, z; };
@@ -105,9 +110,13 @@ __global__ void __launch_bounds__(1024) k_dem_trigger(const Elmt* __restrict__ e
 // partner lists of the PARTICLES: nbr[a * MAX_NBR + q], q < nNbr[a], ascending particle indices of other elements.
 // status[0] = largest list length seen (> MAX_NBR: error)
 constexpr int MAX_NBR = 48;
+// nPdev (may be null): the number of particles when it lives on the device (standard particles + the ghosts of this rebuild)
 __global__ void __launch_bounds__(128) k_dem_neighbours(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
-                                                        uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr, uint32_t* __restrict__ status) {
+                                                        uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr, uint32_t* __restrict__ status,
+                                                        const uint32_t* __restrict__ nPdev) {
     if (!*flag) return;
+    if (nPdev) nP = *nPdev;
+    if (blockIdx.x * blockDim.x >= nP) return;
     __shared__ double sx[128], sy[128], sz[128];
     __shared__ int sc[128];
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -148,8 +157,9 @@ struct Grid { double org[3], inv[3]; uint32_t dim[3], nCells; };
 constexpr uint32_t GRID_MAX_CELLS = 1u << 21;
 
 __global__ void __launch_bounds__(1024) k_grid_bounds(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
-                                                      Grid* __restrict__ g, uint32_t* __restrict__ cellCount) {
+                                                      Grid* __restrict__ g, uint32_t* __restrict__ cellCount, const uint32_t* __restrict__ nPdev) {
     if (!*flag) return;
+    if (nPdev) nP = *nPdev;
     __shared__ double smin[3][32], smax[3][32];
     double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
     for (uint32_t k = threadIdx.x; k < nP; k += blockDim.x)
@@ -184,8 +194,9 @@ __device__ __forceinline__ uint32_t grid_cell(const Grid& g, const double* x, in
     return (uint32_t)*cx + g.dim[0] * ((uint32_t)*cy + g.dim[1] * (uint32_t)*cz);
 }
 __global__ void __launch_bounds__(128) k_grid_count(const Part* __restrict__ pt, uint32_t nP, const uint32_t* __restrict__ flag, const Grid* __restrict__ g,
-                                                    uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellOf) {
+                                                    uint32_t* __restrict__ cellCount, uint32_t* __restrict__ cellOf, const uint32_t* __restrict__ nPdev) {
     if (!*flag) return;
+    if (nPdev) nP = *nPdev;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nP) return;
     int cx, cy, cz;
@@ -216,8 +227,10 @@ __global__ void __launch_bounds__(1024) k_grid_scan(const uint32_t* __restrict__
     if (threadIdx.x == 1023) cellCount[nC] = sa[1023];
 }
 __global__ void __launch_bounds__(128) k_grid_fill(uint32_t nP, const uint32_t* __restrict__ flag, const uint32_t* __restrict__ cellStart,
-                                                   uint32_t* __restrict__ cellFill, const uint32_t* __restrict__ cellOf, uint32_t* __restrict__ sorted) {
+                                                   uint32_t* __restrict__ cellFill, const uint32_t* __restrict__ cellOf, uint32_t* __restrict__ sorted,
+                                                   const uint32_t* __restrict__ nPdev) {
     if (!*flag) return;
+    if (nPdev) nP = *nPdev;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nP) return;
     const uint32_t c = cellOf[k];
@@ -226,8 +239,9 @@ __global__ void __launch_bounds__(128) k_grid_fill(uint32_t nP, const uint32_t* 
 __global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Part* __restrict__ pt, uint32_t nP, double nebrRange, const uint32_t* __restrict__ flag,
                                                              const Grid* __restrict__ gp, const uint32_t* __restrict__ cellStart,
                                                              const uint32_t* __restrict__ sorted, uint32_t* __restrict__ nbr, uint32_t* __restrict__ nNbr,
-                                                             uint32_t* __restrict__ status) {
+                                                             uint32_t* __restrict__ status, const uint32_t* __restrict__ nPdev) {
     if (!*flag) return;
+    if (nPdev) nP = *nPdev;
     const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= nP) return;
     const Grid g = *gp;
@@ -271,6 +285,119 @@ __global__ void __launch_bounds__(128) k_dem_neighbours_grid(const Part* __restr
     if (cnt > (uint32_t)MAX_NBR) atomicMax(status, cnt);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Periodic DEM boundaries (single spheres).  When the tables are rebuilt: DEM::pbcShift (DEM.cpp:1554-1584) brings back the
+// elements that left the domain, DEM::createGhosts (DEM.cpp:1586-1660) gives every particle within nebrRange of a periodic
+// plane a ghost on the other side and every particle with two ghosts one more in the corner.  Ghosts are further entries of
+// the particle array (index nStd + g, g in the reference's creation order: per boundary, per element; then the corner
+// ghosts in the order of their first parent), so the tables, the contacts (which act on the standard particle of a pair only,
+// DEM.cpp:1849-1890) and the lists of the LB side see them as the reference's do.  One block.
+// out: cnt[0] = particles + ghosts, cnt[1] |= 1 (a rebuild happened in this cycle: dem.newNeighborList, DEM.cpp:1414);
+// comps[7 k ..] = element k's particle and its ghosts in creation order, nComp[k] their number.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t* __restrict__ a, uint32_t len, uint32_t* __restrict__ sm) {
+    // exclusive scan of a[0 .. len) in place by the whole block (1024 threads); returns the total
+    const uint32_t per = (len + blockDim.x - 1) / blockDim.x, b0 = threadIdx.x * per, b1 = min(len, b0 + per);
+    uint32_t s = 0;
+    for (uint32_t k = b0; k < b1; ++k) s += a[k];
+    sm[threadIdx.x] = s;
+    __syncthreads();
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {
+        uint32_t v = 0;
+        if (threadIdx.x >= o) v = sm[threadIdx.x - o];
+        __syncthreads();
+        sm[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = sm[threadIdx.x] - s;
+    for (uint32_t k = b0; k < b1; ++k) { const uint32_t v = a[k]; a[k] = run; run += v; }
+    const uint32_t total = sm[blockDim.x - 1];
+    __syncthreads();
+    return total;
+}
+__global__ void __launch_bounds__(1024) k_dem_pbc(Elmt* __restrict__ e, uint32_t n, const __grid_constant__ Params p, Part* __restrict__ pt,
+                                                  const uint32_t* __restrict__ flag, int8_t* __restrict__ gflag, uint32_t* __restrict__ basePos,
+                                                  uint32_t* __restrict__ cornPos, uint32_t* __restrict__ comps, uint32_t* __restrict__ nComp,
+                                                  uint32_t* __restrict__ cnt) {
+    if (!*flag) return;
+    __shared__ uint32_t sm[1024];
+    const int nb = p.nPbc;
+    // pbcShift + the ghost test of every (boundary, element)
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        V3 x0 = v3(e[k].x[0]);
+        for (int b = 0; b < nb; ++b) {
+            const V3 nrm = v3(p.pbcN[b]), v = v3(p.pbcV[b]);
+            const double left = dot(nrm, x0 - v3(p.pbcP[b])), right = dot(-1.0 * nrm, x0 - (v3(p.pbcP[b]) + v));
+            if (left < 0.0) x0 = x0 + v;
+            if (right < 0.0) x0 = x0 + (-1.0 * v);
+        }
+        put(e[k].x[0], x0);
+        put(pt[k].xc, x0);
+        for (int b = 0; b < nb; ++b) {
+            const V3 nrm = v3(p.pbcN[b]), v = v3(p.pbcV[b]);
+            const double left = dot(nrm, x0 - v3(p.pbcP[b])), right = dot(-1.0 * nrm, x0 - (v3(p.pbcP[b]) + v));
+            const int8_t f = left < p.nebrRange ? 1 : (right < p.nebrRange ? -1 : 0);
+            gflag[(size_t)b * n + k] = f;
+            basePos[(size_t)b * n + k] = f ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    // corner ghosts: one per pair (g1 < g2) of base ghosts of the same particle, listed under g1
+    for (uint32_t q = threadIdx.x; q < (uint32_t)nb * n; q += blockDim.x) {
+        const uint32_t b1 = q / n, k = q % n;
+        uint32_t c = 0;
+        if (gflag[q]) for (int b2 = (int)b1 + 1; b2 < nb; ++b2) c += gflag[(size_t)b2 * n + k] ? 1u : 0u;
+        cornPos[q] = c;
+    }
+    __syncthreads();
+    const uint32_t nBase = block_excl_scan(basePos, (uint32_t)nb * n, sm);
+    const uint32_t nCorn = block_excl_scan(cornPos, (uint32_t)nb * n, sm);
+    // the ghosts themselves, and every element's component list: its particle, its base ghosts by boundary, its corner ghosts
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        const V3 x0 = v3(e[k].x[0]);
+        uint32_t nc = 0;
+        comps[(size_t)7 * k + nc++] = k;
+        for (int b = 0; b < nb; ++b) {
+            const int8_t f = gflag[(size_t)b * n + k];
+            if (!f) continue;
+            const uint32_t g = n + basePos[(size_t)b * n + k];
+            const V3 sh = f > 0 ? v3(p.pbcV[b]) : -1.0 * v3(p.pbcV[b]);
+            Part a = pt[k];
+            put(a.shift, sh); put(a.xc, x0 + sh); a.nearWall = -1;
+            pt[g] = a;
+            comps[(size_t)7 * k + nc++] = g;
+        }
+        for (int b1 = 0; b1 < nb; ++b1) {
+            const int8_t f1 = gflag[(size_t)b1 * n + k];
+            if (!f1) continue;
+            uint32_t r = 0;
+            for (int b2 = b1 + 1; b2 < nb; ++b2) {
+                const int8_t f2 = gflag[(size_t)b2 * n + k];
+                if (!f2) continue;
+                const uint32_t g = n + nBase + cornPos[(size_t)b1 * n + k] + r++;
+                const V3 s1 = f1 > 0 ? v3(p.pbcV[b1]) : -1.0 * v3(p.pbcV[b1]), s2 = f2 > 0 ? v3(p.pbcV[b2]) : -1.0 * v3(p.pbcV[b2]);
+                const V3 sh = s1 + s2;
+                Part a = pt[k];
+                put(a.shift, sh); put(a.xc, x0 + sh); a.nearWall = -1;
+                pt[g] = a;
+                comps[(size_t)7 * k + nc++] = g;
+            }
+        }
+        nComp[k] = nc;
+    }
+    if (threadIdx.x == 0) { cnt[0] = n + nBase + nCorn; cnt[1] = 1u; }
+}
+// particle::ghostUpdate (elmt.cpp:292-299): a ghost follows its origin.  PRED: the predicted state (for the contacts), else
+// the corrected one (for the lists of the LB side)
+template <bool PRED>
+__global__ void __launch_bounds__(128) k_dem_ghost_update(Part* __restrict__ pt, uint32_t nStd, const uint32_t* __restrict__ cnt) {
+    const uint32_t a = nStd + blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= cnt[0]) return;
+    const Part& o = pt[pt[a].cluster];  // single spheres: particle index = element index
+    const V3 sh = v3(pt[a].shift);
+    if (PRED) { put(pt[a].xp, v3(o.xp) + sh); put(pt[a].vp, v3(o.vp)); }
+    else put(pt[a].xc, v3(o.xc) + sh);
+}
 // particle::updateCorrected (elmt.cpp:277-290): the spheres of element el at its corrected state
 __device__ __forceinline__ void particles_corrected(const Params& p, const Elmt& el, Part* __restrict__ pt) {
     const V3 x0 = v3(el.x[0]);
@@ -524,6 +651,26 @@ __global__ void __launch_bounds__(128) k_dem_export(const Elmt* __restrict__ e, 
         for (int c = 0; c < 3; ++c) { op.x0[c] = pt[a].xc[c]; op.radiusVec[c] = pt[a].rvc[c]; }
         op.r = e[k].radius; op.clusterIndex = k; op.particleIndex = a;
         parts[a] = op; comps[a] = a;
+    }
+}
+
+// the same with periodic boundaries: the ghosts follow the standard particles in the list, an element's components are the
+// 7-slot rows k_dem_pbc filled
+__global__ void __launch_bounds__(128) k_dem_export_pbc(const Elmt* __restrict__ e, uint32_t n, const Part* __restrict__ pt, const uint32_t* __restrict__ cnt,
+                                                        const uint32_t* __restrict__ nComp, OutParticle* __restrict__ parts, OutElement* __restrict__ elmts) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < cnt[0]) {
+        const uint32_t k = (uint32_t)pt[a].cluster;
+        OutParticle op;
+        for (int c = 0; c < 3; ++c) { op.x0[c] = pt[a].xc[c]; op.radiusVec[c] = 0.0; }
+        op.r = e[k].radius; op.clusterIndex = k; op.particleIndex = a;
+        parts[a] = op;
+    }
+    if (a < n) {
+        OutElement oe;
+        for (int c = 0; c < 3; ++c) { oe.x1[c] = e[a].x[1][c]; oe.wGlobal[c] = e[a].w[0][c]; }
+        oe.compBegin = 7u * a; oe.compEnd = 7u * a + nComp[a];
+        elmts[a] = oe;
     }
 }
 

@@ -497,6 +497,12 @@ struct LbGpuHandle {
         uint32_t n = 0, nP = 0, nWalls = 0;  // elements, their particles (spheres), walls
         DevBuf<lbdem::Elmt> e;
         DevBuf<lbdem::Part> pt;
+        // periodic DEM boundaries (single spheres): ghost particles behind the standard ones in pt, rebuilt with the tables
+        bool pbc = false;
+        uint32_t cap = 0;  // particle slots: nP, or 7 per sphere with periodic boundaries (3 ghosts + 3 corner ghosts at most)
+        DevBuf<int8_t> gflag;
+        DevBuf<uint32_t> basePos, cornPos, nComp, cnt;  // cnt[0] = particles + ghosts, cnt[1] = a rebuild happened since the last coupling step
+        bool rescan = false;
         DevBuf<lbdem::Wall> walls;
         DevBuf<uint32_t> nbr, nNbr, flag;  // flag[0] = rebuild in this sub-step, [1] = longest partner list, [2] = rebuilds so far
         // uniform grid for the table rebuild of large beds (k_grid_*): LBGPU_DEM_GRID=0/1 overrides the choice by size
@@ -2359,7 +2365,7 @@ int run_cycles(LbGpuHandle* h, uint32_t count, bool fsCycle, int kind, Cycle&& c
     uint32_t k = 0;
     const bool coupled = h->nParts > 0;
     const bool graphable = h->graphAllowed && !h->phaseOn && (fsCycle || coupled) && (!h->fs || fsCycle) &&
-                           (!coupled || h->floodGens >= 2) && !lbcomm::active() && !h->dynWall && count >= 8;
+                           (!coupled || h->floodGens >= 2) && !lbcomm::active() && !h->dynWall && !(kind == 1 && h->dem.pbc) && count >= 8;
     if (graphable) {
         constexpr uint32_t TAIL = 2;
         for (; k < count && (h->steps < 2 || h->eagerCycles < 2); ++k) { if (int rc = cycle()) return rc; }
@@ -2437,27 +2443,46 @@ int dem_step(LbGpuHandle* h, const double* hydro) {
     static_assert(sizeof(lbdem::OutParticle) == sizeof(RawParticle) && sizeof(lbdem::OutElement) == sizeof(RawElement), "list layout");
     auto& D = h->dem;
     cudaStream_t st = h->stream;
-    const uint32_t n = D.n, nb = (n + 127) / 128, nP = D.nP, pb = (nP + 127) / 128;
+    const uint32_t n = D.n, nb = (n + 127) / 128, nP = D.nP, pb = (D.cap + 127) / 128;
+    const uint32_t* nPdev = D.pbc ? D.cnt.p : nullptr;  // with periodic boundaries the particle count lives on the device
     for (int sub = 0; sub < D.prm.multiStep; ++sub) {
         lbdem::k_dem_trigger<<<1, 1024, 0, st>>>(D.e.p, n, D.prm.deltat, D.prm.nebrRange, D.scal.p, D.flag.p);
+        if (D.pbc) {
+            lbdem::k_dem_pbc<<<1, 1024, 0, st>>>(D.e.p, n, D.prm, D.pt.p, D.flag.p, D.gflag.p, D.basePos.p, D.cornPos.p, h->comps.p, D.nComp.p, D.cnt.p);
+            ++h->launches;
+        }
         if (D.grid) {
-            lbdem::k_grid_bounds<<<1, 1024, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p);
-            lbdem::k_grid_count<<<pb, 128, 0, st>>>(D.pt.p, nP, D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellOf.p);
+            lbdem::k_grid_bounds<<<1, 1024, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p, nPdev);
+            lbdem::k_grid_count<<<pb, 128, 0, st>>>(D.pt.p, nP, D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellOf.p, nPdev);
             lbdem::k_grid_scan<<<1, 1024, 0, st>>>(D.flag.p, D.gridDesc.p, D.cellCount.p, D.cellFill.p);
-            lbdem::k_grid_fill<<<pb, 128, 0, st>>>(nP, D.flag.p, D.cellCount.p, D.cellFill.p, D.cellOf.p, D.sorted.p);
+            lbdem::k_grid_fill<<<pb, 128, 0, st>>>(nP, D.flag.p, D.cellCount.p, D.cellFill.p, D.cellOf.p, D.sorted.p, nPdev);
             lbdem::k_dem_neighbours_grid<<<pb, 128, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.gridDesc.p, D.cellCount.p, D.sorted.p, D.nbr.p, D.nNbr.p,
-                                                             D.flag.p + 1);
+                                                             D.flag.p + 1, nPdev);
             h->launches += 4;
         } else {
-            lbdem::k_dem_neighbours<<<pb, 128, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1);
+            lbdem::k_dem_neighbours<<<pb, 128, 0, st>>>(D.pt.p, nP, D.prm.nebrRange, D.flag.p, D.nbr.p, D.nNbr.p, D.flag.p + 1, nPdev);
         }
         lbdem::k_dem_predict<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.pt.p, D.walls.p, D.nWalls, D.flag.p);
+        if (D.pbc) { lbdem::k_dem_ghost_update<true><<<(D.cap - n + 127) / 128, 128, 0, st>>>(D.pt.p, n, D.cnt.p); ++h->launches; }
         lbdem::k_dem_forces_correct<<<nb, 128, 0, st>>>(D.e.p, n, D.prm, D.pt.p, D.walls.p, hydro, D.nbr.p, D.nNbr.p);
         h->launches += 4;
     }
+    if (D.pbc) {
+        lbdem::k_dem_ghost_update<false><<<(D.cap - n + 127) / 128, 128, 0, st>>>(D.pt.p, n, D.cnt.p);
+        lbdem::k_dem_export_pbc<<<pb, 128, 0, st>>>(D.e.p, n, D.pt.p, D.cnt.p, D.nComp.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p);
+        // the LB side needs the particle count (and whether to rescan) on the host: one small read-back per DEM step
+        CU(cudaMemcpyAsync(h->pinnedStatus + 512, D.cnt.p, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        h->nParts = h->pinnedStatus[512];
+        if (h->pinnedStatus[513]) { D.rescan = true; CU(cudaMemsetAsync(D.cnt.p + 1, 0, sizeof(uint32_t), st)); }
+        if (h->nParts > D.cap) return fail(LBGPU_EUNSUPPORTED, "DEM: %u particles and ghosts exceed the %u slots", h->nParts, D.cap);
+        k_prepare_particles<<<(std::max(h->nParts, n) + 127) / 128, 128, 0, st>>>(h->rawParts.p, h->nParts, h->rawElmts.p, n, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
+        h->launches += 3;
+    } else {
     lbdem::k_dem_export<<<nb, 128, 0, st>>>(D.e.p, n, D.pt.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
     k_prepare_particles<<<(std::max(nP, n) + 127) / 128, 128, 0, st>>>(h->rawParts.p, nP, h->rawElmts.p, n, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
     h->launches += 2;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -2497,6 +2522,17 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
                                   { -2.0 * s6 / 6.0, -2.0 * s2 / 6.0, -1.0 / 3.0 } };
         memcpy(P.proto[2], p2, sizeof p2); memcpy(P.proto[3], p3, sizeof p3); memcpy(P.proto[4], p4, sizeof p4);
     }
+    P.nPbc = prm->nPbc; P.padPbc = 0;
+    if (P.nPbc < 0 || P.nPbc > 3) return fail(LBGPU_EINVAL, "lbGpuDemInit: %d periodic boundaries (0-3)", P.nPbc);
+    for (int b = 0; b < P.nPbc; ++b) {
+        double nv = 0.0;
+        for (int q = 0; q < 3; ++q) { P.pbcP[b][q] = prm->pbcP[b][q]; P.pbcV[b][q] = prm->pbcV[b][q]; nv += prm->pbcV[b][q] * prm->pbcV[b][q]; }
+        nv = sqrt(nv);
+        if (!(nv > 0.0)) return fail(LBGPU_EINVAL, "lbGpuDemInit: periodic boundary %d has no translation vector", b);
+        for (int q = 0; q < 3; ++q) P.pbcN[b][q] = prm->pbcV[b][q] / nv;  // pbc::setPlanes
+    }
+    D.pbc = P.nPbc > 0;
+    D.rescan = false;
     std::vector<lbdem::Elmt> E(nElmts);
     memset(E.data(), 0, sizeof(lbdem::Elmt) * nElmts);
     std::vector<lbdem::Part> PT;
@@ -2512,6 +2548,7 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
         E[k].size = elmts[k].size > 0 ? elmts[k].size : 1;
         E[k].pBegin = (int)PT.size();
         if (E[k].size > 4) return fail(LBGPU_EINVAL, "lbGpuDemInit: element %u has %d spheres (DEM::compositeProperties knows 1-4)", k, E[k].size);
+        if (E[k].size > 1 && D.pbc) return fail(LBGPU_EUNSUPPORTED, "lbGpuDemInit: periodic DEM boundaries are covered for single spheres only (element %u has %d)", k, E[k].size);
         if (!(E[k].radius > 0.0) || !(E[k].m > 0.0)) return fail(LBGPU_EINVAL, "lbGpuDemInit: element %u has no radius or mass", k);
         for (int i = 0; i < E[k].size; ++i) {
             lbdem::Part a;
@@ -2521,30 +2558,45 @@ int lbGpuDemInit(LbGpuHandle* h, const LbGpuDemParams* prm, const LbGpuDemElemen
         }
     }
     const uint32_t nP = (uint32_t)PT.size();
-    CU(D.e.alloc(nElmts)); CU(D.pt.alloc(nP)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)nP * lbdem::MAX_NBR)); CU(D.nNbr.alloc(nP));
+    D.cap = D.pbc ? 7u * nP : nP;
+    PT.resize(D.cap, PT.empty() ? lbdem::Part() : PT[0]);
+    CU(D.e.alloc(nElmts)); CU(D.pt.alloc(D.cap)); CU(D.walls.alloc(nWalls ? nWalls : 1)); CU(D.nbr.alloc((size_t)D.cap * lbdem::MAX_NBR)); CU(D.nNbr.alloc(D.cap));
+    if (D.pbc) {
+        CU(D.gflag.alloc((size_t)3 * nElmts)); CU(D.basePos.alloc((size_t)3 * nElmts)); CU(D.cornPos.alloc((size_t)3 * nElmts)); CU(D.nComp.alloc(nElmts)); CU(D.cnt.alloc(4));
+    }
     CU(D.flag.alloc(4)); CU(D.scal.alloc(2)); CU(D.hydro.alloc((size_t)7 * nElmts));
-    D.grid = nP >= 4096;  // below that the all-pairs pass (one launch) is as fast as the five launches of the grid
+    D.grid = D.cap >= 4096;  // below that the all-pairs pass (one launch) is as fast as the five launches of the grid
     if (const char* e = getenv("LBGPU_DEM_GRID")) D.grid = atoi(e) != 0;
     if (D.grid) {
         CU(D.gridDesc.alloc(1)); CU(D.cellCount.alloc(lbdem::GRID_MAX_CELLS + 2)); CU(D.cellFill.alloc(lbdem::GRID_MAX_CELLS + 2));
-        CU(D.cellOf.alloc(nP)); CU(D.sorted.alloc(nP));
+        CU(D.cellOf.alloc(D.cap)); CU(D.sorted.alloc(D.cap));
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaMemcpy(D.e.p, E.data(), sizeof(lbdem::Elmt) * nElmts, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(D.pt.p, PT.data(), sizeof(lbdem::Part) * nP, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(D.pt.p, PT.data(), sizeof(lbdem::Part) * D.cap, cudaMemcpyHostToDevice));
     if (nWalls) CU(cudaMemcpy(D.walls.p, walls, sizeof(lbdem::Wall) * nWalls, cudaMemcpyHostToDevice));
-    CU(cudaMemset(D.nNbr.p, 0, sizeof(uint32_t) * nP));
+    CU(cudaMemset(D.nNbr.p, 0, sizeof(uint32_t) * D.cap));
     CU(cudaMemset(D.flag.p, 0, sizeof(uint32_t) * 4));
     const double sc[2] = { prm->maxDisp, 0.0 };
     CU(cudaMemcpy(D.scal.p, sc, sizeof sc, cudaMemcpyHostToDevice));
     CU(cudaDeviceSynchronize());  // the copies ran on the legacy stream (see lbGpuSetCurves)
     D.n = nElmts; D.nP = nP; D.nWalls = nWalls; D.on = true;
-    // the resident lists of the coupling step: the particles of every element
-    if (int rc = particle_capacity(h, nP, nElmts, nP)) return rc;
-    h->nParts = nP; h->nElmts = nElmts; h->nComps = nP;
+    // the resident lists of the coupling step: the particles of every element (+ the ghost slots: 7 components per sphere)
+    if (int rc = particle_capacity(h, D.cap, nElmts, D.cap)) return rc;
+    h->nParts = nP; h->nElmts = nElmts; h->nComps = D.cap;
+    if (D.pbc) {  // until the first rebuild (the first sub-step): no ghosts
+        std::vector<uint32_t> comps0((size_t)D.cap, 0u), one(nElmts, 1u);
+        for (uint32_t k = 0; k < nElmts; ++k) comps0[(size_t)7 * k] = k;
+        const uint32_t c0[4] = { nP, 0u, 0u, 0u };
+        CU(cudaMemcpy(h->comps.p, comps0.data(), sizeof(uint32_t) * D.cap, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(D.nComp.p, one.data(), sizeof(uint32_t) * nElmts, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(D.cnt.p, c0, sizeof c0, cudaMemcpyHostToDevice));
+        CU(cudaDeviceSynchronize());
+    }
     const uint32_t nb = (nElmts + 127) / 128;
     lbdem::k_dem_init_particles<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, D.prm, D.pt.p);
-    lbdem::k_dem_export<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, D.pt.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
+    if (D.pbc) lbdem::k_dem_export_pbc<<<(D.cap + 127) / 128, 128, 0, h->stream>>>(D.e.p, nElmts, D.pt.p, D.cnt.p, D.nComp.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p);
+    else lbdem::k_dem_export<<<nb, 128, 0, h->stream>>>(D.e.p, nElmts, D.pt.p, (lbdem::OutParticle*)h->rawParts.p, (lbdem::OutElement*)h->rawElmts.p, h->comps.p);
     k_prepare_particles<<<(std::max(nP, nElmts) + 127) / 128, 128, 0, h->stream>>>(h->rawParts.p, nP, h->rawElmts.p, nElmts, h->uLength, h->uSpeed, h->parts.p, h->elmts.p);
     h->launches += 3;
     CU(cudaGetLastError());
@@ -2576,7 +2628,10 @@ int lbGpuRunDem(LbGpuHandle* h, int doFreeSurface, uint32_t count) {
         if ((rc = dem_step(h, (h->lastStepCoupled || h->capturing) ? h->slabs[0]->elemOut.p : nullptr))) return rc;
         phase_mark(h, 1);
         if (doFreeSurface && h->fs) { if ((rc = free_surface_step(h))) return rc; } else { phase_mark(h, 2); phase_mark(h, 3); }
-        if ((rc = coupling_step(h, false))) return rc;  // dem.newNeighborList is only raised with periodic DEM boundaries (DEM.cpp:1414)
+        // dem.newNeighborList: raised by a rebuild of the tables with periodic DEM boundaries (DEM.cpp:1414), reset by the coupling step
+        const bool rescan = h->dem.rescan;
+        h->dem.rescan = false;
+        if ((rc = coupling_step(h, rescan))) return rc;
         phase_mark(h, 4);
         return lb_step(h);
     };
@@ -2610,12 +2665,13 @@ int lbGpuDemParticles(LbGpuHandle* h, uint32_t* nParticles, double* x0, double* 
     if (!h || !h->dem.on) return fail(LBGPU_EINVAL, "lbGpuDemParticles: no device-side DEM on this handle (lbGpuDemInit)");
     CU(cudaSetDevice(h->device));
     auto& D = h->dem;
-    if (nParticles) *nParticles = D.nP;
+    const uint32_t nNow = D.pbc ? h->nParts : D.nP;  // with periodic boundaries: the ghosts of the last rebuild included
+    if (nParticles) *nParticles = nNow;
     if (!x0 && !radiusVec && !clusterIndex) return LBGPU_OK;
-    std::vector<lbdem::Part> PT(D.nP);
+    std::vector<lbdem::Part> PT(nNow);
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaMemcpy(PT.data(), D.pt.p, sizeof(lbdem::Part) * D.nP, cudaMemcpyDeviceToHost));
-    for (uint32_t a = 0; a < D.nP; ++a) {
+    CU(cudaMemcpy(PT.data(), D.pt.p, sizeof(lbdem::Part) * nNow, cudaMemcpyDeviceToHost));
+    for (uint32_t a = 0; a < nNow; ++a) {
         for (int q = 0; q < 3; ++q) { if (x0) x0[3 * a + q] = PT[a].xc[q]; if (radiusVec) radiusVec[3 * a + q] = PT[a].rvc[q]; }
         if (clusterIndex) clusterIndex[a] = (uint32_t)PT[a].cluster;
     }
@@ -3142,8 +3198,8 @@ int visit_state(LbGpuHandle* h, F&& fn) {
     if (h->nComps && (rc = fn((void*)h->comps.p, sizeof(uint32_t) * h->nComps))) return rc;
     if (h->dem.on) {  // the elements' Gear state and tables (the handle the blob is loaded into went through lbGpuDemInit)
         auto& D = h->dem;
-        if ((rc = fn((void*)D.e.p, sizeof(lbdem::Elmt) * D.n)) || (rc = fn((void*)D.pt.p, sizeof(lbdem::Part) * D.nP)) ||
-            (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) || (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.nP)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
+        if ((rc = fn((void*)D.e.p, sizeof(lbdem::Elmt) * D.n)) || (rc = fn((void*)D.pt.p, sizeof(lbdem::Part) * D.cap)) ||
+            (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) || (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.cap)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
             (rc = fn((void*)D.scal.p, sizeof(double) * 2)))
             return rc;
     }

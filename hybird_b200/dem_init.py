@@ -4,7 +4,7 @@ single-sphere elements (DEM.cpp:13-83, 186-296, 435-640, 1270-1312; elmt.cpp:13-
 the lattice boundaries.  Same expressions in the same order as the reference (checked number by number against the values
 the unmodified reference holds after its own initialisation, tests/test_dem_port.py).  Periodic pairs of lattice boundaries make
 periodic DEM boundaries (DEM::initializePbcs, DEM.cpp:937-988; listed under `pbcs` for completeness), whose ghost particles the
-device-side DEM does not build: `covered` says so and `LB.demInit` refuses them."""
+device-side DEM builds for single spheres."""
 from __future__ import annotations
 
 import math
@@ -13,11 +13,15 @@ from . import lattice_init as li
 
 
 def covered(case: dict, params: dict) -> bool:
-    """True when the device-side DEM (lbGpuDem*) covers this case: spheres and clusters of 2-4 spheres, no periodic boundary
-    (periodic DEM boundaries mean ghost particles, DEM.cpp:1586-1660, which the device does not build), box geometry, an imposed
-    number of sub-steps."""
-    return (all(1 <= int(e["size"]) <= 4 for e in case.get("elements", [])) and len(case.get("elements", [])) > 0 and
-            all(b != 4 for b in params["boundary"]) and case.get("problemName", "NONE") == "NONE" and int(case.get("multiStep", 1)) > 0 and
+    """True when the device-side DEM (lbGpuDem*) covers this case: spheres and clusters of 2-4 spheres between plane walls,
+    periodic pairs of boundaries for single spheres (ghost particles, DEM.cpp:1586-1660), box geometry, an imposed number of
+    sub-steps."""
+    b = params["boundary"]
+    els = case.get("elements", [])
+    periodic = any(v == 4 for v in b)
+    return (len(els) > 0 and all(1 <= int(e["size"]) <= 4 for e in els) and (not periodic or all(int(e["size"]) == 1 for e in els)) and
+            all((b[2 * a] == 4) == (b[2 * a + 1] == 4) for a in range(3)) and
+            case.get("problemName", "NONE") == "NONE" and int(case.get("multiStep", 1)) > 0 and
             float(case.get("demInitialRepeat", 0.0)) == 0.0)
 
 
@@ -35,8 +39,8 @@ def prototypes():
 def dem_from_case(case: dict, params: dict | None = None) -> dict:
     prm = params or li.params_from_case(case)
     if not covered(case, prm):
-        raise ValueError("dem_from_case: the device-side DEM covers spheres / clusters of 2-4 spheres in a box without periodic "
-                         "boundaries and an imposed multiStep only")
+        raise ValueError("dem_from_case: the device-side DEM covers spheres / clusters of 2-4 spheres in a box (periodic pairs of "
+                         "boundaries: spheres only) with an imposed multiStep")
     L, T, D = prm["unitLength"], prm["unitTime"], prm["unitDensity"]
     accel = L / T / T
     # material (DEM.cpp:13-62); the HERTZIAN case of the switch falls through into LINEAR's damping coefficient

@@ -159,10 +159,15 @@ class LB:
         DEM::discreteElementInit left: sphereMat constants, deltat, multiStep, nebrRange, maxDisp; per element x0, x1, w0,
         radius, m, I; per wall n, p, vel, omega, rotCenter, moving) -- physical units."""
         p = dem["params"]
-        if dem.get("pbcs"):
-            raise ValueError("demInit: periodic DEM boundaries (ghost particles) are not covered by the device-side DEM; keep the host DEM "
-                             "and latticeBoltzmannCouplingStep / latticeBolzmannStep")
+        pbcs = dem.get("pbcs") or []
+        if pbcs and any(int(e.get("size", 1)) != 1 for e in dem["elmts"]):
+            raise ValueError("demInit: periodic DEM boundaries are covered for single spheres only; keep the host DEM and "
+                             "latticeBoltzmannCouplingStep / latticeBolzmannStep")
         P = abi.LbGpuDemParams()
+        P.nPbc = len(pbcs)
+        for b, pb in enumerate(pbcs):
+            for q in range(3):
+                P.pbcP[b][q] = float(pb["p"][q]); P.pbcV[b][q] = float(pb["v"][q])
         P.contactModel = int(p["contactModel"]); P.multiStep = int(p["multiStep"])
         for k in ("knConst", "ksConst", "dampCoeff", "viscTang", "linearStiff", "frictionCoefPart", "frictionCoefWall", "numVisc",
                   "deltat", "nebrRange", "maxDisp"):
@@ -182,7 +187,7 @@ class LB:
             W[k]["moving"] = int(w["moving"])
         abi.check(self.lib.lbGpuDemInit(self.h, C.byref(P), abi.ptr(E), len(E), abi.ptr(W) if len(W) else None, len(W)))
         self._dem_n = len(E)
-        nP = int(E["size"].sum())
+        nP = int(E["size"].sum()) * (7 if pbcs else 1)
         self._last = (np.zeros(nP, abi_particle_dtype()), np.zeros(len(E), abi_element_dtype()), np.arange(nP, dtype=np.uint32))
         return self
 

@@ -161,8 +161,10 @@ int lbGpuRun(LbGpuHandle* h, int doFreeSurface, uint32_t count);
  * 5th-order Gear predictor / corrector (elmt.cpp:139-254), LINEAR / HERTZIAN particle-particle and particle-wall contacts
  * (DEM.cpp:1668-1717, 1801-1982, 2138-2224), Newton's equations with the hydrodynamic force and torque of the last LB step
  * (DEM.cpp:1150-1181).  The particle / element lists of the coupling step and of LB::computeHydroForces are refreshed on
- * the device, so a coupled cycle has no host round trip.  Elements are single spheres or clusters of 2-4 spheres.  Not
- * covered: periodic DEM boundaries (ghost particles), cylinders, objects -- those keep the host DEM and lbGpuStep.  All values in physical units, as the
+ * the device, so a coupled cycle has no host round trip.  Elements are single spheres or clusters of 2-4 spheres; with
+ * periodic DEM boundaries (single spheres) the ghost particles of DEM::createGhosts are rebuilt with the tables, the coupling
+ * step rescans after a rebuild as dem.newNeighborList asks (DEM.cpp:1414), and the host reads the particle count back once
+ * per DEM step.  Not covered: cylinders, objects -- those keep the host DEM and lbGpuStep.  All values in physical units, as the
  * reference's DEM holds them.  With a communicator every rank advances the same (replicated) elements.
  *   contactModel  0 LINEAR, 1 HERTZIAN (material::contactModel, DEM.cpp:150-158)
  *   deltat, multiStep, nebrRange, maxDisp: DEM::deltat / multiStep / nebrRange / maxDisp after DEM::discreteElementInit */
@@ -170,6 +172,9 @@ typedef struct {
     int32_t contactModel, multiStep;
     double knConst, ksConst, dampCoeff, viscTang, linearStiff, frictionCoefPart, frictionCoefWall, numVisc;
     double demF[3], deltat, nebrRange, maxDisp;
+    /* periodic DEM boundaries (DEM::initializePbcs, DEM.cpp:937-988): pbc::p and pbc::v of each; single spheres only */
+    int32_t nPbc, pad;
+    double pbcP[3][3], pbcV[3][3];
 } LbGpuDemParams;
 typedef struct { double x0[3], x1[3], w0[3], radius, m, I[3]; int32_t size, pad; } LbGpuDemElement;
 /* elmt::x0, x1, w0, radius, m, I, size (elmt.h:60-110).  size 1: a sphere; 2-4: the reference's clusters (DEM::compositeProperties,

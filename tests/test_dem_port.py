@@ -9,6 +9,7 @@ import golden_util as gu
 
 DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
 CLUSTER_CASES = ("cluster_dem", "clusters_hit")
+PBC_CASES = ("spheres_pbc_dem",)
 
 
 @pytest.mark.parametrize("name", DEM_CASES)
@@ -32,7 +33,7 @@ def test_dem_port_follows_reference_trace(name):
         assert P.rebuilds >= 4  # the table is rebuilt several times and pairs enter / leave it
 
 
-@pytest.mark.parametrize("name", DEM_CASES + CLUSTER_CASES)
+@pytest.mark.parametrize("name", DEM_CASES + CLUSTER_CASES + PBC_CASES)
 def test_host_mirror_of_the_dem_initialisation(name):
     """hybird_b200.dem_init restates what DEM::discreteElementGet / discreteElementInit derive (material constants, sub-step,
     neighbour-table range, masses, inertias, walls): number by number what the unmodified reference held after its init."""
@@ -51,14 +52,15 @@ def test_host_mirror_of_the_dem_initialisation(name):
     for a, b in zip(mine["walls"], ref["walls"]):
         for k in ("n", "p", "vel", "omega", "rotCenter", "moving"):
             assert a[k] == b[k], k
+    assert mine["pbcs"] == ref["pbcs"]
 
 
 def test_dem_init_refuses_what_the_device_does_not_cover():
     import cases
     from hybird_b200 import dem_init
-    for name in ("two_spheres_kin", "spheres_pbc_dem"):  # periodic boundaries (ghost particles)
-        with pytest.raises(ValueError):
-            dem_init.dem_from_case(cases.catalogue()[name])
+    case = dict(cases.catalogue()["cluster_dem"], boundary0=4, boundary1=4)  # clusters with periodic boundaries
+    with pytest.raises(ValueError):
+        dem_init.dem_from_case(case)
 
 
 def test_lb_mirror_refuses_unknown_shapes_and_periodic_dem_before_touching_the_device():
@@ -72,6 +74,7 @@ def test_lb_mirror_refuses_unknown_shapes_and_periodic_dem_before_touching_the_d
         lb.demInit(dem)
     dem = gu.Golden("spheres_pbc_dem").dem()
     assert len(dem["pbcs"]) == 2
+    dem["elmts"][1]["size"] = 2  # periodic DEM boundaries are covered for single spheres only
     with pytest.raises(ValueError, match="periodic DEM boundaries"):
         lb.demInit(dem)
 

@@ -160,6 +160,32 @@ def test_cfg3_at_full_size_with_the_dem_on_the_device():
     lb.close()
 
 
+def test_periodic_dem_boundaries_on_the_device():
+    """Ghost particles on the device (pbcShift, createGhosts incl. the corner ghost, contacts across a periodic face, a rescan of
+    the particle flags after every rebuild): the particle list handed to the LB side -- count, elements, positions of
+    particles and ghosts -- the cell-type / particle-flag map and the forces against the reference, every cycle."""
+    g = gu.Golden("spheres_pbc_dem")
+    lb = _gpu(g)
+    worst_x = worst_f = 0.0
+    counts = set()
+    for s in range(1, g.steps + 1):
+        parts, elmts, comps, flag = g.trace[s - 1]
+        lb.runDem(1)
+        worst_x = max(worst_x, _worst(lb, parts, elmts))
+        counts.add(len(parts))
+        t = lb.fetch(("type_flags", "solidIndex"))
+        assert np.array_equal(t["type_flags"] & 0x1F, g.types[s]), "type / particle-flag map differs from the reference after step %d" % s
+        F, M, V, W = lb.forces()
+        rF, rM, rV, rW = g.forces[s - 1]
+        arm = float(parts["r"].max()); fmax = float(np.abs(rF).max())
+        for a, b, floor in ((F, rF, 0.0), (M, rM, fmax * arm), (V, rV, 0.0)):
+            worst_f = max(worst_f, np.abs(a - b).max() / max(np.abs(b).max(), floor, 1e-300))
+    assert lb.demState()["rebuilds"] >= 4 and len(counts) >= 2
+    assert worst_x <= TOL_COUPLED and worst_f <= TOL_COUPLED, (worst_x, worst_f)
+    print("spheres_pbc_dem: trajectories (particles and ghosts) %.2e, forces %.2e" % (worst_x, worst_f))
+    lb.close()
+
+
 def _coupled(g, n_slabs, steps):
     from hybird_b200 import LB
     prm = dict(g.params)
