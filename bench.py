@@ -113,7 +113,9 @@ def workload_label(name, n_slabs=1):
             "cfg3": "cfg3: single sphere r=8 in a 128x128x256 no-slip box, particle coupling + force reduction",
             "cfg4": "cfg4: free-surface dam break 512x128x256, Bingham rheology",
             "cfg5": "cfg5: debris flow, 20000 spheres in a 1024x256x256 free-surface fluid (long axis stored as z), "
-                    "%d z-slab(s)" % n_slabs}.get(name, name)
+                    "%d z-slab(s)" % n_slabs,
+            "cfg5_dem": "cfg5 with the DEM in the loop on the device: 20000 spheres advanced every cycle (contacts, ghost particles "
+                        "of the periodic y faces), %d z-slab(s)" % n_slabs}.get(name, name)
 
 
 def workload_case(name, n_slabs=1):
@@ -337,7 +339,13 @@ def main_ours(args, rank, world, local_rank):
     h2d = int(parts.nbytes + elmts.nbytes + comps.nbytes)
     d2h = int(8 * (7 * len(elmts) + 3 * lb.nWalls))
     x0_elmt = parts["x0"].copy() if len(parts) else None
+    dem_on_device = str(info.get("dem", "")).startswith("device")
+    if dem_on_device:
+        h2d = 0  # the particles never leave the device; the forces still come back every cycle
     def e2e_step():
+        if dem_on_device:  # the DEM step, the coupling step and the LB step of one cycle, then the forces on the host
+            lb.runDem(1)
+            return lb.forces()
         if fs:
             lb.latticeBoltzmannFreeSurfaceStep()
         if len(parts):
@@ -388,7 +396,14 @@ def main_ours(args, rank, world, local_rank):
         lbj = LB(host_params, device=local_rank)
         lbj.latticeBolzmannInit(*host_arrays)
         t_up = time.perf_counter() - tj
+        if dem_on_device:
+            from hybird_b200 import dem_init as _di
+            lbj.demInit(_di.dem_from_case(case, host_params))
         for k in range(Kj):
+            if dem_on_device:  # one cycle with the DEM on the device, the forces back on the host
+                lbj.runDem(1)
+                lbj.forces()
+                continue
             if fs:
                 lbj.latticeBoltzmannFreeSurfaceStep()
             if len(pj):
@@ -436,7 +451,7 @@ def main_ours(args, rank, world, local_rank):
     # ---- the other configurations, device-resident, so that they are measured by the same driver run ----
     extra = {}
     if args.workload == "cfg2" and not args.no_extra:
-        for nm in (("cfg1", "cfg3", "cfg4", "cfg5") if world == 1 else ("cfg5",)):
+        for nm in (("cfg1", "cfg3", "cfg4", "cfg5", "cfg5_dem") if world == 1 else ("cfg5",)):
             try:
                 Kx = min(K, 100)
                 lbx, infx, rx = resident_run(nm, args, rank, world, local_rank, dist, Kx, W, False)
@@ -499,7 +514,7 @@ def main_ours(args, rank, world, local_rank):
         "e2e": {"value": job_mlups, "unit": "MLUPS", "kind": e2e_kind,
                 "h2d_bytes_per_step": int(h2d + upload_bytes / Kj), "d2h_bytes_per_step": int(d2h + fetch_bytes / Kj),
                 "steps": Kj,
-                "call": "lbGpuInit(host arrays) + %d x [lbGpuStep(host particle/element arrays) + lbGpuParticleForces(host)] + "
+                "call": ("lbGpuInit(host arrays) + lbGpuDemInit + %d x [lbGpuRunDem(1) + lbGpuParticleForces(host)] + lbGpuFetchFields(host arrays)" % Kj) if dem_on_device else "lbGpuInit(host arrays) + %d x [lbGpuStep(host particle/element arrays) + lbGpuParticleForces(host)] + "
                         "lbGpuFetchFields(host arrays)" % Kj,
                 "step_value": e2e_mlups, "step_h2d_bytes": h2d, "step_d2h_bytes": d2h, "step_steps": Ke,
                 "init_upload_bytes": upload_bytes, "fetch_fields_bytes": fetch_bytes,

@@ -251,16 +251,29 @@ def neighbor_table(size, boundary):
 
 
 def expand_elements(elements, unit_length=1.0):
-    """Particles/elements for single-sphere elements (elmt::generateParticles, elmt.cpp:122-137)."""
+    """Particles / elements as elmt::generateParticles leaves them (elmt.cpp:122-137): a sphere per element, or the 2-4
+    spheres of a cluster at x0 + r * prototype (DEM::compositeProperties, DEM.cpp:404-433; the orientation of a fresh run is the
+    identity, so project(prototype, q0) is the prototype itself)."""
+    from .dem_init import prototypes
+    protos = prototypes()
     nE = len(elements)
-    parts = np.zeros(nE, PARTICLE_DTYPE)
+    nP = sum(int(el.get("size", 1)) for el in elements)
+    parts = np.zeros(nP, PARTICLE_DTYPE)
     elmts = np.zeros(nE, ELEMENT_DTYPE)
+    a = 0
     for e, el in enumerate(elements):
-        if int(el.get("size", 1)) != 1:
-            raise ValueError("expand_elements handles single-sphere elements; clusters come from a DEM trace")
-        parts[e]["x0"] = el["x0"]; parts[e]["r"] = el["radius"]; parts[e]["clusterIndex"] = e; parts[e]["particleIndex"] = e
-        elmts[e]["x1"] = el["x1"]; elmts[e]["wGlobal"] = el["w"]; elmts[e]["compBegin"] = e; elmts[e]["compEnd"] = e + 1
-    return parts, elmts, np.arange(nE, dtype=np.uint32)
+        size = int(el.get("size", 1))
+        elmts[e]["x1"] = el["x1"]; elmts[e]["wGlobal"] = el["w"]; elmts[e]["compBegin"] = a
+        for i in range(size):
+            x0 = np.array(el["x0"], dtype=np.float64)
+            if size > 1:
+                xa = x0 + float(el["radius"]) * np.array(protos[size][i], dtype=np.float64)
+                parts[a]["radiusVec"] = xa - x0
+                x0 = xa
+            parts[a]["x0"] = x0; parts[a]["r"] = el["radius"]; parts[a]["clusterIndex"] = e; parts[a]["particleIndex"] = a
+            a += 1
+        elmts[e]["compEnd"] = a
+    return parts, elmts, np.arange(nP, dtype=np.uint32)
 
 
 def advance_kinematic(parts, elmts, x0_elmt, dt):

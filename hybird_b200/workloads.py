@@ -218,6 +218,10 @@ def catalogue():
         "cfg5", lbSizeX=256, lbSizeY=256, lbSizeZ=1024, boundary2=4, boundary3=4, freeSurfaceSolve=1, lbFX=-1e-4,
         lbFZ=3e-5, initVisc=0.05, fluid_box=(0, 160, 0, 255, 0, 1023), motion="kin", rescan_every=0,
         elements_gen=(20000, (1.0, 1.0, 1.0), (160.0, 255.0, 1023.0), 3.0, 4.0, 12345, [-0.01, 0.0, 0.02]))
+    # cfg 5 as the reference would run it: the DEM advances the 20 000 spheres every cycle (contacts, periodic y with ghost
+    # particles, walls in x and z) -- on the device through lbGpuRunDem
+    C["cfg5_dem"] = dict(C["cfg5"], name="cfg5_dem", motion="dem")
+    C["cfg5_mini_dem"] = dict(copy.deepcopy(C["cfg5_mini"]), name="cfg5_mini_dem", motion="dem", rescan_every=0)
     return C
 
 

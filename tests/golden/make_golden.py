@@ -44,7 +44,7 @@ STEPS = {
     "cfg1_mini": 100, "cfg5_mini": 100,
     "drum_mini": 300, "drum_bingham": 200,
     # DEM in the loop (contacts, table rebuilds): the fixtures also carry what DEM::discreteElementInit left (`dem`)
-    "spheres_dem": 120, "spheres_hertz": 120, "bed_dem": 200, "spheres_pbc_dem": 160, "clusters_hit": 120,
+    "spheres_dem": 120, "spheres_hertz": 120, "bed_dem": 200, "spheres_pbc_dem": 160, "clusters_hit": 120, "cfg5_mini_dem": 100,
 }
 
 

@@ -9,7 +9,7 @@ import golden_util as gu
 
 DEM_CASES = ("spheres_dem", "spheres_hertz", "bed_dem", "cfg3_mini")
 CLUSTER_CASES = ("cluster_dem", "clusters_hit")
-PBC_CASES = ("spheres_pbc_dem",)
+PBC_CASES = ("spheres_pbc_dem", "cfg5_mini_dem")
 
 
 @pytest.mark.parametrize("name", DEM_CASES)
@@ -100,12 +100,13 @@ def test_cluster_port_follows_reference_trace(name):
     assert worst <= 1e-12, worst
 
 
-def test_periodic_port_follows_reference_trace():
+@pytest.mark.parametrize("name", ["spheres_pbc_dem", "cfg5_mini_dem"])
+def test_periodic_port_follows_reference_trace(name):
     """Periodic DEM boundaries (pbcShift, ghost particles incl. the corner ghost, table over particles and ghosts, contacts
     across a periodic face): the particle list the LB side receives -- positions of particles and ghosts, their elements, the
     elements' component lists, the rescan flag -- against the reference's recording, every LB step."""
     import dem_port
-    g = gu.Golden("spheres_pbc_dem")
+    g = gu.Golden(name)
     dem = g.dem()
     P = dem_port.DemPortPbc(dem)
     n = len(dem["elmts"])
@@ -120,4 +121,6 @@ def test_periodic_port_follows_reference_trace():
         worst = max(worst, np.abs(x0 - parts["x0"]).max(), np.abs(x1 - elmts["x1"]).max(), np.abs(wg - elmts["wGlobal"]).max())
         counts.add(len(parts))
         F, M = g.forces[s][0], g.forces[s][1]
-    assert worst <= 1e-12 and P.rebuilds >= 4 and len(counts) >= 2, (worst, P.rebuilds, counts)
+    assert worst <= 1e-12, worst
+    if name == "spheres_pbc_dem":
+        assert P.rebuilds >= 4 and len(counts) >= 2, (P.rebuilds, counts)

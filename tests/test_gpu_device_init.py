@@ -16,7 +16,7 @@ import cases  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 # multi-sphere elements need the DEM's generateParticles; the DRUM geometry is set up by the reference's host code
-NAMES = [n for n in gu.names() if n != "cluster_dem" and not n.startswith("drum")]
+NAMES = [n for n in gu.names() if not n.startswith("drum")]
 
 
 def _pair(name, n_slabs=1):

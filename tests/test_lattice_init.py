@@ -14,7 +14,7 @@ sys.path.insert(0, os.path.join(common.ROOT, "oracle"))
 import cases  # noqa: E402
 
 # multi-sphere elements need the DEM's generateParticles; the DRUM geometry (cylinder) is set up by the reference's host code
-NAMES = [n for n in gu.names() if n != "cluster_dem" and not n.startswith("drum")]
+NAMES = [n for n in gu.names() if not n.startswith("drum")]
 
 
 @pytest.mark.parametrize("name", NAMES)
