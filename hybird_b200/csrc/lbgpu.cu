@@ -3202,6 +3202,7 @@ int visit_state(LbGpuHandle* h, F&& fn) {
             (rc = fn((void*)D.nbr.p, sizeof(uint32_t) * D.nbr.n)) || (rc = fn((void*)D.nNbr.p, sizeof(uint32_t) * D.cap)) || (rc = fn((void*)D.flag.p, sizeof(uint32_t) * 4)) ||
             (rc = fn((void*)D.scal.p, sizeof(double) * 2)))
             return rc;
+        if (D.pbc && ((rc = fn((void*)D.cnt.p, sizeof(uint32_t) * 4)) || (rc = fn((void*)D.nComp.p, sizeof(uint32_t) * D.n)))) return rc;  // ghosts of the last rebuild
     }
     return 0;
 }

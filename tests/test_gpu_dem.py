@@ -80,8 +80,9 @@ def test_coupled_cycle_on_device_matches_reference(name):
     lb.close()
 
 
-def test_run_dem_equals_single_cycles_and_restart():
-    g = gu.Golden("bed_dem")
+@pytest.mark.parametrize("name", ["bed_dem", "spheres_pbc_dem"])
+def test_run_dem_equals_single_cycles_and_restart(name):
+    g = gu.Golden(name)
     a, b, c = _gpu(g), _gpu(g), _gpu(g)
     a.runDem(60)
     for _ in range(60):
