@@ -51,7 +51,8 @@ if "--dem" in sys.argv:
         F, M, V, W = lb.forces()
         Fs.append(F.copy()); Ms.append(M.copy())
     st = lb.demState()
-    extra = dict(dem_x0=st["x0"], dem_x1=st["x1"], dem_w0=st["w0"])
+    pt = lb.demParticles()
+    extra = dict(dem_x0=st["x0"], dem_x1=st["x1"], dem_w0=st["w0"], dem_px0=pt["x0"], dem_pcluster=pt["clusterIndex"])
 else:
     for s, F, M, V, W in gu.replay(g, lb, None):
         Fs.append(F.copy()); Ms.append(M.copy())

@@ -210,7 +210,10 @@ def test_coupled_cycle_on_slabs_of_one_device():
     assert np.abs(F1[0] - F3[0]).max() <= TOL_COUPLED * np.abs(F1[0]).max()
 
 
-def test_coupled_cycle_on_two_gpus(tmp_path):
+@pytest.mark.parametrize("name", ["bed_dem", "cfg5_mini_dem"])
+def test_coupled_cycle_on_two_gpus(name, tmp_path):
+    """Two ranks, each advancing the same elements from the all-reduced forces (cfg5_mini_dem: with a free surface and the ghost
+    particles of the periodic y faces, every rank reading its own particle count back)."""
     import os, subprocess, sys
     import torch
     import common
@@ -218,18 +221,19 @@ def test_coupled_cycle_on_two_gpus(tmp_path):
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     out = tmp_path / "ranks.npz"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29900 + os.getpid() % 90), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), "bed_dem", str(out), "--dem"]
+           "--master-port", str(29900 + os.getpid() % 90), os.path.join(common.ROOT, "tests", "run_slab_ranks.py"), name, str(out), "--dem"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     z = np.load(out)
-    g = gu.Golden("bed_dem")
+    g = gu.Golden(name)
     s1, f1, F1 = _coupled(g, 1, int(z["steps"]))
     assert np.array_equal(z["type_flags"], f1["type_flags"])
     for k in ("x0", "x1", "w0"):
         assert np.abs(z["dem_" + k] - s1[k]).max() <= TOL_COUPLED, k
-    # ... and both follow the reference's recorded trajectory
+    # ... and both follow the reference's recorded trajectory (ghost particles included)
     parts, elmts, comps, flag = g.trace[int(z["steps"]) - 1]
-    assert np.abs(z["dem_x0"] - parts["x0"]).max() <= TOL_COUPLED
+    assert len(z["dem_px0"]) == len(parts) and np.array_equal(z["dem_pcluster"], parts["clusterIndex"])
+    assert np.abs(z["dem_px0"] - parts["x0"]).max() <= TOL_COUPLED
 
 
 def _bed(n, seed=4321):
